@@ -1,0 +1,169 @@
+/* nsb.h -- C ABI of libnsb.so: the B200-native NeRSemble render hot path.
+ *
+ * Plain C: raw DEVICE pointers, sizes, scalar hparams, an explicit cudaStream_t (passed as
+ * void*).  No C++/torch types.  Every entry point returns 0 on success, non-zero on error;
+ * nsb_last_error() returns a thread-local message.  The library allocates nothing that
+ * outlives a call (caller provides outputs and workspaces) and keeps no global mutable state
+ * besides the error string, so it is re-entrant across streams (the reference trainer and
+ * its viewer thread can render concurrently: engine/nersemble_trainer.py:38-40).
+ *
+ * Each entry point replaces a third-party call of the reference (paths relative to
+ * /root/reference/src/nersemble/):
+ *
+ *   nsb_field_forward      tcnn.Encoding x8 + stack/rearrange/window/einsum + tcnn mlp_base/mlp_head
+ *                          + nerfstudio MLP x8 + se3_exp_map, i.e. everything inside
+ *                          SE3DeformationField.forward (nerfstudio/field_components/deformation_field.py:134-166),
+ *                          HashEnsemble.forward (nerfstudio/field_components/hash_ensemble.py:93-158),
+ *                          NeRSembleNeRFactoField.forward (nerfstudio/fields/nersemble_nerfacto_field.py:385-402)
+ *                          and NeRSembleNGPModel.field_density_fn (nerfstudio/models/nersemble_instant_ngp.py:235-266)
+ *   nsb_hash_blend_forward HashEnsemble.forward alone (component API)
+ *   nsb_composite_forward  nerfacc.pack_info / render_weight_from_density + RGB/Depth/Accumulation/
+ *                          Deformation renderers (nersemble_instant_ngp.py:325-343,359-362;
+ *                          nerfstudio/model_components/nersemble_deformation_renderer.py:10-29)
+ *   nsb_march_*            nerfacc OccGridEstimator.sampling -> traverse_grids
+ *                          (nerfstudio/model_components/nersemble_volumetric_sampler.py:95-108)
+ *   nsb_visibility_*       nerfacc render_visibility_from_density (the training pre-pass of sampling())
+ */
+#ifndef NSB_H
+#define NSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_VERSION 100
+#define NSB_MAX_LEVELS 16
+#define NSB_MEMBERS 32        /* ensemble members (hash_ensemble_config.n_hash_encodings) */
+#define NSB_FEATS 2           /* features per member per level */
+#define NSB_TILE 128          /* samples per CTA tile */
+#define NSB_WARP_CODE_DIM 128 /* deformation warp-code width */
+#define NSB_N_FREQ 7          /* SE3DeformationFieldConfig.n_freq_pos */
+
+/* Hash-grid level table, computed on the host with tcnn's float32 formulas
+ * (scale = exp2f(l*log2f(s))*base - 1, res = ceil(scale)+1, entries = min(round_up(res^3,8), 2^log2T)). */
+typedef struct nsb_levels {
+    int32_t n_levels;
+    float scale[NSB_MAX_LEVELS];
+    uint32_t res[NSB_MAX_LEVELS];
+    uint32_t entries[NSB_MAX_LEVELS];
+    uint32_t offset[NSB_MAX_LEVELS]; /* first entry of the level in the table */
+    uint32_t hashed[NSB_MAX_LEVELS]; /* 1: XOR-prime hash, 0: dense stride index */
+} nsb_levels;
+
+/* Parameters of the field, in the native layouts (all DEVICE pointers). */
+typedef struct nsb_field_params {
+    const void *tables;        /* __half [total_entries][32 members][2 feats]: 128 B per entry */
+    const void *deform_packed; /* fp16 deformation weights in MMA-B fragment order (python: pack_deform) */
+    const float *deform_bias;  /* float [6*128 + 8]: stem biases, then v_bias(3), r_bias(3), 0, 0 */
+    const void *field_packed;  /* fp16 mlp_base + mlp_head weights in MMA-B fragment order */
+    const void *warp_codes;    /* __half [n_timesteps][128]  (time_embedding_deformation) */
+    const float *blend_codes;  /* float  [n_timesteps][32]   (time_embedding) */
+    int32_t n_timesteps;
+    float aabb[6];             /* min xyz, max xyz */
+    nsb_levels levels;
+} nsb_field_params;
+
+/* Per-call options of the field evaluation. */
+typedef struct nsb_field_opts {
+    /* effective blend weight of member h: cw[h] = code[h]*cw_scale[h] + cw_bias[h]
+     * (window, disable_initial_hash_ensemble and soft transition folded in on the host:
+     *  hash_ensemble.py:119-139) */
+    float cw_scale[NSB_MEMBERS];
+    float cw_bias[NSB_MEMBERS];
+    float pe_window[8];       /* Hann window of the 7 posenc bands (windowed_nerf_encoding.py:76-92); 1 if None */
+    int32_t use_deformation;  /* config.use_deformation_field */
+    int32_t compute_rgb;      /* 0: density only (field_density_fn) */
+} nsb_field_opts;
+
+/* Sample sources.  Either ray-based packed samples (positions = o + d*(ts+te)/2, per-ray times)
+ * or explicit positions with per-sample times (density_fn / occupancy update). */
+typedef struct nsb_samples {
+    int64_t n_samples;
+    /* ray-based */
+    const float *origins;      /* [n_rays][3] */
+    const float *directions;   /* [n_rays][3] */
+    const float *ray_times;    /* [n_rays] in [0,1] or NULL (timestep 0) */
+    const float *t_starts;     /* [n_samples] */
+    const float *t_ends;       /* [n_samples] */
+    const int32_t *ray_indices;/* [n_samples] */
+    /* explicit (used when origins == NULL) */
+    const float *positions;    /* [n_samples][3] world */
+    const float *sample_times; /* [n_samples] in [0,1] or NULL */
+    /* optional per-sample conditioning overriding the time-embedding tables (component APIs) */
+    const float *sample_blend_codes; /* float  [n_samples][32] or NULL */
+    const void *sample_warp_codes;   /* __half [n_samples][128] or NULL */
+} nsb_samples;
+
+typedef struct nsb_field_out {
+    float *sigma;    /* [n_samples]     or NULL */
+    float *rgb;      /* [n_samples][3]  or NULL (needs compute_rgb) */
+    float *offsets;  /* [n_samples][3]  or NULL: p' - p in normalised-aabb units (deformation_field.py:148-166) */
+    void *feat;      /* __half [n_samples][32] blended hash features or NULL */
+} nsb_field_out;
+
+int nsb_version(void);
+const char *nsb_last_error(void);
+
+/* Sizes (bytes) of the packed weight buffers the python packer must produce. */
+size_t nsb_deform_packed_bytes(void);
+size_t nsb_field_packed_bytes(void);
+
+/* Fused per-sample field evaluation (deformation MLP -> SE(3) warp -> 32-member hash ensemble
+ * gather+blend -> density MLP -> colour MLP).  One persistent kernel. */
+int nsb_field_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
+                      const nsb_field_out *out, void *stream);
+
+/* HashEnsemble.forward: x [n][3] float in [0,1), code float [n][32] -> out __half/float [n][32].
+ * out_is_half: 1 -> __half output, 0 -> float. */
+int nsb_hash_blend_forward(const nsb_field_params *params, const nsb_field_opts *opts, const float *x,
+                           const float *codes, int64_t n, void *out, int32_t out_is_half, void *stream);
+
+/* Alpha compositing of packed samples. packed_info int64 [n_rays][2] = (start, count). */
+typedef struct nsb_composite_args {
+    int64_t n_rays, n_samples;
+    const int64_t *packed_info;
+    const float *t_starts, *t_ends, *sigma, *rgb, *offsets; /* offsets may be NULL */
+    int32_t training;     /* 0: eval (nan_to_num before, clamp[0,1] after) */
+    float *out_rgb;       /* [n_rays][3] white background */
+    float *out_acc;       /* [n_rays] */
+    float *out_depth;     /* [n_rays] expected depth, clipped to [min(steps), max(steps)] */
+    float *out_deform;    /* [n_rays][3] or NULL */
+    float *out_weights;   /* [n_samples] or NULL */
+    uint32_t *workspace;  /* 2 uint32 (ordered-float min/max of sample midpoints) */
+} nsb_composite_args;
+int nsb_composite_forward(const nsb_composite_args *args, void *stream);
+
+/* Fixed-stride marcher (BASELINE configs 1/2): n_per_ray intervals of `step` from max(t_enter, near). */
+int nsb_march_fixed(const float *origins, const float *directions, int64_t n_rays, const float *aabb6,
+                    int32_t n_per_ray, float step, float near_plane, float *t_starts, float *t_ends,
+                    int32_t *ray_indices, int64_t *packed_info, void *stream);
+
+/* Occupancy-grid marcher (nerfacc traverse_grids, levels grids of res^3 bools).
+ * Pass 1 (t_starts == NULL): writes counts[n_rays].  Pass 2: fills packed outputs at offsets[ray]. */
+typedef struct nsb_march_args {
+    int64_t n_rays;
+    const float *origins, *directions;
+    const float *near_planes, *far_planes; /* [n_rays] (jitter already added) */
+    const uint8_t *binaries;               /* [levels][res][res][res] */
+    const float *aabbs;                    /* [levels][6] */
+    int32_t levels, res;
+    float step, cone_angle;
+    int32_t *counts;                       /* pass 1 out */
+    const int64_t *offsets;                /* pass 2 in: exclusive scan of counts */
+    float *t_starts, *t_ends;              /* pass 2 out */
+    int32_t *ray_indices;                  /* pass 2 out */
+} nsb_march_args;
+int nsb_march_occupancy(const nsb_march_args *args, void *stream);
+
+/* Visibility filter of the training pre-pass: keep = (T >= early_stop_eps) & (alpha >= alpha_thre). */
+int nsb_visibility_mask(const int64_t *packed_info, int64_t n_rays, const float *t_starts, const float *t_ends,
+                        const float *sigma, float early_stop_eps, float alpha_thre, uint8_t *mask,
+                        int32_t *kept_counts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of libnsb.so (C ABI declared in include/nsb.h).
+
+The library is built in-tree (nersemble_b200/libnsb.so) by __graft_entry__.build() /
+`make -C nersemble_b200/csrc`.  Loading fails loudly when it is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnsb.so")
+
+MAX_LEVELS = 16
+MEMBERS = 32
+
+
+class Levels(C.Structure):
+    _fields_ = [("n_levels", C.c_int32),
+                ("scale", C.c_float * MAX_LEVELS),
+                ("res", C.c_uint32 * MAX_LEVELS),
+                ("entries", C.c_uint32 * MAX_LEVELS),
+                ("offset", C.c_uint32 * MAX_LEVELS),
+                ("hashed", C.c_uint32 * MAX_LEVELS)]
+
+
+class FieldParams(C.Structure):
+    _fields_ = [("tables", C.c_void_p), ("deform_packed", C.c_void_p), ("deform_bias", C.c_void_p),
+                ("field_packed", C.c_void_p), ("warp_codes", C.c_void_p), ("blend_codes", C.c_void_p),
+                ("n_timesteps", C.c_int32), ("aabb", C.c_float * 6), ("levels", Levels)]
+
+
+class FieldOpts(C.Structure):
+    _fields_ = [("cw_scale", C.c_float * MEMBERS), ("cw_bias", C.c_float * MEMBERS),
+                ("pe_window", C.c_float * 8), ("use_deformation", C.c_int32), ("compute_rgb", C.c_int32)]
+
+
+class Samples(C.Structure):
+    _fields_ = [("n_samples", C.c_int64),
+                ("origins", C.c_void_p), ("directions", C.c_void_p), ("ray_times", C.c_void_p),
+                ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("ray_indices", C.c_void_p),
+                ("positions", C.c_void_p), ("sample_times", C.c_void_p),
+                ("sample_blend_codes", C.c_void_p), ("sample_warp_codes", C.c_void_p)]
+
+
+class FieldOut(C.Structure):
+    _fields_ = [("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p), ("feat", C.c_void_p)]
+
+
+class CompositeArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int64), ("packed_info", C.c_void_p),
+                ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p),
+                ("offsets", C.c_void_p), ("training", C.c_int32),
+                ("out_rgb", C.c_void_p), ("out_acc", C.c_void_p), ("out_depth", C.c_void_p),
+                ("out_deform", C.c_void_p), ("out_weights", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+class MarchArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("origins", C.c_void_p), ("directions", C.c_void_p),
+                ("near_planes", C.c_void_p), ("far_planes", C.c_void_p), ("binaries", C.c_void_p),
+                ("aabbs", C.c_void_p), ("levels", C.c_int32), ("res", C.c_int32),
+                ("step", C.c_float), ("cone_angle", C.c_float), ("counts", C.c_void_p),
+                ("offsets", C.c_void_p), ("t_starts", C.c_void_p), ("t_ends", C.c_void_p),
+                ("ray_indices", C.c_void_p)]
+
+
+# every symbol include/nsb.h declares: (name, restype, argtypes)
+SYMBOLS = {
+    "nsb_version": (C.c_int, []),
+    "nsb_last_error": (C.c_char_p, []),
+    "nsb_deform_packed_bytes": (C.c_size_t, []),
+    "nsb_field_packed_bytes": (C.c_size_t, []),
+    "nsb_field_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
+                                    C.POINTER(FieldOut), C.c_void_p]),
+    "nsb_hash_blend_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "nsb_composite_forward": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),
+    "nsb_march_fixed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsb_march_occupancy": (C.c_int, [C.POINTER(MarchArgs), C.c_void_p]),
+    "nsb_visibility_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                      C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libnsb.so (once) and bind every declared symbol.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C nersemble_b200/csrc`.  nersemble_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nsb_version() != 100:
+        raise RuntimeError(f"libnsb version mismatch: {lib.nsb_version()}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().nsb_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,297 @@
+"""Tensor-level wrappers over the libnsb C ABI (include/nsb.h).
+
+PyTorch is used for device memory and streams only; all arithmetic of the hot path runs in
+the hand-written sm_100a kernels.  There is no CPU fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib, packing
+
+_F32 = torch.float32
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nersemble_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.detach().to(_F32).contiguous()
+
+
+@dataclass
+class NativeParams:
+    """Device-resident parameters in the kernels' layouts (see packing.py)."""
+    tables: torch.Tensor          # half [entries, 32, 2]
+    deform_packed: Optional[torch.Tensor]   # half, fragment order
+    deform_bias: Optional[torch.Tensor]     # float [776]
+    field_packed: torch.Tensor    # half, fragment order
+    warp_codes: Optional[torch.Tensor]      # half [T, 128]
+    blend_codes: torch.Tensor     # float [T, 32]
+    aabb: torch.Tensor            # float [2,3] (cpu copy kept in aabb_list)
+    levels: dict
+    n_timesteps: int
+
+    def __post_init__(self):
+        self.aabb_list = [float(v) for v in self.aabb.detach().cpu().reshape(-1)]
+        lv = self.levels
+        for l in range(lv["n_levels"]):
+            if lv["hashed"][l]:
+                e = lv["entries"][l]
+                assert e & (e - 1) == 0, "hashed levels must have power-of-two size"
+        assert self.tables.dtype == torch.float16 and self.tables.shape[1:] == (32, 2)
+        assert self.tables.shape[0] == lv["total_entries"]
+
+    @staticmethod
+    def build(*, tables, base_w, head_w, time_emb, aabb, levels, deform=None, time_emb_deform=None,
+              device="cuda") -> "NativeParams":
+        """tables: [entries,32,2] (any float dtype); base_w/head_w: lists of [out,in] matrices;
+        deform: dict(stem_w, stem_b, r_w, r_b, v_w, v_b) or None."""
+        dev = torch.device(device)
+        tab = tables.detach().to(dev).half().contiguous()
+        fp = packing.pack_field([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
+        dp = db = wc = None
+        if deform is not None:
+            dp, db = packing.pack_deform([w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]],
+                                         deform["r_w"].to(dev), deform["r_b"].to(dev),
+                                         deform["v_w"].to(dev), deform["v_b"].to(dev))
+            wc = time_emb_deform.detach().to(dev).half().contiguous()
+        return NativeParams(tab, dp, db, fp, wc, time_emb.detach().to(dev).float().contiguous(),
+                            aabb.detach().float().cpu(), levels, int(time_emb.shape[0]))
+
+    def c_params(self) -> _lib.FieldParams:
+        p = _lib.FieldParams()
+        p.tables = _ptr(self.tables)
+        p.deform_packed = _ptr(self.deform_packed)
+        p.deform_bias = _ptr(self.deform_bias)
+        p.field_packed = _ptr(self.field_packed)
+        p.warp_codes = _ptr(self.warp_codes)
+        p.blend_codes = _ptr(self.blend_codes)
+        p.n_timesteps = self.n_timesteps
+        for i, v in enumerate(self.aabb_list):
+            p.aabb[i] = v
+        lv = self.levels
+        p.levels.n_levels = lv["n_levels"]
+        for l in range(lv["n_levels"]):
+            p.levels.scale[l] = lv["scale"][l]
+            p.levels.res[l] = lv["res"][l]
+            p.levels.entries[l] = lv["entries"][l]
+            p.levels.offset[l] = lv["offset"][l]
+            p.levels.hashed[l] = lv["hashed"][l]
+        return p
+
+
+def make_opts(window_hash: Optional[float], window_deform: Optional[float], use_deformation: bool,
+              compute_rgb: bool, disable_initial: bool = True, soft_transition: bool = True) -> _lib.FieldOpts:
+    o = _lib.FieldOpts()
+    sc, bi = packing.blend_fold(window_hash, 32, disable_initial, soft_transition)
+    for h in range(32):
+        o.cw_scale[h] = sc[h]
+        o.cw_bias[h] = bi[h]
+    for j, w in enumerate(packing.deform_window(window_deform)):
+        o.pe_window[j] = w
+    o.use_deformation = int(use_deformation)
+    o.compute_rgb = int(compute_rgb)
+    return o
+
+
+def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_deformation=True,
+                  origins=None, directions=None, ray_times=None, t_starts=None, t_ends=None, ray_indices=None,
+                  positions=None, sample_times=None, sample_blend_codes=None, sample_warp_codes=None,
+                  want: Sequence[str] = ("sigma", "rgb", "offsets"),
+                  disable_initial: bool = True, soft_transition: bool = True) -> Dict[str, torch.Tensor]:
+    """Fused deformation + hash ensemble + field MLPs for packed samples (nsb_field_forward)."""
+    lib = _lib.load()
+    ray_based = origins is not None
+    keep = []
+    s = _lib.Samples()
+    if ray_based:
+        origins, directions, t_starts, t_ends = map(_f32c, (origins, directions, t_starts, t_ends))
+        ray_indices = ray_indices.detach().to(torch.int32).contiguous()
+        ray_times = None if ray_times is None else _f32c(ray_times).reshape(-1)
+        _need_cuda(origins, directions, t_starts, t_ends, ray_indices, ray_times)
+        n = int(t_starts.shape[0])
+        s.origins, s.directions, s.ray_times = _ptr(origins), _ptr(directions), _ptr(ray_times)
+        s.t_starts, s.t_ends, s.ray_indices = _ptr(t_starts), _ptr(t_ends), _ptr(ray_indices)
+        keep += [origins, directions, t_starts, t_ends, ray_indices, ray_times]
+        dev = origins.device
+    else:
+        positions = _f32c(positions).reshape(-1, 3)
+        sample_times = None if sample_times is None else _f32c(sample_times).reshape(-1)
+        _need_cuda(positions, sample_times)
+        n = int(positions.shape[0])
+        s.positions, s.sample_times = _ptr(positions), _ptr(sample_times)
+        keep += [positions, sample_times]
+        dev = positions.device
+    if sample_blend_codes is not None:
+        sample_blend_codes = _f32c(sample_blend_codes)
+        assert sample_blend_codes.shape == (n, 32)
+        s.sample_blend_codes = _ptr(sample_blend_codes); keep.append(sample_blend_codes)
+    if sample_warp_codes is not None:
+        sample_warp_codes = sample_warp_codes.detach().half().contiguous()
+        assert sample_warp_codes.shape == (n, 128)
+        s.sample_warp_codes = _ptr(sample_warp_codes); keep.append(sample_warp_codes)
+    s.n_samples = n
+    out = {}
+    o = _lib.FieldOut()
+    if "sigma" in want:
+        out["sigma"] = torch.empty((n,), dtype=_F32, device=dev); o.sigma = _ptr(out["sigma"])
+    if "rgb" in want:
+        out["rgb"] = torch.empty((n, 3), dtype=_F32, device=dev); o.rgb = _ptr(out["rgb"])
+    if "offsets" in want:
+        if use_deformation:
+            out["offsets"] = torch.empty((n, 3), dtype=_F32, device=dev); o.offsets = _ptr(out["offsets"])
+        else:
+            out["offsets"] = torch.zeros((n, 3), dtype=_F32, device=dev)
+    if "feat" in want:
+        out["feat"] = torch.empty((n, 32), dtype=torch.float16, device=dev); o.feat = _ptr(out["feat"])
+    if n == 0:
+        return out
+    opts = make_opts(window_hash, window_deform, use_deformation, "rgb" in want, disable_initial, soft_transition)
+    cp = P.c_params()
+    rc = lib.nsb_field_forward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(o), _stream())
+    _lib.check(rc, "nsb_field_forward")
+    return out
+
+
+def hash_blend_forward(P: NativeParams, x: torch.Tensor, codes: torch.Tensor, window_hash=None,
+                       out_half: bool = True, disable_initial=True, soft_transition=True) -> torch.Tensor:
+    """HashEnsemble.forward (hash_ensemble.py:93-158): x [n,3] in [0,1), codes [n,32]."""
+    lib = _lib.load()
+    x = _f32c(x); codes = _f32c(codes)
+    _need_cuda(x, codes)
+    n = x.shape[0]
+    out = torch.empty((n, 32), dtype=torch.float16 if out_half else _F32, device=x.device)
+    if n == 0:
+        return out
+    opts = make_opts(window_hash, None, False, False, disable_initial, soft_transition)
+    cp = P.c_params()
+    rc = lib.nsb_hash_blend_forward(C.byref(cp), C.byref(opts), _ptr(x), _ptr(codes), n, _ptr(out), int(out_half), _stream())
+    _lib.check(rc, "nsb_hash_blend_forward")
+    return out
+
+
+def composite(packed_info: torch.Tensor, t_starts, t_ends, sigma, rgb, offsets=None, training=False,
+              want_weights=True) -> Dict[str, torch.Tensor]:
+    """render_weight_from_density + RGB(white)/Depth(expected)/Accumulation/Deformation renderers."""
+    lib = _lib.load()
+    _need_cuda(packed_info, t_starts, t_ends, sigma, rgb, offsets)
+    packed_info = packed_info.to(torch.int64).contiguous()
+    R = packed_info.shape[0]; n = t_starts.shape[0]; dev = t_starts.device
+    a = _lib.CompositeArgs()
+    a.n_rays, a.n_samples = R, n
+    a.packed_info = _ptr(packed_info)
+    ts, te, sg, cc = map(_f32c, (t_starts, t_ends, sigma, rgb))
+    off = _f32c(offsets)
+    a.t_starts, a.t_ends, a.sigma, a.rgb, a.offsets = _ptr(ts), _ptr(te), _ptr(sg), _ptr(cc), _ptr(off)
+    a.training = int(training)
+    out = {"rgb": torch.empty((R, 3), dtype=_F32, device=dev), "accumulation": torch.empty((R, 1), dtype=_F32, device=dev),
+           "depth": torch.empty((R, 1), dtype=_F32, device=dev)}
+    a.out_rgb, a.out_acc, a.out_depth = _ptr(out["rgb"]), _ptr(out["accumulation"]), _ptr(out["depth"])
+    if off is not None:
+        out["deformation"] = torch.empty((R, 3), dtype=_F32, device=dev); a.out_deform = _ptr(out["deformation"])
+    if want_weights:
+        out["weights"] = torch.empty((n, 1), dtype=_F32, device=dev); a.out_weights = _ptr(out["weights"])
+    ws = torch.empty((2,), dtype=torch.int32, device=dev)
+    a.workspace = _ptr(ws)
+    rc = lib.nsb_composite_forward(C.byref(a), _stream())
+    _lib.check(rc, "nsb_composite_forward")
+    return out
+
+
+def march_fixed(origins, directions, aabb: torch.Tensor, n_per_ray: int, step: float, near_plane: float = 0.0):
+    lib = _lib.load()
+    origins, directions = _f32c(origins), _f32c(directions)
+    _need_cuda(origins, directions)
+    dev = origins.device
+    R = origins.shape[0]
+    aabb_d = aabb.detach().to(dev, _F32).reshape(-1).contiguous()
+    n = R * n_per_ray
+    ts = torch.empty((n,), dtype=_F32, device=dev); te = torch.empty((n,), dtype=_F32, device=dev)
+    ri = torch.empty((n,), dtype=torch.int32, device=dev)
+    info = torch.empty((R, 2), dtype=torch.int64, device=dev)
+    rc = lib.nsb_march_fixed(_ptr(origins), _ptr(directions), R, _ptr(aabb_d), n_per_ray, float(step), float(near_plane),
+                             _ptr(ts), _ptr(te), _ptr(ri), _ptr(info), _stream())
+    _lib.check(rc, "nsb_march_fixed")
+    return ts, te, ri, info
+
+
+def march_occupancy(origins, directions, near_planes, far_planes, binaries: torch.Tensor, aabbs: torch.Tensor,
+                    step: float, cone_angle: float = 0.0):
+    """nerfacc traverse_grids: two passes (count, exclusive scan, fill).  Returns packed
+    (t_starts, t_ends, ray_indices int32, packed_info int64 [R,2])."""
+    lib = _lib.load()
+    origins, directions, near_planes, far_planes = map(_f32c, (origins, directions, near_planes, far_planes))
+    _need_cuda(origins, directions, near_planes, far_planes, binaries, aabbs)
+    dev = origins.device
+    R = origins.shape[0]
+    b8 = binaries.detach().to(torch.uint8).contiguous()
+    levels, res = int(b8.shape[0]), int(b8.shape[1])
+    assert b8.shape[1] == b8.shape[2] == b8.shape[3], "cubic grids only"
+    ab = aabbs.detach().to(dev, _F32).reshape(levels, 6).contiguous()
+    a = _lib.MarchArgs()
+    a.n_rays = R
+    a.origins, a.directions, a.near_planes, a.far_planes = _ptr(origins), _ptr(directions), _ptr(near_planes), _ptr(far_planes)
+    a.binaries, a.aabbs, a.levels, a.res = _ptr(b8), _ptr(ab), levels, res
+    a.step, a.cone_angle = float(step), float(cone_angle)
+    counts = torch.empty((R,), dtype=torch.int32, device=dev)
+    a.counts = _ptr(counts)
+    _lib.check(lib.nsb_march_occupancy(C.byref(a), _stream()), "nsb_march_occupancy(count)")
+    cnt64 = counts.to(torch.int64)
+    incl = torch.cumsum(cnt64, 0)
+    offsets = (incl - cnt64).contiguous()
+    n = int(incl[-1].item()) if R > 0 else 0       # host sync: the packed size is data dependent
+    ts = torch.empty((n,), dtype=_F32, device=dev); te = torch.empty((n,), dtype=_F32, device=dev)
+    ri = torch.empty((n,), dtype=torch.int32, device=dev)
+    if n > 0:
+        a.offsets, a.t_starts, a.t_ends, a.ray_indices = _ptr(offsets), _ptr(ts), _ptr(te), _ptr(ri)
+        _lib.check(lib.nsb_march_occupancy(C.byref(a), _stream()), "nsb_march_occupancy(fill)")
+    return ts, te, ri, torch.stack([offsets, cnt64], -1)
+
+
+def visibility_mask(packed_info, t_starts, t_ends, sigma, early_stop_eps: float, alpha_thre: float):
+    lib = _lib.load()
+    _need_cuda(packed_info, t_starts, t_ends, sigma)
+    packed_info = packed_info.to(torch.int64).contiguous()
+    ts, te, sg = map(_f32c, (t_starts, t_ends, sigma))
+    R = packed_info.shape[0]; n = ts.shape[0]
+    mask = torch.zeros((n,), dtype=torch.uint8, device=ts.device)
+    kept = torch.zeros((R,), dtype=torch.int32, device=ts.device)
+    rc = lib.nsb_visibility_mask(_ptr(packed_info), R, _ptr(ts), _ptr(te), _ptr(sg), float(early_stop_eps),
+                                 float(alpha_thre), _ptr(mask), _ptr(kept), _stream())
+    _lib.check(rc, "nsb_visibility_mask")
+    return mask.bool(), kept
+
+
+def render_packed(P: NativeParams, origins, directions, ray_times, t_starts, t_ends, ray_indices, packed_info, *,
+                  window_hash=None, window_deform=None, use_deformation=True, training=False,
+                  disable_initial=True, soft_transition=True) -> Dict[str, torch.Tensor]:
+    """NeRSembleNGPModel.get_outputs after the sampler (nersemble_instant_ngp.py:297-364)."""
+    f = field_forward(P, window_hash=window_hash, window_deform=window_deform, use_deformation=use_deformation,
+                      origins=origins, directions=directions, ray_times=ray_times, t_starts=t_starts, t_ends=t_ends,
+                      ray_indices=ray_indices, want=("sigma", "rgb", "offsets"),
+                      disable_initial=disable_initial, soft_transition=soft_transition)
+    c = composite(packed_info, t_starts, t_ends, f["sigma"], f["rgb"], f["offsets"] if use_deformation else None,
+                  training=training)
+    c["num_samples_per_ray"] = packed_info[:, 1]
+    c["offsets"] = f["offsets"]
+    c["density"] = f["sigma"][:, None]
+    c["rgb_samples"] = f["rgb"]
+    return c

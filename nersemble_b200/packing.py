@@ -1,0 +1,179 @@
+"""Host-side parameter layout for the B200 kernels (pure torch ops; runs on CPU or GPU).
+
+* hash tables: 8 tcnn grids (flat [(entry)*8 + p*2 + f], the reference's
+  `field.hash_ensemble.hash_encodings.{c}.params`) <-> native [entry][member=c*4+p][feat] fp16,
+  one 128-byte line per entry (field_components/hash_ensemble.py:102-112).
+* MLP weights: nn.Linear / tcnn [out,in] matrices -> fp16 in mma.sync m16n8k16 B-fragment order,
+  so a warp reads the fragments of two n-tiles with one 512-byte LDS.128 (csrc/nsb_field.cu).
+* level table: tcnn's float32 formulas (grid.h) evaluated once on the host.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+N_FREQ = 7
+WARP_CODE_DIM = 128
+DEFORM_IN_DIM = 3 * N_FREQ * 2 + 3 + WARP_CODE_DIM      # 173
+DEFORM_IN_PAD = 48 + WARP_CODE_DIM                      # 176 (posenc permuted+padded to 48)
+
+
+# ------------------------------------------------------------------ level table
+def level_table(n_levels=16, log2_hashmap_size=19, base_resolution=16, per_level_scale=1.4472692012786865):
+    """tcnn grid.h: scale = exp2f(l*log2f(s))*base - 1 (float32), res = ceil(scale)+1,
+    entries = min(round_up(res^3, 8), 2^log2T); hashed iff entries < res^3-stride walk."""
+    s = np.float32(per_level_scale)
+    l2 = np.log2(s)
+    out = dict(scale=[], res=[], entries=[], offset=[], hashed=[])
+    off = 0
+    for l in range(n_levels):
+        sc = np.float32(np.exp2(np.float32(l) * l2) * np.float32(base_resolution) - np.float32(1.0))
+        r = int(np.ceil(sc)) + 1
+        e = min(((r ** 3 + 7) // 8) * 8, 1 << log2_hashmap_size)
+        stride = 1
+        for _ in range(3):
+            if stride <= e:
+                stride *= r
+        out["scale"].append(float(sc)); out["res"].append(r); out["entries"].append(e)
+        out["offset"].append(off); out["hashed"].append(int(e < stride))
+        off += e
+    out["total_entries"] = off
+    out["n_levels"] = n_levels
+    return out
+
+
+# ------------------------------------------------------------------ hash tables
+def tables_from_tcnn(grid_params: Sequence[torch.Tensor], n_feats: int = 2) -> torch.Tensor:
+    """8 flat tcnn grids -> native [entries, 32, 2] (same dtype)."""
+    P = 8 // n_feats
+    per = [g.reshape(-1, P, n_feats) for g in grid_params]
+    return torch.stack(per, 1).reshape(per[0].shape[0], len(per) * P, n_feats).contiguous()
+
+
+def tables_to_tcnn(tables: torch.Tensor) -> List[torch.Tensor]:
+    N, H, F = tables.shape
+    P = 8 // F
+    t = tables.reshape(N, H // P, P, F)
+    return [t[:, c].reshape(-1).contiguous() for c in range(H // P)]
+
+
+# ------------------------------------------------------------------ MMA B-fragment packing
+def pack_mma_b(W: torch.Tensor, colmap: Sequence[int], group_cols: int) -> torch.Tensor:
+    """W [N_out, K_in] -> fp16 tensor in order [group][k-tile][n-tile pair][lane][ntsel][hi][e]:
+    lane = g*4+q holds, for n = group*group_cols + pair*16 + ntsel*8 + g and
+    k = kt*16 + hi*8 + 2q + e, the element W[n, colmap[k]] (0 where colmap[k] < 0 or n >= N_out)."""
+    N, _ = W.shape
+    Kp = len(colmap)
+    assert Kp % 16 == 0 and group_cols % 16 == 0
+    Np = ((N + group_cols - 1) // group_cols) * group_cols
+    cm = torch.as_tensor(list(colmap), dtype=torch.long, device=W.device)
+    Wp = torch.zeros((Np, Kp), dtype=torch.float32, device=W.device)
+    valid = cm >= 0
+    Wp[:N][:, valid] = W.detach().float()[:, cm[valid]]
+    Wh = Wp.half()
+    G, NPR, KT = Np // group_cols, group_cols // 16, Kp // 16
+    t = Wh.view(G, NPR, 2, 8, KT, 2, 4, 2)          # (grp, pair, ntsel, g, kt, hi, q, e)
+    t = t.permute(0, 4, 1, 3, 6, 2, 5, 7)           # (grp, kt, pair, g, q, ntsel, hi, e)
+    return t.contiguous().view(-1)
+
+
+def deform_input_colmap() -> List[int]:
+    """Kernel input column k' (176) -> reference input column (173) of mlp_stem layer 0.
+    Kernel order: pairs (sin, cos) of arg i = dim*7 + freq for i < 21, then (2pi x, 2pi y),
+    (2pi z, 0), (0, 0), then the 128 warp-code columns.  Reference order
+    (windowed_nerf_encoding.py:50-73): sin block (21), cos block (21), 2pi*xyz (3), code (128)."""
+    m = []
+    for kp in range(48):
+        i, s = divmod(kp, 2)
+        if i < 21:
+            m.append(i if s == 0 else 21 + i)
+        elif i == 21:
+            m.append(42 if s == 0 else 43)
+        elif i == 22:
+            m.append(44 if s == 0 else -1)
+        else:
+            m.append(-1)
+    m += [45 + k for k in range(WARP_CODE_DIM)]
+    return m
+
+
+def pack_deform(stem_w: Sequence[torch.Tensor], stem_b: Sequence[torch.Tensor], r_w, r_b, v_w, v_b):
+    """mlp_stem (6 Linear, skip at 4: input [in(173) | hidden(128)]), mlp_r, mlp_v
+    (field_components/deformation_field.py:50-75) -> (packed fp16 weights, fp32 bias[776])."""
+    assert len(stem_w) == 6 and stem_w[0].shape == (128, DEFORM_IN_DIM) and stem_w[4].shape == (128, DEFORM_IN_DIM + 128)
+    in_map = deform_input_colmap()
+    ident = list(range(128))
+    skip_map = [DEFORM_IN_DIM + k for k in range(128)] + in_map      # kernel order: [hidden | input]
+    maps = [in_map, ident, ident, ident, skip_map, ident]
+    parts = [pack_mma_b(w, m, 64) for w, m in zip(stem_w, maps)]
+    heads = torch.cat([v_w.detach().float(), r_w.detach().float()], 0)    # cols 0..2 = v, 3..5 = r
+    parts.append(pack_mma_b(heads, ident, 16))
+    packed = torch.cat(parts)
+    dev = stem_b[0].device
+    bias = torch.cat([b.detach().float().reshape(-1) for b in stem_b] +
+                     [v_b.detach().float().reshape(-1), r_b.detach().float().reshape(-1),
+                      torch.zeros(2, device=dev)])
+    assert packed.numel() * 2 == 258048 and bias.numel() == 776
+    return packed.contiguous(), bias.contiguous()
+
+
+def head_input_colmap() -> List[int]:
+    """Kernel colour-MLP input column -> reference column of [d'(3) | geo(15) | ones(14)]
+    (fields/nersemble_nerfacto_field.py:371-377 + tcnn pad-with-1.0).  Kernel order:
+    [1.0 | geo(15) | d'(3) | 1.0 x 13] so the density-MLP accumulators feed k-tile 0 directly."""
+    return [18] + [3 + j for j in range(15)] + [0, 1, 2] + list(range(19, 32))
+
+
+def pack_field(base_w: Sequence[torch.Tensor], head_w: Sequence[torch.Tensor]) -> torch.Tensor:
+    """tcnn mlp_base (32->64->16) and mlp_head (32->64->64->16) weight matrices [out,in]."""
+    assert base_w[0].shape == (64, 32) and base_w[1].shape == (16, 64)
+    assert head_w[0].shape == (64, 32) and head_w[1].shape == (64, 64) and head_w[2].shape == (16, 64)
+    parts = [pack_mma_b(base_w[0], range(32), 64), pack_mma_b(base_w[1], range(64), 16),
+             pack_mma_b(head_w[0], head_input_colmap(), 64), pack_mma_b(head_w[1], range(64), 64),
+             pack_mma_b(head_w[2], range(64), 16)]
+    packed = torch.cat(parts)
+    assert packed.numel() * 2 == 20480
+    return packed.contiguous()
+
+
+def split_tcnn_mlp_params(flat: torch.Tensor, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:
+    """tcnn Network .params (layers consecutive, each [out,in] row-major) -> list of matrices."""
+    out, ofs = [], 0
+    for (o, i) in shapes:
+        out.append(flat[ofs:ofs + o * i].view(o, i)); ofs += o * i
+    assert ofs == flat.numel()
+    return out
+
+
+# ------------------------------------------------------------------ windows / blend folding
+def posenc_window(windows_param: float, min_bands: float, max_bands: float, dim: int) -> torch.Tensor:
+    """hash_ensemble.py:12-28 / windowed_nerf_encoding.py:76-92."""
+    bands = torch.linspace(min_bands, max_bands, dim)
+    x = torch.clamp(windows_param - bands, 0, 1)
+    return 0.5 * (1 - torch.cos(torch.pi * x))
+
+
+def blend_fold(window_hash: Optional[float], n_members: int = 32, disable_initial: bool = True,
+               soft_transition: bool = True):
+    """Fold hash_ensemble.py:119-139 into cw[h] = code[h]*scale[h] + bias[h]."""
+    scale = torch.ones(n_members); bias = torch.zeros(n_members)
+    if window_hash is not None:
+        window = posenc_window(window_hash, 0, n_members - 1, n_members)
+        if window_hash == 1 and disable_initial:
+            scale = torch.zeros(n_members); bias = window.clone()
+        elif soft_transition and window_hash < 2:
+            alpha = window_hash - 1
+            scale = window * alpha
+            bias = torch.zeros(n_members); bias[0] = window[0] * (1 - alpha)
+        else:
+            scale = window
+    return scale.tolist(), bias.tolist()
+
+
+def deform_window(window_deform: Optional[float]) -> List[float]:
+    if window_deform is None:
+        return [1.0] * 8
+    return posenc_window(window_deform, 0.0, N_FREQ - 1, N_FREQ).tolist() + [0.0]

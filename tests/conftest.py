@@ -34,3 +34,16 @@ def oracle_params(knobs):
             _PARAM_CACHE.clear()
         _PARAM_CACHE[key] = pl.random_params(**knobs)
     return _PARAM_CACHE[key]
+
+
+def native_from_oracle(P, device="cuda"):
+    """oracle FieldParams -> nersemble_b200.ops.NativeParams (same numbers, kernel layouts)."""
+    from nersemble_b200 import ops, packing
+    lv = P.levels
+    levels = dict(n_levels=lv.n_levels, scale=[float(x) for x in lv.scale], res=[int(x) for x in lv.res],
+                  entries=[int(x) for x in lv.entries], offset=[int(x) for x in lv.offset[:-1]],
+                  hashed=[int(x) for x in lv.hashed], total_entries=lv.total_entries)
+    deform = dict(stem_w=P.deform_w, stem_b=P.deform_b, r_w=P.r_w, r_b=P.r_b, v_w=P.v_w, v_b=P.v_b)
+    return ops.NativeParams.build(tables=P.tables, base_w=P.base_w, head_w=P.head_w, time_emb=P.time_emb,
+                                  aabb=P.aabb, levels=levels, deform=deform, time_emb_deform=P.time_emb_deform,
+                                  device=device)

@@ -1,0 +1,116 @@
+"""CPU tests of the host logic: packing layouts, level table, window folding, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from nersemble_b200 import _lib, packing
+from oracle import pipeline as pl
+from oracle.tp.tcnn_cpu import hashgrid_levels
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_level_table_matches_oracle_and_survey():
+    lv = packing.level_table()
+    o = hashgrid_levels()
+    assert lv["res"] == [16, 24, 34, 49, 71, 102, 148, 213, 308, 446, 646, 934, 1352, 1956, 2831, 4096]
+    assert lv["total_entries"] == 6299960 == o.total_entries
+    assert lv["offset"][:6] == [0, 4096, 17920, 57224, 174880, 532792]
+    assert lv["hashed"] == [0] * 5 + [1] * 11 == [int(h) for h in o.hashed]
+    np.testing.assert_array_equal(np.array(lv["scale"], np.float32), o.scale)
+
+
+def test_tables_roundtrip_and_rearrange():
+    g = torch.Generator().manual_seed(0)
+    grids = [torch.rand(40 * 8, generator=g) for _ in range(8)]
+    t = packing.tables_from_tcnn(grids)
+    assert t.shape == (40, 32, 2)
+    # reference mapping (hash_ensemble.py:112): column l*8 + p*2 + f of grid c -> member c*4+p, feature f
+    assert t[7, 2 * 4 + 3, 1] == grids[2][7 * 8 + 3 * 2 + 1]
+    back = packing.tables_to_tcnn(t)
+    for a, b in zip(grids, back):
+        assert torch.equal(a, b)
+    assert torch.equal(pl.tables_from_tcnn(grids), t)
+
+
+def _brute_pack(W, colmap, group_cols):
+    N, _ = W.shape
+    Kp = len(colmap); Np = ((N + group_cols - 1) // group_cols) * group_cols
+    out = []
+    for grp in range(Np // group_cols):
+        for kt in range(Kp // 16):
+            for pair in range(group_cols // 16):
+                for lane in range(32):
+                    g, q = lane >> 2, lane & 3
+                    for ntsel in range(2):
+                        n = grp * group_cols + pair * 16 + ntsel * 8 + g
+                        for hi in range(2):
+                            for e in range(2):
+                                k = kt * 16 + hi * 8 + 2 * q + e
+                                c = colmap[k]
+                                out.append(float(W[n, c]) if (c >= 0 and n < N) else 0.0)
+    return torch.tensor(out).half()
+
+
+def test_pack_mma_b_matches_fragment_definition():
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn((6, 32), generator=g)
+    cm = list(range(31, -1, -1)); cm[5] = -1
+    assert torch.equal(packing.pack_mma_b(W, cm, 16), _brute_pack(W, cm, 16))
+    W = torch.randn((128, 40), generator=g)
+    cm = [(-1 if k % 7 == 0 else k % 40) for k in range(48)]
+    assert torch.equal(packing.pack_mma_b(W, cm, 64), _brute_pack(W, cm, 64))
+
+
+def test_colmaps_are_consistent_with_reference_orders():
+    cm = packing.deform_input_colmap()
+    assert len(cm) == 176 and sorted(c for c in cm if c >= 0) == list(range(173))
+    assert cm[0] == 0 and cm[1] == 21            # (sin, cos) of x*f0
+    assert cm[2 * 7] == 7 and cm[2 * 7 + 1] == 28  # y*f0
+    assert cm[42:46] == [42, 43, 44, -1]
+    hm = packing.head_input_colmap()
+    assert sorted(hm) == list(range(32)) and hm[16:19] == [0, 1, 2] and hm[1] == 3
+
+
+def test_pack_sizes():
+    P = pl.random_params(n_timesteps=2, log2_hashmap_size=4)
+    dp, db = packing.pack_deform(P.deform_w, P.deform_b, P.r_w, P.r_b, P.v_w, P.v_b)
+    assert dp.numel() * 2 == 258048 and db.numel() == 776
+    assert packing.pack_field(P.base_w, P.head_w).numel() * 2 == 20480
+
+
+def test_blend_fold_matches_reference_semantics():
+    code = torch.randn(5, 32)
+    for w in (None, 1, 1.25, 1.999, 2.0, 7.3, 32.0):
+        sc, bi = packing.blend_fold(w)
+        cw = code * torch.tensor(sc) + torch.tensor(bi)
+        P = pl.random_params(n_timesteps=2, log2_hashmap_size=4)
+        c2, win = pl.blend_code(P, code, w)
+        want = c2 if win is None else c2 * win[None]
+        torch.testing.assert_close(cw, want, rtol=1e-6, atol=1e-7)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "nsb.h")).read()
+    declared = set(re.findall(r"\b(nsb_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nsb_version() == 100
+    lib.nsb_deform_packed_bytes.restype = ctypes.c_size_t
+    lib.nsb_field_packed_bytes.restype = ctypes.c_size_t
+    assert lib.nsb_deform_packed_bytes() == 258048 and lib.nsb_field_packed_bytes() == 20480
+
+
+def test_ops_refuse_cpu_tensors():
+    from nersemble_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.march_fixed(torch.zeros(2, 3), torch.ones(2, 3), torch.tensor([[0., 0, 0], [1, 1, 1]]), 4, 0.1)
