@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsb.so")
+LIB_PATH = os.environ.get("NSB_LIB", os.path.join(_HERE, "libnsb.so"))   # NSB_LIB: kernel-variant A/B runs
 
 MAX_LEVELS = 16
 MEMBERS = 32

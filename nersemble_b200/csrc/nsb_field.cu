@@ -22,6 +22,7 @@
 //     hold (corner-group, member-group) partial sums that a 31-shuffle transposing butterfly
 //     reduces so that lane i ends with output feature i.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nsb_common.cuh"
 
@@ -49,6 +50,13 @@ constexpr int kDeformPackedBytes = kNumSlabs * kSlabBytes;  // 258048
 constexpr int kFieldPackedU4 = 256 + 128 + 256 + 512 + 128;  // base0, base1, head0, head1, head2
 constexpr int kFeatStride = 40;  // halfs per feature row in smem (bank-conflict-free fragment loads)
 constexpr int kBiasFloats = 6 * 128 + 8;
+#ifndef NSB_GATHER_LB
+#define NSB_GATHER_LB 4
+#endif
+#ifndef NSB_GATHER_MMA
+#define NSB_GATHER_MMA 1
+#endif
+constexpr int kGatherLB = NSB_GATHER_LB;  // levels per load batch: 2*LB LDG.128 in flight per lane
 
 struct FieldArgs {
     nsb_field_params P;
@@ -56,6 +64,7 @@ struct FieldArgs {
     nsb_samples S;
     nsb_field_out out;
     float aabb_size[3];
+    uint32_t stagger_ns;   // second-wave CTAs start this much later (de-phases the two CTAs of an SM)
 };
 
 struct alignas(16) WarpScratch {
@@ -88,7 +97,7 @@ __device__ __forceinline__ void ring_gemm(float (&acc)[8][4], const int j0, cons
     for (int kt = 0; kt < KT; ++kt) {
         const int j = j0 + kt;
         const int chunk = j >> 2, stage = chunk & 3;
-        if ((j & 3) == 0) mbar_wait(&sm.full[stage], (chunk >> 2) & 1);
+        if ((j & 3) == 0) mbar_wait<20>(&sm.full[stage], (chunk >> 2) & 1);
         uint32_t a[4];
         afn(kt, a);
         const uint4 *slab = reinterpret_cast<const uint4 *>(&sm.ring[stage][(j & 3) * kSlabBytes]);
@@ -262,6 +271,133 @@ __device__ __forceinline__ float gather_blend(const nsb_field_params &P, float x
     return result;
 }
 
+// -------------------------------------------------------------------------------------------
+// Tensor-core variant of the gather: the sum over the 32 ensemble members IS a dense contraction
+//   out[line, f] = sum_m V[line, m, f] * cw[m]          (line = one (level, corner) table entry)
+// so it runs as mma.sync m16n8k16 with A = 16 table lines x 16 halfs straight from the LDG
+// registers (no conversion instructions), B = the sample's blend weights (fp16, like the
+// reference: hash_ensemble.py:155 casts the code to half), fp32 accumulate.
+//   m-tile t: rows 0-7 = level 2t corners 0-7, rows 8-15 = level 2t+1 corners 0-7.
+//   lane (g,q) owns corner g of every level and loads bytes [32q,32q+32) of its two lines with one
+//   256-bit LDG each (LDG.E.256: 4 lanes cover a whole 128 B line, so every table line is ONE L2/DRAM
+//   request -- two 64 B half-line requests hit the DRAM access-rate limit, profiles/r1 notes);
+//   k-step s uses words s and 4+s, i.e. k=2q,2q+1 <-> member 8q+s (f0,f1) and k=2q+8,2q+9 <->
+//   member 8q+4+s.  B[k][n] = cw[member(k)] * (feat(k)==n), n<2.
+//   C (lanes q==0): c0,c1 = (level 2t, corner g, f0/f1); c2,c3 = (level 2t+1, corner g, f0/f1).
+// Epilogue: times the lane's trilinear corner weight, then a 28-shuffle transposing butterfly
+// over the corner lanes.  Returns feature `lane` (= level*2+feat) in every lane.
+// -------------------------------------------------------------------------------------------
+struct BlendB {
+    uint32_t lo[4], hi[4];  // B fragments of the 4 k-steps (b0, b1)
+};
+
+__device__ __forceinline__ BlendB make_blend_b(const nsb_field_opts &O, const float *code_row, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    BlendB B;
+    const float4 c0 = __ldg(reinterpret_cast<const float4 *>(code_row) + 2 * q);
+    const float4 c1 = __ldg(reinterpret_cast<const float4 *>(code_row) + 2 * q + 1);
+    const float lo[4] = {c0.x, c0.y, c0.z, c0.w}, hi[4] = {c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float a = fmaf(lo[s], O.cw_scale[8 * q + s], O.cw_bias[8 * q + s]);
+        const float b = fmaf(hi[s], O.cw_scale[8 * q + 4 + s], O.cw_bias[8 * q + 4 + s]);
+        const uint32_t ha = __half_as_ushort(__float2half_rn(a)), hb = __half_as_ushort(__float2half_rn(b));
+        B.lo[s] = g == 0 ? ha : (g == 1 ? (ha << 16) : 0u);
+        B.hi[s] = g == 0 ? hb : (g == 1 ? (hb << 16) : 0u);
+    }
+    return B;
+}
+
+// One m-tile (2 levels) of loads for this lane's corner: 2 lines x 2 chunks of 16 B, plus the
+// lane's trilinear corner weights.
+struct GatherTile {
+    uint32_t v[2][8];   // row g (level 2t) / row g+8 (level 2t+1): members 8q..8q+7, (f0,f1) each
+    float w[2];
+};
+
+// 256-bit read-only global load (sm_100+: LDG.E.256)
+__device__ __forceinline__ void ldg256(const void *p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+template <int T>
+__device__ __forceinline__ void gather_issue(const nsb_field_params &P, const uint8_t *tab, float x, float y, float z,
+                                             uint32_t dx, uint32_t dy, uint32_t dz, GatherTile &G) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        constexpr int dummy = 0; (void)dummy;
+        const int l = 2 * T + i;
+        const float scale = P.levels.scale[l];
+        const uint32_t res = P.levels.res[l], ent = P.levels.entries[l], off = P.levels.offset[l];
+        const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+        const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+        const float fx = px - flx, fy = py - fly, fz = pz - flz;
+        const uint32_t cx = (uint32_t)(int)flx + dx, cy = (uint32_t)(int)fly + dy, cz = (uint32_t)(int)flz + dz;
+        G.w[i] = ((dx ? fx : 1.0f - fx) * (dy ? fy : 1.0f - fy)) * (dz ? fz : 1.0f - fz);
+        uint32_t idx;
+        if (P.levels.hashed[l]) {
+            idx = (cx ^ (cy * kPrimeY) ^ (cz * kPrimeZ)) & (ent - 1);   // hashed levels: entries = 2^log2T
+        } else {
+            idx = cx + cy * res + cz * res * res;                         // < 2*entries: `% entries` is one subtract
+            idx = idx >= ent ? idx - ent : idx;
+        }
+        ldg256(tab + (size_t)(off + idx) * 128, G.v[i]);
+    }
+}
+
+// 4 HMMAs + corner-weight scaling + the butterfly stages over lane bits 2 (feat) and 3 (level parity)
+__device__ __forceinline__ float gather_consume(const GatherTile &G, const BlendB &B, int lane) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t a[4] = {G.v[0][s], G.v[1][s], G.v[0][4 + s], G.v[1][4 + s]};
+        mma16816(c, a, B.lo[s], B.hi[s]);
+    }
+    const float u0 = butterfly(c[0] * G.w[0], c[1] * G.w[0], 2, lane);
+    const float u1 = butterfly(c[2] * G.w[1], c[3] * G.w[1], 2, lane);
+    return butterfly(u0, u1, 3, lane);
+}
+
+// Software-pipelined gather of one sample: the loads of m-tile t+1 (and, at the end, of the NEXT
+// sample's m-tile 0) are issued before m-tile t is consumed, so every warp always has 4-8 LDG.128
+// in flight.  Ga must already hold this sample's m-tile 0; on return it holds the next sample's
+// m-tile 0 (if has_next).  Returns feature `lane` (= level*2+feat) in every lane.
+__device__ __forceinline__ float gather_sample_pipelined(const nsb_field_params &P, const uint8_t *tab, float x,
+                                                         float y, float z, bool has_next, float nx, float ny, float nz,
+                                                         const BlendB &B, GatherTile &Ga, int lane) {
+    const int g = lane >> 2;
+    const uint32_t dx = g & 1, dy = (g >> 1) & 1, dz = g >> 2;
+    GatherTile Gb;
+    float yv[4];
+    float e, o;
+    gather_issue<1>(P, tab, x, y, z, dx, dy, dz, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue<2>(P, tab, x, y, z, dx, dy, dz, Ga); o = gather_consume(Gb, B, lane); yv[0] = butterfly(e, o, 4, lane);
+    gather_issue<3>(P, tab, x, y, z, dx, dy, dz, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue<4>(P, tab, x, y, z, dx, dy, dz, Ga); o = gather_consume(Gb, B, lane); yv[1] = butterfly(e, o, 4, lane);
+    gather_issue<5>(P, tab, x, y, z, dx, dy, dz, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue<6>(P, tab, x, y, z, dx, dy, dz, Ga); o = gather_consume(Gb, B, lane); yv[2] = butterfly(e, o, 4, lane);
+    gather_issue<7>(P, tab, x, y, z, dx, dy, dz, Gb); e = gather_consume(Ga, B, lane);
+    if (has_next) gather_issue<0>(P, tab, nx, ny, nz, dx, dy, dz, Ga);
+    o = gather_consume(Gb, B, lane); yv[3] = butterfly(e, o, 4, lane);
+    // lanes (g, q==0) hold out[8k+g] in yv[k]; deliver out[lane] to every lane
+    const int src = (lane & 7) * 4;
+    const float s0 = __shfl_sync(0xffffffffu, yv[0], src), s1 = __shfl_sync(0xffffffffu, yv[1], src);
+    const float s2 = __shfl_sync(0xffffffffu, yv[2], src), s3 = __shfl_sync(0xffffffffu, yv[3], src);
+    const int k = lane >> 3;
+    return k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3));
+}
+
+__device__ __forceinline__ float gather_blend_mma(const nsb_field_params &P, float x, float y, float z,
+                                                  const BlendB &B, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const uint8_t *tab = reinterpret_cast<const uint8_t *>(P.tables) + q * 32;
+    GatherTile Ga;
+    gather_issue<0>(P, tab, x, y, z, g & 1, (g >> 1) & 1, g >> 2, Ga);
+    return gather_sample_pipelined(P, tab, x, y, z, false, 0.f, 0.f, 0.f, B, Ga, lane);
+}
+
 // effective blend weights of this lane's 4 members for a sample (hash_ensemble.py:119-139 folded)
 __device__ __forceinline__ void load_cw(const FieldArgs &A, const float *code_row, int mg, float (&cw)[4]) {
     float4 c = __ldg(reinterpret_cast<const float4 *>(code_row) + mg);
@@ -276,8 +412,10 @@ __device__ __forceinline__ void load_cw(const FieldArgs &A, const float *code_ro
 // -------------------------------------------------------------------------------------------
 template <bool DEFORM, bool FIELD, bool HEAD>
 __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constant__ FieldArgs A) {
-    extern __shared__ uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // NOTE: no integer round-trip on the pointer, or the compiler loses the shared address space and
+    // emits generic LD/ST instead of LDS/STS (seen in profiles/r1b).
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = A.S.n_samples;
     const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
@@ -298,6 +436,17 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
         }
     }
     __syncthreads();
+    // The two co-resident CTAs of an SM run identical tile sequences and would stay in lock-step
+    // (both in the tensor-bound deformation phase, then both in the memory-bound gather).  Starting the
+    // second wave half a tile later keeps one CTA gathering while the other deforms.
+    if (DEFORM && A.stagger_ns && blockIdx.x >= (gridDim.x + 1) / 2) {
+        uint64_t t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(1000);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < A.stagger_ns);
+    }
 
     // ---- producer warp: stream the deformation weights through the ring, once per tile ----
     if (warp == kConsumerWarps) {
@@ -306,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < kNumChunks; ++c) {
                     const int s = c % kStages;
-                    mbar_wait(&sm.empty[s], ((c / kStages) & 1) ^ 1);
+                    mbar_wait<64>(&sm.empty[s], ((c / kStages) & 1) ^ 1);
                     const uint32_t bytes = (c == kNumChunks - 1) ? (kNumSlabs - c * kChunkSlabs) * kSlabBytes : kChunkBytes;
                     mbar_expect_tx(&sm.full[s], bytes);
                     bulk_g2s(sm.ring[s], src + (size_t)c * kChunkBytes, bytes, &sm.full[s]);
@@ -465,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
                 for (int k = 0; k < 4; ++k) hacc[i][k] = 0.f;
             {
                 constexpr int j = kJ_HEADS;
-                mbar_wait(&sm.full[(j / kChunkSlabs) % kStages], (j / kChunkSlabs / kStages) & 1);
+                mbar_wait<20>(&sm.full[(j / kChunkSlabs) % kStages], (j / kChunkSlabs / kStages) & 1);
                 const uint4 *hw = reinterpret_cast<const uint4 *>(&sm.ring[(j / kChunkSlabs) % kStages][0]);
 #pragma unroll
                 for (int kt = 0; kt < 8; ++kt) {
@@ -527,6 +676,30 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
 
         // ---- stage 3: hash-ensemble gather + blend, one sample at a time, whole warp ----
         const int rows_valid = (int)min((int64_t)16, n - row0);
+#if NSB_GATHER_MMA
+        {
+            const uint8_t *tab = reinterpret_cast<const uint8_t *>(A.P.tables) + q * 32;
+            GatherTile Ga;
+            float4 xs = *reinterpret_cast<const float4 *>(ws.xs[0]);
+            if (rows_valid > 0) gather_issue<0>(A.P, tab, xs.x, xs.y, xs.z, g & 1, (g >> 1) & 1, g >> 2, Ga);
+            for (int r = 0; r < 16; ++r) {
+                float val = 0.f;
+                if (r < rows_valid) {
+                    const float *code_row = A.S.sample_blend_codes
+                                                ? A.S.sample_blend_codes + (row0 + r) * NSB_MEMBERS
+                                                : A.P.blend_codes + (size_t)__float_as_int(ws.pos[r][3]) * NSB_MEMBERS;
+                    const BlendB Bf = make_blend_b(A.O, code_row, lane);
+                    const bool has_next = r + 1 < rows_valid;
+                    const float4 nx = *reinterpret_cast<const float4 *>(ws.xs[has_next ? r + 1 : r]);
+                    val = gather_sample_pipelined(A.P, tab, xs.x, xs.y, xs.z, has_next, nx.x, nx.y, nx.z, Bf, Ga, lane);
+                    xs = nx;
+                    if (A.out.feat)
+                        reinterpret_cast<__half *>(A.out.feat)[(row0 + r) * 32 + lane] = __float2half_rn(val);
+                }
+                ws.feat[r * kFeatStride + lane] = __float2half_rn(val);
+            }
+        }
+#else
         for (int r = 0; r < 16; ++r) {
             float val = 0.f;
             if (r < rows_valid) {
@@ -536,12 +709,13 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
                                             : A.P.blend_codes + (size_t)__float_as_int(ws.pos[r][3]) * NSB_MEMBERS;
                 float cw[4];
                 load_cw(A, code_row, lane & 7, cw);
-                val = gather_blend<2>(A.P, xs.x, xs.y, xs.z, cw, lane);
+                val = gather_blend<kGatherLB>(A.P, xs.x, xs.y, xs.z, cw, lane);
                 if (A.out.feat)
                     reinterpret_cast<__half *>(A.out.feat)[(row0 + r) * 32 + lane] = __float2half_rn(val);
             }
             ws.feat[r * kFeatStride + lane] = __float2half_rn(val);
         }
+#endif
         __syncwarp();
 
         // ---- stage 4: density MLP 32 -> 64 -> 16 (tcnn FullyFusedMLP, no bias) ----
@@ -635,6 +809,10 @@ __global__ void __launch_bounds__(256) hash_blend_kernel(const __grid_constant__
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t s = warp_global; s < H.n; s += n_warps) {
         const float x = H.x[3 * s + 0], y = H.x[3 * s + 1], z = H.x[3 * s + 2];
+#if NSB_GATHER_MMA
+        const BlendB Bf = make_blend_b(H.O, H.codes + s * NSB_MEMBERS, lane);
+        const float val = gather_blend_mma(H.P, x, y, z, Bf, lane);
+#else
         const int mg = lane & 7;
         float4 c = __ldg(reinterpret_cast<const float4 *>(H.codes + s * NSB_MEMBERS) + mg);
         float cw[4];
@@ -643,6 +821,7 @@ __global__ void __launch_bounds__(256) hash_blend_kernel(const __grid_constant__
         cw[2] = fmaf(c.z, H.O.cw_scale[4 * mg + 2], H.O.cw_bias[4 * mg + 2]);
         cw[3] = fmaf(c.w, H.O.cw_scale[4 * mg + 3], H.O.cw_bias[4 * mg + 3]);
         const float val = gather_blend<2>(H.P, x, y, z, cw, lane);
+#endif
         if (H.out_is_half)
             reinterpret_cast<__half *>(H.out)[s * 32 + lane] = __float2half_rn(val);
         else
@@ -666,7 +845,7 @@ static int num_sms() {
 
 template <bool D, bool F, bool H>
 static int launch_field(const FieldArgs &A, cudaStream_t st) {
-    const size_t smem = sizeof(Smem) + 128;
+    const size_t smem = sizeof(Smem);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(field_kernel<D, F, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -677,7 +856,12 @@ static int launch_field(const FieldArgs &A, cudaStream_t st) {
         configured = true;
     }
     const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
-    const int grid = (int)std::min<int64_t>(n_tiles, 2 * (int64_t)num_sms());
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        const char *e = getenv("NSB_CTAS_PER_SM");   // tuning/debug knob
+        ctas_per_sm = e ? std::max(1, atoi(e)) : 2;
+    }
+    const int grid = (int)std::min<int64_t>(n_tiles, ctas_per_sm * (int64_t)num_sms());
     field_kernel<D, F, H><<<grid, kThreads, smem, st>>>(A);
     return check_launch("field_kernel");
 }
@@ -713,6 +897,14 @@ extern "C" int nsb_field_forward(const nsb_field_params *params, const nsb_field
     FieldArgs A;
     A.P = *params; A.O = *opts; A.S = *samples; A.out = *out;
     for (int k = 0; k < 3; ++k) A.aabb_size[k] = params->aabb[3 + k] - params->aabb[k];
+    {
+        static int stagger = -1;
+        if (stagger < 0) {
+            const char *e = getenv("NSB_STAGGER_NS");
+            stagger = e ? atoi(e) : 0;
+        }
+        A.stagger_ns = (uint32_t)stagger;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (deform) {
         if (!need_field) return launch_field<true, false, false>(A, st);
