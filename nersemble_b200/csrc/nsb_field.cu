@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
                 vr[2 * k + 1] = rsel ? b1 : a1;
             }
             const int r = g + 8 * rsel;
-            const float p[3] = {pn[rsel][0], pn[rsel][1], pn[rsel][2]};
+            const float p[3] = {rsel ? pn[1][0] : pn[0][0], rsel ? pn[1][1] : pn[0][1], rsel ? pn[1][2] : pn[0][2]};
             const float v[3] = {vr[0], vr[1], vr[2]}, rr[3] = {vr[3], vr[4], vr[5]};
             float pw[3];
             se3_apply(p, rr, v, pw);
@@ -790,6 +790,505 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
     }
 }
 
+// ===========================================================================================
+// v2: warp-specialised persistent kernel, 1 CTA per SM (profiles/r1: with every warp doing every stage the
+// gather is latency-bound on the number of gathering warps and cannot overlap the deformation phase).
+//   4 TENSOR warps (120 regs): deformation MLP of tile i+1 (32 rows each, B fragments reused by two
+//     m-tiles), then density+colour MLPs of tile i.  Tensor warp 0 lane 0 also refills the weight ring.
+//   24 GATHER warps (64 regs): nothing but the hash-ensemble gather; rows of a tile are claimed
+//     dynamically; each warp keeps 2 m-tiles (2 x 2 LDG.256) in flight.
+// Hand-off through shared memory, double-buffered by tile parity, two mbarrier arrays:
+//   xs_full[b]   tensor -> gather : warped positions of tile i are in sm.xs[b]
+//   feat_full[b] gather -> tensor : blended features of tile i are in sm.feat[b]
+// The reverse (buffer-free) edges are implied by program order: tensor warps issue D(i+2) only after
+// F(i), which waited for feat_full(i), i.e. for every gather warp to be done with tile i.
+// ===========================================================================================
+#ifndef NSB_WS_MT
+#define NSB_WS_MT 1
+#endif
+constexpr int kMT = NSB_WS_MT;                    // m-tiles (16 rows) per tensor warp
+constexpr int kTRows = 16 * kMT;                  // rows per tensor warp
+constexpr int kTensorWarps = NSB_TILE / kTRows;   // 8 (kMT=1) or 4 (kMT=2)
+constexpr int kGatherWarps = 28 - kTensorWarps;   // 20 or 24: 28 warps = 7 warpgroups
+constexpr int kThreadsWS = (kTensorWarps + kGatherWarps) * 32;
+// Register budget: 896 threads are launched with 72 registers each (64512 of the SM's 65536).
+// setmaxnreg can only move registers WITHIN the CTA's allocation (inc blocks until a dec released
+// enough -- an inc that exceeds the pool hangs the kernel), so
+//   kTensorWarps*32*kTensorRegs + kGatherWarps*32*kGatherRegs <= 64512.
+constexpr int kGatherRegs = 64;
+constexpr int kTensorRegs = kMT == 1 ? 88 : 120;
+static_assert(kTensorWarps * 32 * kTensorRegs + kGatherWarps * 32 * kGatherRegs <= kThreadsWS * 72, "register pool");
+constexpr int kLaunchBoundWS = kThreadsWS;
+static_assert(kTensorWarps % 4 == 0 && kGatherWarps % 4 == 0, "setmaxnreg works on warpgroups");
+
+struct alignas(16) TensorScratch {
+    float pos[kTRows][4];          // world position xyz, w = timestep (int bits)
+    float dirsel[2][kTRows][4];    // [tile parity] ray direction xyz, w = in-box selector
+    uint4 enc[kMT][3][32];         // posenc A fragments [m-tile][k-tile][lane]
+    uint4 act[2][kMT][8][32];      // [ping-pong][m-tile][k-tile][lane] hidden activations (lane-private)
+};
+
+struct alignas(128) SmemWS {
+    uint8_t ring[kStages][kChunkBytes];
+    uint4 field_w[kFieldPackedU4];
+    float bias[kBiasFloats];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t xs_full[2];
+    uint64_t feat_full[2];
+    int tile_ctr[2];
+    alignas(16) float xs[2][NSB_TILE][4];  // normalised warped position (0 outside the box), w = timestep bits
+    alignas(16) __half feat[2][NSB_TILE * kFeatStride];
+    TensorScratch ts[kTensorWarps];
+};
+
+struct RingRefill {
+    bool active;           // tensor warp 0, lane 0
+    uint32_t gbase;        // global chunk index of this tile's chunk 0
+    uint32_t total;        // chunks this CTA will consume in total
+    const uint8_t *src;
+    __device__ __forceinline__ void issue(SmemWS &sm, uint32_t gt) const {
+        if (active && gt < total) {
+            const uint32_t s = gt % kStages, kf = gt / kStages, c = gt % kNumChunks;
+            mbar_wait<20>(&sm.empty[s], (kf & 1) ^ 1);   // every tensor warp released the previous use
+            const uint32_t bytes = (c == kNumChunks - 1) ? (kNumSlabs - c * kChunkSlabs) * kSlabBytes : kChunkBytes;
+            mbar_expect_tx(&sm.full[s], bytes);
+            bulk_g2s(sm.ring[s], src + (size_t)c * kChunkBytes, bytes, &sm.full[s]);
+        }
+    }
+};
+
+// one N-half of a deformation layer for TWO m-tiles (32 rows): each B fragment pair feeds 4 HMMAs
+template <class AFn>
+__device__ __forceinline__ void ring_gemm2(float (&acc)[kMT][8][4], const int j0, const int KT, AFn &&afn, SmemWS &sm,
+                                           const RingRefill &rf, int lane) {
+    static_assert(kChunkSlabs == 4 && kStages == 4 && kNumChunks % (2 * kStages) == 0, "ring index arithmetic");
+#pragma unroll 2
+    for (int kt = 0; kt < KT; ++kt) {
+        const int j = j0 + kt;
+        const int chunk = j >> 2, stage = chunk & 3;
+        if ((j & 3) == 0) {
+            rf.issue(sm, rf.gbase + chunk + (kStages - 1));   // refill three chunks ahead
+            __syncwarp();
+            mbar_wait<20>(&sm.full[stage], (chunk >> 2) & 1);
+        }
+        uint32_t a[kMT][4];
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) afn(m, kt, a[m]);
+        const uint4 *slab = reinterpret_cast<const uint4 *>(&sm.ring[stage][(j & 3) * kSlabBytes]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint4 b = slab[p * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < kMT; ++m) {
+                mma16816(acc[m][2 * p], a[m], b.x, b.y);
+                mma16816(acc[m][2 * p + 1], a[m], b.z, b.w);
+            }
+        }
+        if ((j & 3) == 3) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        }
+    }
+}
+
+// bias + ReLU + pack one N-half of both m-tiles straight into the ping-pong activation buffer
+template <int HALF>
+__device__ __forceinline__ void relu_store2(const float (&acc)[kMT][8][4], uint4 (*dst)[8][32], const float *bias, int q,
+                                            int lane) {
+#pragma unroll
+    for (int m = 0; m < kMT; ++m) {
+        uint4 t[4];
+        relu_pack<HALF>(acc[m], t, bias, q);
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) dst[m][HALF * 4 + kt][lane] = t[kt];
+    }
+}
+
+__device__ __forceinline__ void zero_acc2(float (&acc)[kMT][8][4]) {
+#pragma unroll
+    for (int m = 0; m < kMT; ++m) zero_acc(acc[m]);
+}
+
+// density + colour MLPs for one m-tile (16 rows); feat rows / dirsel rows are this m-tile's row 0
+template <bool HEAD>
+__device__ __forceinline__ void field_mlp_tile(const FieldArgs &A, const uint4 *field_w, const __half *feat,
+                                               const float (*dirsel)[4], int64_t row0, int64_t n, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    uint32_t fa[2][4];
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+        fa[kt][0] = *reinterpret_cast<const uint32_t *>(&feat[g * kFeatStride + kt * 16 + 2 * q]);
+        fa[kt][1] = *reinterpret_cast<const uint32_t *>(&feat[(g + 8) * kFeatStride + kt * 16 + 2 * q]);
+        fa[kt][2] = *reinterpret_cast<const uint32_t *>(&feat[g * kFeatStride + kt * 16 + 2 * q + 8]);
+        fa[kt][3] = *reinterpret_cast<const uint32_t *>(&feat[(g + 8) * kFeatStride + kt * 16 + 2 * q + 8]);
+    }
+    float b0acc[8][4];
+    smem_gemm<2, 4>(b0acc, fa, field_w, lane);
+    uint32_t h1[4][4];
+    relu_pack_nobias<8>(b0acc, h1);
+    float b1acc[2][4];
+    smem_gemm<4, 1>(b1acc, h1, field_w + 256, lane);
+    const float sel0 = dirsel[g][3], sel1 = dirsel[g + 8][3];
+    if (q == 0 && A.out.sigma) {
+        if (row0 + g < n) A.out.sigma[row0 + g] = expf(b1acc[0][0]) * sel0;
+        if (row0 + g + 8 < n) A.out.sigma[row0 + g + 8] = expf(b1acc[0][2]) * sel1;
+    }
+    if (!HEAD) return;
+    uint32_t ha[2][4];
+    {
+        float g00 = b1acc[0][0], g02 = b1acc[0][2];
+        if (q == 0) { g00 = 1.0f; g02 = 1.0f; }
+        ha[0][0] = pack_h2(g00, b1acc[0][1]);
+        ha[0][1] = pack_h2(g02, b1acc[0][3]);
+        ha[0][2] = pack_h2(b1acc[1][0], b1acc[1][1]);
+        ha[0][3] = pack_h2(b1acc[1][2], b1acc[1][3]);
+        float e[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = g + 8 * h;
+            const float d0 = (dirsel[r][0] + 1.0f) / 2.0f, d1 = (dirsel[r][1] + 1.0f) / 2.0f,
+                        d2 = (dirsel[r][2] + 1.0f) / 2.0f;
+            e[h][0] = q == 0 ? d0 : (q == 1 ? d2 : 1.0f);
+            e[h][1] = q == 0 ? d1 : 1.0f;
+        }
+        ha[1][0] = pack_h2(e[0][0], e[0][1]);
+        ha[1][1] = pack_h2(e[1][0], e[1][1]);
+        ha[1][2] = pack_h2(1.0f, 1.0f);
+        ha[1][3] = pack_h2(1.0f, 1.0f);
+    }
+    float c0acc[8][4];
+    smem_gemm<2, 4>(c0acc, ha, field_w + 384, lane);
+    uint32_t c1in[4][4];
+    relu_pack_nobias<8>(c0acc, c1in);
+    float c1acc[8][4];
+    smem_gemm<4, 4>(c1acc, c1in, field_w + 640, lane);
+    uint32_t c2in[4][4];
+    relu_pack_nobias<8>(c1acc, c2in);
+    float c2acc[2][4];
+    smem_gemm<4, 1>(c2acc, c2in, field_w + 1152, lane);
+    if (A.out.rgb) {
+        const int64_t sa = row0 + g, sb = row0 + g + 8;
+        if (q == 0) {
+            if (sa < n) { A.out.rgb[3 * sa + 0] = 1.f / (1.f + expf(-c2acc[0][0])); A.out.rgb[3 * sa + 1] = 1.f / (1.f + expf(-c2acc[0][1])); }
+            if (sb < n) { A.out.rgb[3 * sb + 0] = 1.f / (1.f + expf(-c2acc[0][2])); A.out.rgb[3 * sb + 1] = 1.f / (1.f + expf(-c2acc[0][3])); }
+        } else if (q == 1) {
+            if (sa < n) A.out.rgb[3 * sa + 2] = 1.f / (1.f + expf(-c2acc[0][0]));
+            if (sb < n) A.out.rgb[3 * sb + 2] = 1.f / (1.f + expf(-c2acc[0][2]));
+        }
+    }
+}
+
+template <bool DEFORM, bool FIELD, bool HEAD>
+__global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __grid_constant__ FieldArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = A.S.n_samples;
+    const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (FIELD) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.P.field_packed);
+        for (int i = tid; i < kFieldPackedU4; i += kThreadsWS) sm.field_w[i] = __ldg(src + i);
+    }
+    if (DEFORM)
+        for (int i = tid; i < kBiasFloats; i += kThreadsWS) sm.bias[i] = __ldg(A.P.deform_bias + i);
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kTensorWarps);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm.xs_full[b], kTensorWarps);
+            mbar_init(&sm.feat_full[b], kGatherWarps);
+            sm.tile_ctr[b] = 0;
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp >= kTensorWarps) {
+        // =============================== GATHER warps ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+        if (!FIELD) return;
+        const int g = lane >> 2, q = lane & 3;
+        const uint8_t *tab = reinterpret_cast<const uint8_t *>(A.P.tables) + q * 32;
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int64_t tile = blockIdx.x + it * gridDim.x;
+            const int b = (int)(it & 1);
+            const int rows_valid = (int)min((int64_t)NSB_TILE, n - tile * NSB_TILE);
+            mbar_wait<20>(&sm.xs_full[b], (uint32_t)(it >> 1) & 1);
+            int row = 0, nrow = 0;
+            if (lane == 0) { row = atomicAdd(&sm.tile_ctr[b], 1); nrow = atomicAdd(&sm.tile_ctr[b], 1); }
+            row = __shfl_sync(0xffffffffu, row, 0);
+            nrow = __shfl_sync(0xffffffffu, nrow, 0);
+            GatherTile Ga;
+            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows_valid) {
+                xs = *reinterpret_cast<const float4 *>(sm.xs[b][row]);
+                gather_issue<0>(A.P, tab, xs.x, xs.y, xs.z, g & 1, (g >> 1) & 1, g >> 2, Ga);
+            }
+            while (row < rows_valid) {
+                const float *code_row = A.S.sample_blend_codes
+                                            ? A.S.sample_blend_codes + (tile * NSB_TILE + row) * NSB_MEMBERS
+                                            : A.P.blend_codes + (size_t)__float_as_int(xs.w) * NSB_MEMBERS;
+                const BlendB Bf = make_blend_b(A.O, code_row, lane);
+                const bool has_next = nrow < rows_valid;
+                const float4 nx = *reinterpret_cast<const float4 *>(sm.xs[b][has_next ? nrow : row]);
+                const float val = gather_sample_pipelined(A.P, tab, xs.x, xs.y, xs.z, has_next, nx.x, nx.y, nx.z, Bf, Ga, lane);
+                sm.feat[b][row * kFeatStride + lane] = __float2half_rn(val);
+                if (A.out.feat)
+                    reinterpret_cast<__half *>(A.out.feat)[(tile * NSB_TILE + row) * 32 + lane] = __float2half_rn(val);
+                row = nrow;
+                xs = nx;
+                if (has_next) {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(&sm.tile_ctr[b], 1);
+                    nrow = __shfl_sync(0xffffffffu, t, 0);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.feat_full[b]);
+        }
+        return;
+    }
+
+    // =============================== TENSOR warps ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+    TensorScratch &ts = sm.ts[warp];
+    const int g = lane >> 2, q = lane & 3;
+    const float amin0 = A.P.aabb[0], amin1 = A.P.aabb[1], amin2 = A.P.aabb[2];
+    RingRefill rf;
+    rf.active = DEFORM && warp == 0 && lane == 0;
+    rf.total = (uint32_t)(my_tiles * kNumChunks);
+    rf.src = reinterpret_cast<const uint8_t *>(A.P.deform_packed);
+    rf.gbase = 0;
+    if (DEFORM) {
+        for (uint32_t c = 0; c < kStages - 1; ++c) rf.issue(sm, c);
+        __syncwarp();
+    }
+
+    // D(i): per-row inputs + deformation of tile iteration `it` -> sm.xs[it&1]
+    auto deform_stage = [&](int64_t it) {
+        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int b = (int)(it & 1);
+        const int64_t row0 = tile * NSB_TILE + warp * kTRows;
+        __syncwarp();
+        if (lane < kTRows) {   // one row per lane
+            const int64_t s = row0 + lane;
+            float px = 0.f, py = 0.f, pz = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f, tt = 0.f;
+            if (s < n) {
+                if (A.S.origins != nullptr) {
+                    const int ri = A.S.ray_indices[s];
+                    const float mid = __fadd_rn(A.S.t_starts[s], A.S.t_ends[s]);
+                    ddx = A.S.directions[3 * (int64_t)ri + 0];
+                    ddy = A.S.directions[3 * (int64_t)ri + 1];
+                    ddz = A.S.directions[3 * (int64_t)ri + 2];
+                    px = __fadd_rn(A.S.origins[3 * (int64_t)ri + 0], __fmul_rn(__fmul_rn(ddx, mid), 0.5f));
+                    py = __fadd_rn(A.S.origins[3 * (int64_t)ri + 1], __fmul_rn(__fmul_rn(ddy, mid), 0.5f));
+                    pz = __fadd_rn(A.S.origins[3 * (int64_t)ri + 2], __fmul_rn(__fmul_rn(ddz, mid), 0.5f));
+                    if (A.S.ray_times) tt = A.S.ray_times[ri];
+                } else {
+                    px = A.S.positions[3 * s + 0]; py = A.S.positions[3 * s + 1]; pz = A.S.positions[3 * s + 2];
+                    ddx = ddy = ddz = 1.0f;
+                    if (A.S.sample_times) tt = A.S.sample_times[s];
+                }
+            }
+            int tsi = __float2int_rn(__fmul_rn(tt, (float)(A.P.n_timesteps - 1)));
+            tsi = min(max(tsi, 0), A.P.n_timesteps - 1);
+            ts.pos[lane][0] = px; ts.pos[lane][1] = py; ts.pos[lane][2] = pz; ts.pos[lane][3] = __int_as_float(tsi);
+            ts.dirsel[b][lane][0] = ddx; ts.dirsel[b][lane][1] = ddy; ts.dirsel[b][lane][2] = ddz;
+        }
+        __syncwarp();
+        float wx = 0.f, wy = 0.f, wz = 0.f;   // warped world position of row `lane`
+        if (DEFORM) {
+            rf.gbase = (uint32_t)(it * kNumChunks);
+            float pn[kMT][2][3];   // [m-tile][row g / g+8][xyz]
+#pragma unroll
+            for (int m = 0; m < kMT; ++m)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = m * 16 + g + 8 * h;
+                    pn[m][h][0] = __fdiv_rn(__fsub_rn(ts.pos[r][0], amin0), A.aabb_size[0]);
+                    pn[m][h][1] = __fdiv_rn(__fsub_rn(ts.pos[r][1], amin1), A.aabb_size[1]);
+                    pn[m][h][2] = __fdiv_rn(__fsub_rn(ts.pos[r][2], amin2), A.aabb_size[2]);
+                }
+#pragma unroll
+            for (int m = 0; m < kMT; ++m)
+#pragma unroll
+                for (int kt = 0; kt < 3; ++kt) {
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int hi = 0; hi < 2; ++hi) {
+                        const int i = kt * 8 + hi * 4 + q;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float e0 = 0.f, e1 = 0.f;
+                            if (i < 21) {
+                                const int d = i / 7, j = i - d * 7;
+                                const float arg = (6.283185307179586f * pn[m][h][d]) * (float)(1 << j);
+                                const float wj = A.O.pe_window[j];
+                                e0 = wj * sinf(arg);
+                                e1 = wj * sinf(arg + 1.5707963267948966f);
+                            } else if (i == 21) {
+                                e0 = 6.283185307179586f * pn[m][h][0];
+                                e1 = 6.283185307179586f * pn[m][h][1];
+                            } else if (i == 22) {
+                                e0 = 6.283185307179586f * pn[m][h][2];
+                            }
+                            w4[hi * 2 + h] = pack_h2(e0, e1);
+                        }
+                    }
+                    ts.enc[m][kt][lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+            const __half *code[kMT][2];
+#pragma unroll
+            for (int m = 0; m < kMT; ++m)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = m * 16 + g + 8 * h;
+                    if (A.S.sample_warp_codes) {
+                        const int64_t sa = min(row0 + r, n - 1);
+                        code[m][h] = reinterpret_cast<const __half *>(A.S.sample_warp_codes) + sa * NSB_WARP_CODE_DIM;
+                    } else {
+                        code[m][h] = reinterpret_cast<const __half *>(A.P.warp_codes) +
+                                     (size_t)__float_as_int(ts.pos[r][3]) * NSB_WARP_CODE_DIM;
+                    }
+                }
+            auto in_a = [&](int m, int kt, uint32_t(&a)[4]) {
+                if (kt < 3) {
+                    const uint4 v = ts.enc[m][kt][lane];
+                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+                } else {
+                    const int kc = kt - 3;
+                    a[0] = __ldg(reinterpret_cast<const uint32_t *>(code[m][0] + kc * 16 + 2 * q));
+                    a[1] = __ldg(reinterpret_cast<const uint32_t *>(code[m][1] + kc * 16 + 2 * q));
+                    a[2] = __ldg(reinterpret_cast<const uint32_t *>(code[m][0] + kc * 16 + 2 * q + 8));
+                    a[3] = __ldg(reinterpret_cast<const uint32_t *>(code[m][1] + kc * 16 + 2 * q + 8));
+                }
+            };
+            float acc[kMT][8][4];
+            // layer l reads act[src] (or the input), writes act[dst]
+            auto hid = [&](int src) {
+                return [&, src](int m, int kt, uint32_t(&a)[4]) {
+                    const uint4 v = ts.act[src][m][kt][lane];
+                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+                };
+            };
+            auto hid1 = hid(1), hid0 = hid(0);
+            auto skip_a = [&](int m, int kt, uint32_t(&a)[4]) {
+                if (kt < 8) hid1(m, kt, a); else in_a(m, kt - 8, a);
+            };
+            // layer 0: input -> act[0]
+            zero_acc2(acc); ring_gemm2(acc, kJ_L0, 11, in_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], sm.bias + 0 * 128, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kJ_L0 + 11, 11, in_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], sm.bias + 0 * 128, q, lane);
+            // layer 1: act[0] -> act[1]
+            zero_acc2(acc); ring_gemm2(acc, kJ_L1, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], sm.bias + 1 * 128, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kJ_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], sm.bias + 1 * 128, q, lane);
+            // layer 2: act[1] -> act[0]
+            zero_acc2(acc); ring_gemm2(acc, kJ_L2, 8, hid1, sm, rf, lane); relu_store2<0>(acc, ts.act[0], sm.bias + 2 * 128, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kJ_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1>(acc, ts.act[0], sm.bias + 2 * 128, q, lane);
+            // layer 3: act[0] -> act[1]
+            zero_acc2(acc); ring_gemm2(acc, kJ_L3, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], sm.bias + 3 * 128, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kJ_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], sm.bias + 3 * 128, q, lane);
+            // layer 4 (skip): [act[1] | input] -> act[0]
+            zero_acc2(acc); ring_gemm2(acc, kJ_L4, 19, skip_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], sm.bias + 4 * 128, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kJ_L4 + 19, 19, skip_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], sm.bias + 4 * 128, q, lane);
+            // layer 5: act[0] -> act[1]
+            zero_acc2(acc); ring_gemm2(acc, kJ_L5, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], sm.bias + 5 * 128, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kJ_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], sm.bias + 5 * 128, q, lane);
+            // heads (chunk 31: slabs 124,125)
+            float hacc[kMT][2][4];
+#pragma unroll
+            for (int m = 0; m < kMT; ++m)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hacc[m][i][k] = 0.f;
+            {
+                constexpr int chunk = kJ_HEADS / kChunkSlabs, stage = chunk % kStages;
+                rf.issue(sm, rf.gbase + chunk + (kStages - 1));
+                __syncwarp();
+                mbar_wait<20>(&sm.full[stage], (chunk / kStages) & 1);
+                const uint4 *hw = reinterpret_cast<const uint4 *>(&sm.ring[stage][0]);
+#pragma unroll
+                for (int kt = 0; kt < 8; ++kt) {
+                    const uint4 bw = hw[kt * 32 + lane];
+#pragma unroll
+                    for (int m = 0; m < kMT; ++m) {
+                        uint32_t am[4];
+                        hid1(m, kt, am);
+                        mma16816(hacc[m][0], am, bw.x, bw.y);
+                        mma16816(hacc[m][1], am, bw.z, bw.w);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[stage]);
+            }
+            const float hb0 = sm.bias[6 * 128 + 2 * q], hb1 = sm.bias[6 * 128 + 2 * q + 1];
+#pragma unroll
+            for (int m = 0; m < kMT; ++m) {
+                const float c0 = hacc[m][0][0] + hb0, c1 = hacc[m][0][1] + hb1, c2 = hacc[m][0][2] + hb0, c3 = hacc[m][0][3] + hb1;
+                const int rsel = q & 1;
+                float vr[6];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int srcl = (lane & ~3) | k;
+                    const float a0 = __shfl_sync(0xffffffffu, c0, srcl), a1 = __shfl_sync(0xffffffffu, c1, srcl);
+                    const float b0 = __shfl_sync(0xffffffffu, c2, srcl), b1 = __shfl_sync(0xffffffffu, c3, srcl);
+                    vr[2 * k] = rsel ? b0 : a0;
+                    vr[2 * k + 1] = rsel ? b1 : a1;
+                }
+                const int r = m * 16 + g + 8 * rsel;
+                const float p[3] = {rsel ? pn[m][1][0] : pn[m][0][0], rsel ? pn[m][1][1] : pn[m][0][1], rsel ? pn[m][1][2] : pn[m][0][2]};
+                const float v[3] = {vr[0], vr[1], vr[2]}, rr[3] = {vr[3], vr[4], vr[5]};
+                float pw[3];
+                se3_apply(p, rr, v, pw);
+                if (q < 2) {
+                    const float o0 = pw[0] - p[0], o1 = pw[1] - p[1], o2 = pw[2] - p[2];
+                    const int64_t s = row0 + r;
+                    if (A.out.offsets && s < n) {
+                        A.out.offsets[3 * s + 0] = o0; A.out.offsets[3 * s + 1] = o1; A.out.offsets[3 * s + 2] = o2;
+                    }
+                    // reuse pos[] as the warped world position (normalised offsets added to world coords: ref quirk)
+                    ts.pos[r][0] += o0; ts.pos[r][1] += o1; ts.pos[r][2] += o2;
+                }
+            }
+            __syncwarp();
+        }
+        if (FIELD && lane < kTRows) {
+            wx = ts.pos[lane][0]; wy = ts.pos[lane][1]; wz = ts.pos[lane][2];
+            float x = __fdiv_rn(__fsub_rn(wx, amin0), A.aabb_size[0]);
+            float y = __fdiv_rn(__fsub_rn(wy, amin1), A.aabb_size[1]);
+            float z = __fdiv_rn(__fsub_rn(wz, amin2), A.aabb_size[2]);
+            const bool sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
+            float4 o4 = make_float4(sel ? x : 0.f, sel ? y : 0.f, sel ? z : 0.f, ts.pos[lane][3]);
+            *reinterpret_cast<float4 *>(sm.xs[b][warp * kTRows + lane]) = o4;
+            ts.dirsel[b][lane][3] = sel ? 1.f : 0.f;
+            if (warp == 0 && lane == 0) sm.tile_ctr[b] = 0;
+        }
+        if (FIELD) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.xs_full[b]);
+        }
+    };
+
+    if (my_tiles > 0) deform_stage(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) deform_stage(it + 1);
+        if (FIELD) {
+            const int64_t tile = blockIdx.x + it * gridDim.x;
+            const int b = (int)(it & 1);
+            mbar_wait<100>(&sm.feat_full[b], (uint32_t)(it >> 1) & 1);
+#pragma unroll 1
+            for (int m = 0; m < kMT; ++m)
+                field_mlp_tile<HEAD>(A, sm.field_w, &sm.feat[b][(warp * kTRows + m * 16) * kFeatStride],
+                                     &ts.dirsel[b][m * 16], tile * NSB_TILE + warp * kTRows + m * 16, n, lane);
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // stand-alone HashEnsemble.forward (component API): one warp per sample, grid-stride
 // -------------------------------------------------------------------------------------------
@@ -843,8 +1342,37 @@ static int num_sms() {
     return g_num_sms;
 }
 
+static int kernel_version() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("NSB_KERNEL");   // 1: SPMD-warp kernel (2 CTAs/SM), 2: warp-specialised (default)
+        v = e ? atoi(e) : 2;
+        if (v != 1) v = 2;
+    }
+    return v;
+}
+
+template <bool D, bool F, bool H>
+static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
+    const size_t smem = sizeof(SmemWS);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(field_kernel_ws<D, F, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(field_kernel_ws): %s", cudaGetErrorString(e));
+            return 1;
+        }
+        configured = true;
+    }
+    const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms());
+    field_kernel_ws<D, F, H><<<grid, kThreadsWS, smem, st>>>(A);
+    return check_launch("field_kernel_ws");
+}
+
 template <bool D, bool F, bool H>
 static int launch_field(const FieldArgs &A, cudaStream_t st) {
+    if (kernel_version() == 2) return launch_field_ws<D, F, H>(A, st);
     const size_t smem = sizeof(Smem);
     static bool configured = false;
     if (!configured) {
