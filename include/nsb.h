@@ -92,6 +92,7 @@ typedef struct nsb_samples {
     /* explicit (used when origins == NULL) */
     const float *positions;    /* [n_samples][3] world */
     const float *sample_times; /* [n_samples] in [0,1] or NULL */
+    const float *sample_directions; /* [n_samples][3] or NULL (density_fn uses ones: nersemble_nerfacto_field.py:240) */
     /* optional per-sample conditioning overriding the time-embedding tables (component APIs) */
     const float *sample_blend_codes; /* float  [n_samples][32] or NULL */
     const void *sample_warp_codes;   /* __half [n_samples][128] or NULL */

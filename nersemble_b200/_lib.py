@@ -39,7 +39,7 @@ class Samples(C.Structure):
     _fields_ = [("n_samples", C.c_int64),
                 ("origins", C.c_void_p), ("directions", C.c_void_p), ("ray_times", C.c_void_p),
                 ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("ray_indices", C.c_void_p),
-                ("positions", C.c_void_p), ("sample_times", C.c_void_p),
+                ("positions", C.c_void_p), ("sample_times", C.c_void_p), ("sample_directions", C.c_void_p),
                 ("sample_blend_codes", C.c_void_p), ("sample_warp_codes", C.c_void_p)]
 
 

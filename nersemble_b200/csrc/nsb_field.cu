@@ -494,6 +494,10 @@ __global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constan
                     py = A.S.positions[3 * s + 1];
                     pz = A.S.positions[3 * s + 2];
                     ddx = ddy = ddz = 1.0f;  // density_fn builds dummy frustums with direction ones
+                    if (A.S.sample_directions) {
+                        ddx = A.S.sample_directions[3 * s + 0]; ddy = A.S.sample_directions[3 * s + 1];
+                        ddz = A.S.sample_directions[3 * s + 2];
+                    }
                     if (A.S.sample_times) tt = A.S.sample_times[s];
                 }
             }
@@ -1092,6 +1096,10 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                 } else {
                     px = A.S.positions[3 * s + 0]; py = A.S.positions[3 * s + 1]; pz = A.S.positions[3 * s + 2];
                     ddx = ddy = ddz = 1.0f;
+                    if (A.S.sample_directions) {
+                        ddx = A.S.sample_directions[3 * s + 0]; ddy = A.S.sample_directions[3 * s + 1];
+                        ddz = A.S.sample_directions[3 * s + 2];
+                    }
                     if (A.S.sample_times) tt = A.S.sample_times[s];
                 }
             }

@@ -39,12 +39,12 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 @dataclass
 class NativeParams:
     """Device-resident parameters in the kernels' layouts (see packing.py)."""
-    tables: torch.Tensor          # half [entries, 32, 2]
+    tables: Optional[torch.Tensor]          # half [entries, 32, 2]
     deform_packed: Optional[torch.Tensor]   # half, fragment order
     deform_bias: Optional[torch.Tensor]     # float [776]
-    field_packed: torch.Tensor    # half, fragment order
+    field_packed: Optional[torch.Tensor]    # half, fragment order
     warp_codes: Optional[torch.Tensor]      # half [T, 128]
-    blend_codes: torch.Tensor     # float [T, 32]
+    blend_codes: Optional[torch.Tensor]     # float [T, 32]
     aabb: torch.Tensor            # float [2,3] (cpu copy kept in aabb_list)
     levels: dict
     n_timesteps: int
@@ -56,25 +56,29 @@ class NativeParams:
             if lv["hashed"][l]:
                 e = lv["entries"][l]
                 assert e & (e - 1) == 0, "hashed levels must have power-of-two size"
-        assert self.tables.dtype == torch.float16 and self.tables.shape[1:] == (32, 2)
-        assert self.tables.shape[0] == lv["total_entries"]
+        if self.tables is not None:
+            assert self.tables.dtype == torch.float16 and self.tables.shape[1:] == (32, 2)
+            assert self.tables.shape[0] == lv["total_entries"]
 
     @staticmethod
-    def build(*, tables, base_w, head_w, time_emb, aabb, levels, deform=None, time_emb_deform=None,
+    def build(*, tables, time_emb, aabb, levels, base_w=None, head_w=None, deform=None, time_emb_deform=None,
               device="cuda") -> "NativeParams":
         """tables: [entries,32,2] (any float dtype); base_w/head_w: lists of [out,in] matrices;
         deform: dict(stem_w, stem_b, r_w, r_b, v_w, v_b) or None."""
         dev = torch.device(device)
-        tab = tables.detach().to(dev).half().contiguous()
-        fp = packing.pack_field([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
+        tab = None if tables is None else tables.detach().to(dev).half().contiguous()
+        fp = None
+        if base_w is not None:
+            fp = packing.pack_field([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
         dp = db = wc = None
         if deform is not None:
             dp, db = packing.pack_deform([w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]],
                                          deform["r_w"].to(dev), deform["r_b"].to(dev),
                                          deform["v_w"].to(dev), deform["v_b"].to(dev))
             wc = time_emb_deform.detach().to(dev).half().contiguous()
-        return NativeParams(tab, dp, db, fp, wc, time_emb.detach().to(dev).float().contiguous(),
-                            aabb.detach().float().cpu(), levels, int(time_emb.shape[0]))
+        te = None if time_emb is None else time_emb.detach().to(dev).float().contiguous()
+        n_t = int(time_emb.shape[0]) if time_emb is not None else (int(time_emb_deform.shape[0]) if time_emb_deform is not None else 1)
+        return NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
 
     def c_params(self) -> _lib.FieldParams:
         p = _lib.FieldParams()
@@ -114,7 +118,8 @@ def make_opts(window_hash: Optional[float], window_deform: Optional[float], use_
 
 def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_deformation=True,
                   origins=None, directions=None, ray_times=None, t_starts=None, t_ends=None, ray_indices=None,
-                  positions=None, sample_times=None, sample_blend_codes=None, sample_warp_codes=None,
+                  positions=None, sample_times=None, sample_directions=None, sample_blend_codes=None,
+                  sample_warp_codes=None,
                   want: Sequence[str] = ("sigma", "rgb", "offsets"),
                   disable_initial: bool = True, soft_transition: bool = True) -> Dict[str, torch.Tensor]:
     """Fused deformation + hash ensemble + field MLPs for packed samples (nsb_field_forward)."""
@@ -137,8 +142,10 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
         sample_times = None if sample_times is None else _f32c(sample_times).reshape(-1)
         _need_cuda(positions, sample_times)
         n = int(positions.shape[0])
-        s.positions, s.sample_times = _ptr(positions), _ptr(sample_times)
-        keep += [positions, sample_times]
+        sample_directions = None if sample_directions is None else _f32c(sample_directions).reshape(-1, 3)
+        _need_cuda(sample_directions)
+        s.positions, s.sample_times, s.sample_directions = _ptr(positions), _ptr(sample_times), _ptr(sample_directions)
+        keep += [positions, sample_times, sample_directions]
         dev = positions.device
     if sample_blend_codes is not None:
         sample_blend_codes = _f32c(sample_blend_codes)

@@ -1,0 +1,356 @@
+"""NeRSembleNGPModel -- mirror of models/nersemble_instant_ngp.py:39-516 and models/base.py:15-249."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from math import sqrt
+from typing import Dict, List, Optional, Tuple, Type
+
+import torch
+from torch import Tensor, nn
+from torch.nn import Parameter, init
+
+from .. import ops
+from ..nerfstudio_shim import (FieldHeadNames, RayBundle, RaySamples, SceneBox, TrainingCallback,
+                               TrainingCallbackAttributes, TrainingCallbackLocation)
+from .components import (GenericScheduler, HashEnsembleConfig, SE3DeformationField, SE3DeformationFieldConfig,
+                         _no_autograd)
+from .field import NeRSembleNeRFactoField
+from .sampler import NeRSembleVolumetricSampler, OccGridEstimator
+
+
+@dataclass
+class BaseModelConfig:
+    """models/base.py:15-32 (+ the nerfstudio ModelConfig fields the scripts touch)."""
+    enable_collider: bool = False
+    collider_params: Optional[Dict[str, float]] = None
+    loss_coefficients: Optional[Dict[str, float]] = None
+    eval_num_rays_per_chunk: int = 4096
+    use_masked_rgb_loss: bool = False
+    alpha_mask_threshold: float = 0.5
+    lambda_alpha_loss: float = 0
+    lambda_empty_loss: float = 0
+    lambda_near_loss: float = 0
+    lambda_depth_loss: float = 0
+    eps_depth_initial: float = 0.9
+    eps_depth_final: float = 0.01
+    eps_depth_begin_step: int = 0
+    eps_depth_end_step: int = 10000
+    lambda_dist_loss: float = 0
+    dist_loss_max_rays: int = 5000
+
+
+@dataclass
+class NeRSembleNGPModelConfig(BaseModelConfig):
+    """models/nersemble_instant_ngp.py:39-75 on top of nerfstudio InstantNGPModelConfig's defaults."""
+    _target: Type = field(default_factory=lambda: NeRSembleNGPModel)
+    # InstantNGPModelConfig
+    grid_resolution: int = 128
+    grid_levels: int = 4
+    max_res: int = 2048
+    log2_hashmap_size: int = 19
+    alpha_thre: float = 0.01
+    cone_angle: float = 0.004
+    render_step_size: Optional[float] = None
+    near_plane: float = 0.05
+    far_plane: float = 1e3
+    use_appearance_embedding: bool = False
+    background_color: str = "random"
+    disable_scene_contraction: bool = False
+    # NeRSemble
+    n_timesteps: int = 1
+    latent_dim_time: int = 128
+    spherical_harmonics_degree: int = 0
+    use_hash_ensemble: bool = False
+    hash_ensemble_config: Optional[HashEnsembleConfig] = None
+    use_deformation_field: bool = False
+    deformation_field_config: Optional[SE3DeformationFieldConfig] = None
+    use_separate_deformation_time_embedding: bool = True
+    window_deform_begin: int = 0
+    window_deform_end: int = 0
+    window_hash_encodings_begin: int = 0
+    window_hash_encodings_end: int = 1
+    early_stop_eps: float = 1e-4
+    occ_thre: float = 1e-2
+    disable_occupancy_grid: bool = False
+    occupancy_grid_ema_decay: float = 0.95
+    occupancy_grid_warmup_steps: int = 256
+    max_n_samples_per_batch: int = -1
+    use_view_frustum_culling: bool = False
+    view_frustum_culling: int = 2
+
+    def setup(self, **kwargs):
+        return self._target(self, **kwargs)
+
+
+def _segment_exclusive_sum(x: Tensor, ray_indices: Tensor, n_rays: int) -> Tensor:
+    cnt = torch.zeros(n_rays, dtype=torch.long, device=x.device).index_add_(0, ray_indices, torch.ones_like(ray_indices))
+    starts = cnt.cumsum(0) - cnt
+    inc = torch.cumsum(x.double(), 0)
+    before = torch.cat([torch.zeros(1, dtype=torch.float64, device=x.device), inc])[starts]
+    return (inc - x.double() - before[ray_indices]).to(x.dtype)
+
+
+class NeRSembleNGPModel(nn.Module):
+    config: NeRSembleNGPModelConfig
+
+    def __init__(self, config: NeRSembleNGPModelConfig, scene_box: SceneBox, num_train_data: int, **kwargs):
+        super().__init__()
+        self.config = config
+        self.scene_box = scene_box
+        self.num_train_data = num_train_data
+        self.kwargs = kwargs
+        self.collider = None
+        self.populate_modules()
+        self.device_indicator_param = nn.Parameter(torch.empty(0))
+        self._native = None
+        self._native_version = None
+
+    @property
+    def device(self):
+        return self.device_indicator_param.device
+
+    def populate_modules(self):
+        """models/nersemble_instant_ngp.py:81-179 (+ BaseModel.populate_modules, base.py:38-47)."""
+        cfg = self.config
+        if cfg.lambda_empty_loss > 0 or cfg.lambda_near_loss > 0:
+            self.sched_eps_depth = GenericScheduler(cfg.eps_depth_initial, cfg.eps_depth_final, cfg.eps_depth_begin_step,
+                                                    cfg.eps_depth_end_step)
+        else:
+            self.sched_eps_depth = None
+        if not cfg.disable_scene_contraction:
+            raise NotImplementedError("scene contraction (the NeRSemble recipe sets disable_scene_contraction=True)")
+        if cfg.background_color != "white":
+            raise NotImplementedError("only background_color='white' (train_nersemble.py:193)")
+        self.field = NeRSembleNeRFactoField(
+            aabb=self.scene_box.aabb, num_images=self.num_train_data, log2_hashmap_size=cfg.log2_hashmap_size,
+            max_res=cfg.max_res, spatial_distortion=None, spherical_harmonics_degree=cfg.spherical_harmonics_degree,
+            use_hash_ensemble=cfg.use_hash_ensemble, hash_ensemble_config=cfg.hash_ensemble_config,
+            use_appearance_embedding=cfg.use_appearance_embedding, max_n_samples_per_batch=cfg.max_n_samples_per_batch)
+        self.deformation_field = None
+        if cfg.use_deformation_field:
+            self.deformation_field = SE3DeformationField(self.scene_box.aabb, cfg.deformation_field_config,
+                                                         max_n_samples_per_batch=cfg.max_n_samples_per_batch)
+        self.time_embedding = None
+        if cfg.use_deformation_field or cfg.use_hash_ensemble:
+            self.time_embedding = nn.Embedding(cfg.n_timesteps, cfg.latent_dim_time)
+            init.normal_(self.time_embedding.weight, mean=0., std=0.01 / sqrt(cfg.latent_dim_time))
+            if cfg.use_separate_deformation_time_embedding:
+                self.time_embedding_deformation = nn.Embedding(cfg.n_timesteps, cfg.deformation_field_config.warp_code_dim)
+                init.normal_(self.time_embedding_deformation.weight, mean=0.,
+                             std=0.01 / sqrt(cfg.deformation_field_config.warp_code_dim))
+        self.scene_aabb = Parameter(self.scene_box.aabb.flatten(), requires_grad=False)
+        if cfg.render_step_size is None:
+            cfg.render_step_size = ((self.scene_aabb[3:] - self.scene_aabb[:3]) ** 2).sum().sqrt().item() / 1000
+        self.occupancy_grid = OccGridEstimator(roi_aabb=self.scene_aabb, resolution=cfg.grid_resolution, levels=cfg.grid_levels)
+        self.sampler = NeRSembleVolumetricSampler(
+            occupancy_grid=self.occupancy_grid, density_fn=self.field_density_fn, scene_aabb=self.scene_box.aabb,
+            camera_frustums=self.kwargs.get('metadata', {}).get('camera_frustums'),
+            view_frustum_culling=cfg.view_frustum_culling if cfg.use_view_frustum_culling else None)
+        self.sched_window_deform = None
+        if cfg.window_deform_end >= 1:
+            self.sched_window_deform = GenericScheduler(0, cfg.deformation_field_config.n_freq_pos,
+                                                        cfg.window_deform_begin, cfg.window_deform_end)
+        self.sched_window_hash_encodings = None
+        if cfg.use_hash_ensemble and cfg.window_hash_encodings_end > 0:
+            self.sched_window_hash_encodings = GenericScheduler(1, cfg.hash_ensemble_config.n_hash_encodings,
+                                                                cfg.window_hash_encodings_begin, cfg.window_hash_encodings_end)
+
+    # ------------------------------------------------------------------ native parameter cache
+    def native_params(self) -> ops.NativeParams:
+        params = [p for p in self.parameters()]
+        v = tuple((p._version, p.data_ptr()) for p in params)
+        if self._native is None or v != self._native_version:
+            with torch.no_grad():
+                cfg = self.config
+                deform = self.deformation_field.se3_field.deform_dict() if self.deformation_field is not None else None
+                if cfg.use_separate_deformation_time_embedding and self.deformation_field is not None:
+                    ted = self.time_embedding_deformation.weight
+                else:
+                    ted = self.time_embedding.weight if deform is not None else None
+                self._native = ops.NativeParams.build(
+                    tables=None, time_emb=self.time_embedding.weight, aabb=self.scene_box.aabb, levels=self.field.hash_ensemble.levels,
+                    base_w=self.field.base_weights(), head_w=self.field.head_weights(), deform=deform, time_emb_deform=ted,
+                    device=self.scene_aabb.device)
+            self._native_version = v
+        self._native.tables = self.field.hash_ensemble.native_tables()
+        return self._native
+
+    def _windows(self):
+        wh = self.sched_window_hash_encodings.value if self.sched_window_hash_encodings is not None else None
+        wd = self.sched_window_deform.value if self.sched_window_deform is not None else None
+        return wh, wd
+
+    def _blend_opts(self):
+        he = self.field.hash_ensemble
+        return dict(disable_initial=he.disable_initial_hash_ensemble, soft_transition=he.use_soft_transition)
+
+    # ------------------------------------------------------------------ callbacks
+    def get_training_callbacks(self, training_callback_attributes: TrainingCallbackAttributes) -> List[TrainingCallback]:
+        """models/nersemble_instant_ngp.py:181-233."""
+
+        def update_occupancy_grid(step: int):
+            self.occupancy_grid.update_every_n_steps(
+                step=step,
+                occ_eval_fn=lambda x: self.field_density_fn(
+                    x, torch.randint(0, self.config.n_timesteps, (x.shape[0], 1), dtype=torch.int, device=x.device) / (
+                        self.config.n_timesteps - 1)) * self.config.render_step_size,
+                n=16, occ_thre=self.config.occ_thre, ema_decay=self.config.occupancy_grid_ema_decay,
+                warmup_steps=self.config.occupancy_grid_warmup_steps)
+
+        callbacks = [TrainingCallback(where_to_run=[TrainingCallbackLocation.BEFORE_TRAIN_ITERATION],
+                                      update_every_num_iters=1, func=update_occupancy_grid)]
+
+        def update_window_param(sched: GenericScheduler, name: str, step: int):
+            sched.update(step)
+
+        for sched, name in ((self.sched_window_deform, "sched_window_deform"),
+                            (self.sched_window_hash_encodings, "sched_window_hash_encodings"),
+                            (self.sched_eps_depth, "sched_eps_depth")):
+            if sched is not None:
+                callbacks.append(TrainingCallback(where_to_run=[TrainingCallbackLocation.BEFORE_TRAIN_ITERATION],
+                                                  update_every_num_iters=1, func=update_window_param, args=[sched, name]))
+        return callbacks
+
+    # ------------------------------------------------------------------ density / outputs
+    def field_density_fn(self, positions: Tensor, times: Optional[Tensor]) -> Tensor:
+        """models/nersemble_instant_ngp.py:235-266: one fused density-only kernel launch."""
+        if self.config.disable_occupancy_grid:
+            return torch.ones((positions.shape[0],), dtype=positions.dtype, device=positions.device)
+        assert times is not None, "Times need to be provided to NeRSemble's density_fn"
+        wh, wd = self._windows()
+        out = ops.field_forward(self.native_params(), window_hash=wh, window_deform=wd,
+                                use_deformation=self.config.use_deformation_field, positions=positions,
+                                sample_times=times.reshape(-1).float(), want=("sigma",), **self._blend_opts())
+        return out["sigma"][:, None]
+
+    def get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None):
+        """models/nersemble_instant_ngp.py:280-364."""
+        cfg = self.config
+        wh, wd = self._windows()
+        num_rays = len(ray_bundle)
+        _no_autograd(*self.parameters())
+        with torch.no_grad():
+            ray_samples, ray_indices = self.sampler(
+                ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
+                render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
+                early_stop_eps=cfg.early_stop_eps, jitter=jitter)
+        if ray_samples.metadata is None:
+            ray_samples.metadata = dict()
+        if ray_bundle.times is not None:
+            ray_times = ray_bundle.times.reshape(-1).float()
+        else:
+            ray_times = ray_bundle.metadata['timesteps'].reshape(-1).float() / max(cfg.n_timesteps - 1, 1)
+        starts = ray_samples.frustums.starts[..., 0].contiguous()
+        ends = ray_samples.frustums.ends[..., 0].contiguous()
+        cnt = torch.zeros(num_rays, dtype=torch.long, device=starts.device).index_add_(
+            0, ray_indices, torch.ones_like(ray_indices))
+        packed_info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)           # nerfacc.pack_info (:325)
+        out = ops.render_packed(self.native_params(), ray_bundle.origins, ray_bundle.directions, ray_times, starts, ends,
+                                ray_indices, packed_info, window_hash=wh, window_deform=wd,
+                                use_deformation=cfg.use_deformation_field, training=self.training, **self._blend_opts())
+        if cfg.use_deformation_field:
+            ray_samples.frustums.set_offsets(out["offsets"])
+        outputs = {
+            "rgb": out["rgb"], "accumulation": out["accumulation"], "depth": out["depth"],
+            "num_samples_per_ray": packed_info[:, 1],
+            "ray_samples": (ray_samples,), "ray_indices": (ray_indices,), "weights": (out["weights"],),
+        }
+        if cfg.use_deformation_field:
+            outputs["deformation"] = out["deformation"]
+        return outputs
+
+    def forward(self, ray_bundle: RayBundle):
+        return self.get_outputs(ray_bundle)
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle: chunk loop; tuple-wrapped outputs are skipped."""
+        n = self.config.eval_num_rays_per_chunk
+        h, w = camera_ray_bundle.origins.shape[:2]
+        lists: Dict[str, list] = {}
+        for i in range(0, h * w, n):
+            rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + n)
+            for name, out in self.forward(ray_bundle=rb).items():
+                if torch.is_tensor(out):
+                    lists.setdefault(name, []).append(out)
+        return {k: torch.cat(v).view(h, w, -1) for k, v in lists.items()}
+
+    # ------------------------------------------------------------------ losses / metrics (models/base.py)
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
+        """models/nersemble_instant_ngp.py:366-407 -> models/base.py:90-249 (plain torch on per-ray/per-sample outputs)."""
+        cfg = self.config
+        ld: Dict[str, Tensor] = {}
+        acc, depth = outputs["accumulation"], outputs["depth"]
+        rs: RaySamples = outputs["ray_samples"][0]
+        ri = outputs["ray_indices"][0]
+        weights = outputs["weights"][0]
+        rgb = outputs["rgb"]
+        image = batch["image"].to(rgb.device)
+        if cfg.use_masked_rgb_loss and "alpha_map" in batch:
+            alpha_per_ray = batch["alpha_map"].squeeze(1).to(rgb.device) / 255.
+            mask = alpha_per_ray > cfg.alpha_mask_threshold
+            ld["rgb_loss"] = torch.nn.functional.mse_loss(image[mask], rgb[mask])
+        else:
+            ld["rgb_loss"] = torch.nn.functional.mse_loss(image, rgb)
+        if cfg.lambda_alpha_loss is not None and cfg.lambda_alpha_loss > 0:
+            alpha_per_ray = batch["alpha_map"].squeeze(1).to(rgb.device) / 255.
+            bg = alpha_per_ray < 1
+            if bg.any():
+                ld["alpha_loss"] = (acc.squeeze(1)[bg] - alpha_per_ray[bg]).abs().mean() * cfg.lambda_alpha_loss
+        starts = rs.frustums.starts.squeeze(1)
+        ends = rs.frustums.ends.squeeze(1)
+        if (cfg.lambda_empty_loss > 0 or cfg.lambda_near_loss > 0) and self.training:
+            eps = self.sched_eps_depth.value
+            tgt_ray = batch["depth_maps"].to(rgb.device)
+            mid = (starts + ends) * 0.5
+            tgt = tgt_ray[ri]
+            w = weights.squeeze(1)
+            if cfg.lambda_empty_loss > 0:
+                vn = (tgt > 0) & (mid < tgt - eps)
+                if vn.any():
+                    ld["empty_loss"] = cfg.lambda_empty_loss * (w[vn] ** 2).mean()
+            if cfg.lambda_near_loss > 0:
+                near = (tgt > 0) & (tgt - eps <= mid) & (mid <= tgt + eps)
+                expected = torch.distributions.Normal(0, (eps / 3) ** 2).cdf(mid - tgt)
+                if near.any():
+                    accumulated = _segment_exclusive_sum(w, ri, acc.shape[0]) + w
+                    ld["near_loss"] = cfg.lambda_near_loss * ((accumulated[near] - expected[near]) ** 2).mean()
+        if cfg.lambda_depth_loss > 0 and self.training:
+            tgt_ray = batch["depth_maps"].to(rgb.device)
+            dm = tgt_ray > 0
+            if dm.any():
+                ld["depth_loss"] = ((tgt_ray[dm] - depth.squeeze()[dm]) ** 2).mean() * cfg.lambda_depth_loss
+        if cfg.lambda_dist_loss > 0:
+            sel = ri < cfg.dist_loss_max_rays
+            w = weights.squeeze(1)[sel]
+            te_, ts_ = ends[sel], starts[sel]
+            m, interval, rid = (te_ + ts_) * 0.5, te_ - ts_, ri[sel]
+            if w.numel():
+                n_rays = int(rid.max()) + 1
+                w_pre = _segment_exclusive_sum(w, rid, n_rays)
+                wm_pre = _segment_exclusive_sum(w * m, rid, n_rays)
+                dist = ((1.0 / 3.0) * (interval * w * w).sum() + 2.0 * (w * (m * w_pre - wm_pre)).sum()) / n_rays
+                ld["dist_loss"] = cfg.lambda_dist_loss * dist
+        return ld
+
+    def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:
+        """models/nersemble_instant_ngp.py:409-422 (PSNR with data_range 1)."""
+        rgb = outputs["rgb"]
+        image = batch["image"].to(rgb.device)
+        psnr = lambda a, b: -10.0 * torch.log10(torch.mean((a - b) ** 2))
+        md = {"psnr": psnr(rgb, image), "num_samples_per_batch": outputs["num_samples_per_ray"].sum()}
+        if "alpha_map" in batch:
+            mask = batch["alpha_map"].squeeze(1).to(rgb.device) > 127
+            md["psnr_masked"] = psnr(rgb[mask], image[mask])
+        return md
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        """models/nersemble_instant_ngp.py:502-514."""
+        groups = {"fields": list(self.field.parameters())}
+        if self.time_embedding is not None:
+            groups["embeddings"] = list(self.time_embedding.parameters())
+            if self.config.use_separate_deformation_time_embedding:
+                groups["embeddings"].extend(list(self.time_embedding_deformation.parameters()))
+        if self.config.use_deformation_field:
+            groups["deformation_field"] = list(self.deformation_field.parameters())
+        return groups

@@ -1,0 +1,95 @@
+"""Plugin surface on CPU: state_dict / param-group compatibility with the real reference model, config
+surface, scheduler semantics, loss restatement vs the reference-glue golden, no-CPU-fallback behaviour."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import load_golden
+from nersemble_b200.nerfstudio_shim import SceneBox
+from nersemble_b200.plugin import (GenericScheduler, HashEnsemble, HashEnsembleConfig, NeRSembleNGPModel,
+                                   NeRSembleNGPModelConfig, SE3DeformationFieldConfig, TCNNHashEncodingConfig)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AABB = torch.tensor([[-2.5, -1.8, -2.5], [2.2, 1.8, 2.0]])
+
+
+def make_model(T=4, log2T=12, **over):
+    kw = dict(render_step_size=0.011, near_plane=0.2, far_plane=1e3, cone_angle=0.0, alpha_thre=1e-2, occ_thre=1e-2,
+              early_stop_eps=0, background_color="white", grid_levels=1, disable_scene_contraction=True, n_timesteps=T,
+              latent_dim_time=32, use_masked_rgb_loss=True, alpha_mask_threshold=0, lambda_alpha_loss=1e-2,
+              lambda_near_loss=1e-4, lambda_empty_loss=1e-2, lambda_depth_loss=1e-4, lambda_dist_loss=1e-4,
+              use_hash_ensemble=True,
+              hash_ensemble_config=HashEnsembleConfig(32, TCNNHashEncodingConfig(log2_hashmap_size=log2T), True, True),
+              use_deformation_field=True, use_separate_deformation_time_embedding=True,
+              deformation_field_config=SE3DeformationFieldConfig(warp_code_dim=128, mlp_num_layers=6, mlp_layer_width=128),
+              window_hash_encodings_begin=40000, window_hash_encodings_end=80000, window_deform_begin=0,
+              window_deform_end=20000, use_view_frustum_culling=False)
+    kw.update(over)
+    cfg = NeRSembleNGPModelConfig(**kw)
+    return cfg.setup(scene_box=SceneBox(AABB.clone()), num_train_data=16, metadata={"camera_frustums": None})
+
+
+def test_state_dict_and_param_groups_match_reference():
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_state_dict.json")))
+    m = make_model()
+    sd = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert sd == ref["state_dict"], (set(sd) ^ set(ref["state_dict"]))
+    assert {k: len(v) for k, v in m.get_param_groups().items()} == ref["param_groups"]
+
+
+def test_scheduler_semantics():
+    s = GenericScheduler(1, 32, 40000, 80000)
+    assert s.value == 32                       # value starts at final (generic_scheduler.py:14)
+    s.update(0); assert s.value == 1
+    s.update(60000); assert abs(s.value - 16.5) < 1e-9
+    s.update(80001); assert s.value == 32
+    s.eval(); s.update(0); assert s.get_value() == 32 and s.value == 1
+
+
+def test_callbacks_drive_schedulers_and_require_training_for_occupancy():
+    m = make_model()
+    cbs = m.get_training_callbacks(None)
+    assert len(cbs) == 4
+    for cb in cbs[1:]:
+        cb.run_callback(10000)
+    assert abs(m.sched_window_deform.value - 3.5) < 1e-9 and m.sched_window_hash_encodings.value == 1
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m.occupancy_grid.update_every_n_steps(0, lambda x: x[:, :1])
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        make_model(disable_scene_contraction=False)
+    with pytest.raises(NotImplementedError):
+        make_model(spherical_harmonics_degree=4)
+    with pytest.raises(AssertionError):
+        HashEnsemble(HashEnsembleConfig(8, TCNNHashEncodingConfig(log2_hashmap_size=4)))
+
+
+def test_no_cpu_fallback():
+    m = make_model(log2T=4)
+    with pytest.raises(RuntimeError, match="CUDA|libnsb"):
+        with torch.no_grad():
+            m.field_density_fn(torch.zeros(4, 3), torch.zeros(4, 1))
+
+
+def test_loss_dict_matches_reference_glue_golden():
+    g, meta = load_golden("losses_train")
+    r, _ = load_golden(meta["render_case"])
+    m = make_model(log2T=4)
+    m.train()
+    m.sched_eps_depth.value = meta["eps_depth"]
+    from nersemble_b200.nerfstudio_shim import Frustums, RaySamples
+    n = r["t_starts"].shape[0]
+    rs = RaySamples(Frustums(torch.zeros(n, 3), torch.zeros(n, 3), r["t_starts"][:, None], r["t_ends"][:, None], torch.zeros(n, 1)))
+    outputs = {"rgb": r["rgb"], "accumulation": r["accumulation"], "depth": r["depth"], "ray_samples": (rs,),
+               "ray_indices": (r["ray_indices"],), "weights": (r["weights"],)}
+    batch = {k[len("batch_"):]: v for k, v in g.items() if k.startswith("batch_")}
+    ld = m.get_loss_dict(outputs, batch)
+    want = {k[len("loss_"):]: v for k, v in g.items() if k.startswith("loss_")}
+    assert set(ld) == set(want)
+    for k in want:
+        torch.testing.assert_close(ld[k].float(), want[k].float(), rtol=1e-4, atol=1e-9)

@@ -1,0 +1,132 @@
+"""Plugin surface on the GPU: NeRSembleNGPModel.get_outputs (sampler + fused field + composite) against the goldens
+produced by the REAL reference model, plus the component modules."""
+import pytest
+import torch
+
+from conftest import load_golden, oracle_params
+from oracle import pipeline as pl
+from oracle.tp.tcnn_cpu import Precision
+from test_plugin_cpu import make_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def load_oracle_params_into(model, P):
+    from nersemble_b200 import packing
+    with torch.no_grad():
+        for c, g in enumerate(packing.tables_to_tcnn(P.tables)):
+            model.field.hash_ensemble.hash_encodings[c].params.copy_(g)
+        model.field.mlp_base.params.copy_(torch.cat([w.reshape(-1) for w in P.base_w]))
+        model.field.mlp_head.params.copy_(torch.cat([w.reshape(-1) for w in P.head_w]))
+        se3 = model.deformation_field.se3_field
+        for i, layer in enumerate(se3.mlp_stem.layers):
+            layer.weight.copy_(P.deform_w[i]); layer.bias.copy_(P.deform_b[i])
+        se3.mlp_r.layers[0].weight.copy_(P.r_w); se3.mlp_r.layers[0].bias.copy_(P.r_b)
+        se3.mlp_v.layers[0].weight.copy_(P.v_w); se3.mlp_v.layers[0].bias.copy_(P.v_b)
+        model.time_embedding.weight.copy_(P.time_emb)
+        model.time_embedding_deformation.weight.copy_(P.time_emb_deform)
+
+
+def _bundle(g):
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    R = g["origins"].shape[0]
+    return RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                     camera_indices=g["camera_indices"].to(DEV), times=g["times"].to(DEV))
+
+
+@pytest.mark.parametrize("name", ["occ_eval_soft", "occ_eval_whash1", "occ_train_prepass"])
+def test_model_get_outputs_vs_reference_golden(name):
+    from oracle.gen_golden import blob_grid
+    g, meta = load_golden(name)
+    P = oracle_params(meta["knobs"])
+    m = make_model(T=meta["knobs"]["n_timesteps"], log2T=meta["knobs"]["log2_hashmap_size"])
+    load_oracle_params_into(m, P)
+    m = m.to(DEV)
+    m.sched_window_hash_encodings.value = meta["w_hash"]
+    m.sched_window_deform.value = meta["w_deform"]
+    occ = blob_grid(meta["grid_seed"])
+    m.occupancy_grid.binaries[0] = occ.to(DEV)
+    m.occupancy_grid.occs.copy_((occ.flatten().float() * 0.05).to(DEV))
+    m.train(meta["training"])
+    jitter = None
+    if meta["training"]:
+        torch.manual_seed(meta["jitter_seed"])
+        jitter = torch.rand(meta["R"]).to(DEV)
+    with torch.no_grad():
+        out = m.get_outputs(_bundle(g), jitter=jitter)
+    rs = out["ray_samples"][0]
+    ri = out["ray_indices"][0].cpu()
+    if not meta["training"]:
+        # eval: no pre-pass -> the marcher alone decides; bit-exact to nerfacc semantics
+        assert torch.equal(ri, g["ray_indices"])
+        assert torch.equal(rs.frustums.starts[:, 0].cpu(), g["t_starts"]) and torch.equal(rs.frustums.ends[:, 0].cpu(), g["t_ends"])
+        torch.testing.assert_close(rs.frustums.offsets.cpu(), g["offsets"], rtol=5e-3, atol=5e-6)
+        torch.testing.assert_close(out["weights"][0].cpu(), g["weights"], rtol=2e-2, atol=1e-4)
+    else:
+        # training: the visibility pre-pass thresholds fp16-path densities; allow a handful of flips
+        assert abs(ri.numel() - g["ray_indices"].numel()) <= max(4, g["ray_indices"].numel() // 200)
+    assert (out["rgb"].cpu() - g["rgb"]).norm(dim=-1).max() < 1e-3
+    torch.testing.assert_close(out["accumulation"].cpu(), g["accumulation"], rtol=0, atol=2e-3)
+    torch.testing.assert_close(out["depth"].cpu(), g["depth"], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(out["deformation"].cpu(), g["deformation"], rtol=2e-2, atol=2e-5)
+    assert out["num_samples_per_ray"].sum().item() == ri.numel()
+
+
+def test_field_density_fn_and_components():
+    g, meta = load_golden("density_fn_kernel")
+    P = oracle_params(meta["knobs"])
+    m = make_model(T=4, log2T=14)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).eval()
+    m.sched_window_hash_encodings.value = meta["w_hash"]
+    m.sched_window_deform.value = meta["w_deform"]
+    with torch.no_grad():
+        sig = m.field_density_fn(g["positions"].to(DEV), g["times"].to(DEV)).cpu()
+    torch.testing.assert_close(sig, g["density"], rtol=5e-3, atol=1e-5)
+    # component modules: HashEnsemble.forward and SE3DeformationField.compute_offsets vs the oracle
+    Precision.mode = "kernel"
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand((300, 3), generator=gen)
+    code = torch.randn((300, 32), generator=gen) * 0.2
+    with torch.no_grad():
+        want = pl.hash_ensemble(P, x, code, 20.25)
+        got = m.field.hash_ensemble(x.to(DEV), code.to(DEV), window_hash_encodings=20.25).float().cpu()
+    assert got.dtype == torch.float32 and ((got - want).abs().max() / want.abs().max()) < 3e-3
+    pos = P.aabb[0] + torch.rand((300, 3), generator=gen) * (P.aabb[1] - P.aabb[0])
+    wc = P.time_emb_deform[torch.randint(0, 4, (300,), generator=gen)]
+    with torch.no_grad():
+        want_o = pl.compute_offsets(P, pos, wc, 5.5)
+        got_o = m.deformation_field.compute_offsets(pos.to(DEV), wc.to(DEV), 5.5).cpu()
+    torch.testing.assert_close(got_o, want_o, rtol=5e-3, atol=5e-6)
+    Precision.mode = "reference"
+
+
+def test_occupancy_update_and_full_frame_render():
+    """update_every_n_steps through the fused density kernel, then a small full-frame render in chunks."""
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    P = oracle_params(dict(seed=19980801, n_timesteps=4, log2_hashmap_size=14, table_scale=0.5, time_std_scale=100.0,
+                           deform_last_scale=1e-3))
+    m = make_model(T=4, log2T=14, eval_num_rays_per_chunk=1000)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).train()
+    cb = m.get_training_callbacks(None)[0]
+    torch.manual_seed(0)
+    cb.run_callback(0)                                    # warm-up step: all 128^3 cells evaluated
+    frac = m.occupancy_grid.binaries.float().mean().item()
+    assert 0.0 < frac < 1.0 and m.occupancy_grid.occs.max() > 0
+    cb.run_callback(256 * 16)                             # post-warm-up path (uniform + occupied cells)
+    m.eval()
+    H, W = 24, 40
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1.5, 1.5, W), indexing="ij")
+    o = torch.tensor([0.0, 0.0, 9.0]).expand(H, W, 3)
+    d = torch.stack([xs, ys, torch.full_like(xs, -9.0)], -1); d = d / d.norm(dim=-1, keepdim=True)
+    rb = RayBundle(origins=o.contiguous().to(DEV), directions=d.to(DEV), pixel_area=torch.ones(H, W, 1, device=DEV),
+                   camera_indices=torch.zeros(H, W, 1, dtype=torch.long, device=DEV), times=torch.full((H, W, 1), 0.34, device=DEV))
+    img = m.get_outputs_for_camera_ray_bundle(rb)
+    assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W, 1) and torch.isfinite(img["rgb"]).all()
+    assert img["rgb"].min() >= 0 and img["rgb"].max() <= 1
+    full = m.get_outputs(RayBundle(origins=rb.origins.view(-1, 3), directions=rb.directions.view(-1, 3),
+                                   pixel_area=rb.pixel_area.view(-1, 1), camera_indices=rb.camera_indices.view(-1, 1),
+                                   times=rb.times.view(-1, 1)))
+    torch.testing.assert_close(img["rgb"].view(-1, 3), full["rgb"], rtol=0, atol=1e-6)   # chunking is exact
