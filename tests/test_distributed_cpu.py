@@ -1,0 +1,34 @@
+"""world_size-2 gloo test of the N>1 host logic (ray sharding + output gather)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nersemble_b200.distributed import gather_rays, shard_bounds, shard_rays
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 5, 4096, 2088960):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _worker(rank, world, port, n):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
+    local = shard_rays({"rgb": full}, rank, world)["rgb"]
+    out = gather_rays(local * 2.0, n)          # "render" = x2 on the local shard
+    assert torch.equal(out, full * 2.0)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_shard_and_gather():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, 101), nprocs=2, join=True)

@@ -126,7 +126,11 @@ def test_occupancy_update_and_full_frame_render():
     img = m.get_outputs_for_camera_ray_bundle(rb)
     assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W, 1) and torch.isfinite(img["rgb"]).all()
     assert img["rgb"].min() >= 0 and img["rgb"].max() <= 1
-    full = m.get_outputs(RayBundle(origins=rb.origins.view(-1, 3), directions=rb.directions.view(-1, 3),
-                                   pixel_area=rb.pixel_area.view(-1, 1), camera_indices=rb.camera_indices.view(-1, 1),
-                                   times=rb.times.view(-1, 1)))
+    flat = RayBundle(origins=rb.origins.view(-1, 3), directions=rb.directions.view(-1, 3),
+                     pixel_area=rb.pixel_area.view(-1, 1), camera_indices=rb.camera_indices.view(-1, 1),
+                     times=rb.times.view(-1, 1))
+    with pytest.raises(NotImplementedError):          # autograd-enabled call: forward-only in round 1, fails loudly
+        m.get_outputs(flat)
+    with torch.no_grad():
+        full = m.get_outputs(flat)
     torch.testing.assert_close(img["rgb"].view(-1, 3), full["rgb"], rtol=0, atol=1e-6)   # chunking is exact
