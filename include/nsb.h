@@ -58,6 +58,10 @@ typedef struct nsb_field_params {
     const void *tables;        /* __half [total_entries][32 members][2 feats]: 128 B per entry */
     const void *deform_packed; /* fp16 deformation weights in MMA-B fragment order (python: pack_deform) */
     const float *deform_bias;  /* float [6*128 + 8]: stem biases, then v_bias(3), r_bias(3), 0, 0 */
+    const void *deform_packed_tb;   /* same weights WITHOUT the warp-code columns of layers 0 and 4 (python: pack_deform_tb) */
+    const float *deform_code_bias;  /* float [n_timesteps][2][128]: W_code(layer 0|4) . warp_code[t] + bias, fp32.  With
+                                       both set, table-indexed warp codes cost no tensor work (-26 % MACs); per-sample
+                                       warp codes (nsb_samples.sample_warp_codes) use deform_packed. */
     const void *field_packed;  /* fp16 mlp_base + mlp_head weights in MMA-B fragment order */
     const void *warp_codes;    /* __half [n_timesteps][128]  (time_embedding_deformation) */
     const float *blend_codes;  /* float  [n_timesteps][32]   (time_embedding) */

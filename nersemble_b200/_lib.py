@@ -26,6 +26,7 @@ class Levels(C.Structure):
 
 class FieldParams(C.Structure):
     _fields_ = [("tables", C.c_void_p), ("deform_packed", C.c_void_p), ("deform_bias", C.c_void_p),
+                ("deform_packed_tb", C.c_void_p), ("deform_code_bias", C.c_void_p),
                 ("field_packed", C.c_void_p), ("warp_codes", C.c_void_p), ("blend_codes", C.c_void_p),
                 ("n_timesteps", C.c_int32), ("aabb", C.c_float * 6), ("levels", Levels)]
 

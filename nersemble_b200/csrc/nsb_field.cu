@@ -823,6 +823,18 @@ constexpr int kGatherRegs = 64;
 constexpr int kTensorRegs = kMT == 1 ? 88 : 120;
 static_assert(kTensorWarps * 32 * kTensorRegs + kGatherWarps * 32 * kGatherRegs <= kThreadsWS * 72, "register pool");
 constexpr int kLaunchBoundWS = kThreadsWS;
+// Slab layout of deform_packed_tb: layers 0 and 4 without their 128 warp-code columns (those enter as the
+// per-timestep bias deform_code_bias[t][0|1][128]).
+constexpr int kT_L0 = 0;                  // 2 x 3
+constexpr int kT_L1 = kT_L0 + 6;          // 2 x 8
+constexpr int kT_L2 = kT_L1 + 16;
+constexpr int kT_L3 = kT_L2 + 16;
+constexpr int kT_L4 = kT_L3 + 16;         // 2 x 11
+constexpr int kT_L5 = kT_L4 + 22;         // 2 x 8
+constexpr int kT_HEADS = kT_L5 + 16;      // 92
+constexpr int kTbNumSlabs = kT_HEADS + 2; // 94
+constexpr int kTbNumChunks = (kTbNumSlabs + kChunkSlabs - 1) / kChunkSlabs;  // 24
+static_assert(kTbNumChunks % (2 * kStages) == 0 && kT_HEADS % kChunkSlabs == 0, "ring parity / heads chunk");
 static_assert(kTensorWarps % 4 == 0 && kGatherWarps % 4 == 0, "setmaxnreg works on warpgroups");
 
 struct alignas(16) TensorScratch {
@@ -853,9 +865,9 @@ struct RingRefill {
     const uint8_t *src;
     __device__ __forceinline__ void issue(SmemWS &sm, uint32_t gt) const {
         if (active && gt < total) {
-            const uint32_t s = gt % kStages, kf = gt / kStages, c = gt % kNumChunks;
+            const uint32_t s = gt % kStages, kf = gt / kStages, c = gt % kTbNumChunks;
             mbar_wait<20>(&sm.empty[s], (kf & 1) ^ 1);   // every tensor warp released the previous use
-            const uint32_t bytes = (c == kNumChunks - 1) ? (kNumSlabs - c * kChunkSlabs) * kSlabBytes : kChunkBytes;
+            const uint32_t bytes = (c == kTbNumChunks - 1) ? (kTbNumSlabs - c * kChunkSlabs) * kSlabBytes : kChunkBytes;
             mbar_expect_tx(&sm.full[s], bytes);
             bulk_g2s(sm.ring[s], src + (size_t)c * kChunkBytes, bytes, &sm.full[s]);
         }
@@ -866,7 +878,7 @@ struct RingRefill {
 template <class AFn>
 __device__ __forceinline__ void ring_gemm2(float (&acc)[kMT][8][4], const int j0, const int KT, AFn &&afn, SmemWS &sm,
                                            const RingRefill &rf, int lane) {
-    static_assert(kChunkSlabs == 4 && kStages == 4 && kNumChunks % (2 * kStages) == 0, "ring index arithmetic");
+    static_assert(kChunkSlabs == 4 && kStages == 4 && kTbNumChunks % (2 * kStages) == 0, "ring index arithmetic");
 #pragma unroll 2
     for (int kt = 0; kt < KT; ++kt) {
         const int j = j0 + kt;
@@ -896,16 +908,26 @@ __device__ __forceinline__ void ring_gemm2(float (&acc)[kMT][8][4], const int j0
     }
 }
 
-// bias + ReLU + pack one N-half of both m-tiles straight into the ping-pong activation buffer
+// bias + ReLU + pack one N-half straight into the ping-pong activation buffer.  bias[m][0|1] = bias row of
+// the m-tile's rows g / g+8 (a shared layer bias, or the per-timestep code bias of layers 0 and 4).
 template <int HALF>
-__device__ __forceinline__ void relu_store2(const float (&acc)[kMT][8][4], uint4 (*dst)[8][32], const float *bias, int q,
-                                            int lane) {
+__device__ __forceinline__ void relu_store2(const float (&acc)[kMT][8][4], uint4 (*dst)[8][32],
+                                            const float *const (&bias)[kMT][2], int q, int lane) {
 #pragma unroll
     for (int m = 0; m < kMT; ++m) {
-        uint4 t[4];
-        relu_pack<HALF>(acc[m], t, bias, q);
 #pragma unroll
-        for (int kt = 0; kt < 4; ++kt) dst[m][HALF * 4 + kt][lane] = t[kt];
+        for (int kt = 0; kt < 4; ++kt) {
+            uint32_t r[4];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int nt = 2 * kt + o, col = HALF * 64 + nt * 8 + 2 * q;
+                const float2 b0 = *reinterpret_cast<const float2 *>(bias[m][0] + col);
+                const float2 b1 = *reinterpret_cast<const float2 *>(bias[m][1] + col);
+                r[o * 2 + 0] = pack_h2(fmaxf(acc[m][nt][0] + b0.x, 0.f), fmaxf(acc[m][nt][1] + b0.y, 0.f));
+                r[o * 2 + 1] = pack_h2(fmaxf(acc[m][nt][2] + b1.x, 0.f), fmaxf(acc[m][nt][3] + b1.y, 0.f));
+            }
+            dst[m][HALF * 4 + kt][lane] = make_uint4(r[0], r[1], r[2], r[3]);
+        }
     }
 }
 
@@ -1065,8 +1087,8 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
     const float amin0 = A.P.aabb[0], amin1 = A.P.aabb[1], amin2 = A.P.aabb[2];
     RingRefill rf;
     rf.active = DEFORM && warp == 0 && lane == 0;
-    rf.total = (uint32_t)(my_tiles * kNumChunks);
-    rf.src = reinterpret_cast<const uint8_t *>(A.P.deform_packed);
+    rf.total = (uint32_t)(my_tiles * kTbNumChunks);
+    rf.src = reinterpret_cast<const uint8_t *>(A.P.deform_packed_tb);
     rf.gbase = 0;
     if (DEFORM) {
         for (uint32_t c = 0; c < kStages - 1; ++c) rf.issue(sm, c);
@@ -1111,7 +1133,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
         __syncwarp();
         float wx = 0.f, wy = 0.f, wz = 0.f;   // warped world position of row `lane`
         if (DEFORM) {
-            rf.gbase = (uint32_t)(it * kNumChunks);
+            rf.gbase = (uint32_t)(it * kTbNumChunks);
             float pn[kMT][2][3];   // [m-tile][row g / g+8][xyz]
 #pragma unroll
             for (int m = 0; m < kMT; ++m)
@@ -1150,31 +1172,16 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                     }
                     ts.enc[m][kt][lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
-            const __half *code[kMT][2];
+            // per-row bias pointers: layers 0/4 use the per-timestep code bias, the others the layer bias
+            const float *cb[kMT][2];
 #pragma unroll
             for (int m = 0; m < kMT; ++m)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = m * 16 + g + 8 * h;
-                    if (A.S.sample_warp_codes) {
-                        const int64_t sa = min(row0 + r, n - 1);
-                        code[m][h] = reinterpret_cast<const __half *>(A.S.sample_warp_codes) + sa * NSB_WARP_CODE_DIM;
-                    } else {
-                        code[m][h] = reinterpret_cast<const __half *>(A.P.warp_codes) +
-                                     (size_t)__float_as_int(ts.pos[r][3]) * NSB_WARP_CODE_DIM;
-                    }
-                }
+                for (int h = 0; h < 2; ++h)
+                    cb[m][h] = A.P.deform_code_bias + (size_t)__float_as_int(ts.pos[m * 16 + g + 8 * h][3]) * 256;
             auto in_a = [&](int m, int kt, uint32_t(&a)[4]) {
-                if (kt < 3) {
-                    const uint4 v = ts.enc[m][kt][lane];
-                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-                } else {
-                    const int kc = kt - 3;
-                    a[0] = __ldg(reinterpret_cast<const uint32_t *>(code[m][0] + kc * 16 + 2 * q));
-                    a[1] = __ldg(reinterpret_cast<const uint32_t *>(code[m][1] + kc * 16 + 2 * q));
-                    a[2] = __ldg(reinterpret_cast<const uint32_t *>(code[m][0] + kc * 16 + 2 * q + 8));
-                    a[3] = __ldg(reinterpret_cast<const uint32_t *>(code[m][1] + kc * 16 + 2 * q + 8));
-                }
+                const uint4 v = ts.enc[m][kt][lane];
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
             };
             float acc[kMT][8][4];
             // layer l reads act[src] (or the input), writes act[dst]
@@ -1188,25 +1195,38 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             auto skip_a = [&](int m, int kt, uint32_t(&a)[4]) {
                 if (kt < 8) hid1(m, kt, a); else in_a(m, kt - 8, a);
             };
-            // layer 0: input -> act[0]
-            zero_acc2(acc); ring_gemm2(acc, kJ_L0, 11, in_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], sm.bias + 0 * 128, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kJ_L0 + 11, 11, in_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], sm.bias + 0 * 128, q, lane);
+            const float *b0[kMT][2], *b4[kMT][2], *bl[kMT][2];
+#pragma unroll
+            for (int m = 0; m < kMT; ++m)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { b0[m][h] = cb[m][h]; b4[m][h] = cb[m][h] + 128; }
+            auto layer_bias = [&](int l) {
+#pragma unroll
+                for (int m = 0; m < kMT; ++m) { bl[m][0] = sm.bias + l * 128; bl[m][1] = sm.bias + l * 128; }
+            };
+            // layer 0: posenc (48) -> act[0]; the 128 warp-code columns are in the bias
+            zero_acc2(acc); ring_gemm2(acc, kT_L0, 3, in_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], b0, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L0 + 3, 3, in_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], b0, q, lane);
             // layer 1: act[0] -> act[1]
-            zero_acc2(acc); ring_gemm2(acc, kJ_L1, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], sm.bias + 1 * 128, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kJ_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], sm.bias + 1 * 128, q, lane);
+            layer_bias(1);
+            zero_acc2(acc); ring_gemm2(acc, kT_L1, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
             // layer 2: act[1] -> act[0]
-            zero_acc2(acc); ring_gemm2(acc, kJ_L2, 8, hid1, sm, rf, lane); relu_store2<0>(acc, ts.act[0], sm.bias + 2 * 128, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kJ_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1>(acc, ts.act[0], sm.bias + 2 * 128, q, lane);
+            layer_bias(2);
+            zero_acc2(acc); ring_gemm2(acc, kT_L2, 8, hid1, sm, rf, lane); relu_store2<0>(acc, ts.act[0], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1>(acc, ts.act[0], bl, q, lane);
             // layer 3: act[0] -> act[1]
-            zero_acc2(acc); ring_gemm2(acc, kJ_L3, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], sm.bias + 3 * 128, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kJ_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], sm.bias + 3 * 128, q, lane);
-            // layer 4 (skip): [act[1] | input] -> act[0]
-            zero_acc2(acc); ring_gemm2(acc, kJ_L4, 19, skip_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], sm.bias + 4 * 128, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kJ_L4 + 19, 19, skip_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], sm.bias + 4 * 128, q, lane);
+            layer_bias(3);
+            zero_acc2(acc); ring_gemm2(acc, kT_L3, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            // layer 4 (skip): [act[1] | posenc] -> act[0]
+            zero_acc2(acc); ring_gemm2(acc, kT_L4, 11, skip_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], b4, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L4 + 11, 11, skip_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], b4, q, lane);
             // layer 5: act[0] -> act[1]
-            zero_acc2(acc); ring_gemm2(acc, kJ_L5, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], sm.bias + 5 * 128, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kJ_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], sm.bias + 5 * 128, q, lane);
-            // heads (chunk 31: slabs 124,125)
+            layer_bias(5);
+            zero_acc2(acc); ring_gemm2(acc, kT_L5, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            // heads (last chunk: slabs 92,93)
             float hacc[kMT][2][4];
 #pragma unroll
             for (int m = 0; m < kMT; ++m)
@@ -1215,7 +1235,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
 #pragma unroll
                     for (int k = 0; k < 4; ++k) hacc[m][i][k] = 0.f;
             {
-                constexpr int chunk = kJ_HEADS / kChunkSlabs, stage = chunk % kStages;
+                constexpr int chunk = kT_HEADS / kChunkSlabs, stage = chunk % kStages;
                 rf.issue(sm, rf.gbase + chunk + (kStages - 1));
                 __syncwarp();
                 mbar_wait<20>(&sm.full[stage], (chunk / kStages) & 1);
@@ -1380,7 +1400,8 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
 
 template <bool D, bool F, bool H>
 static int launch_field(const FieldArgs &A, cudaStream_t st) {
-    if (kernel_version() == 2) return launch_field_ws<D, F, H>(A, st);
+    if (kernel_version() == 2 && (!D || (A.P.deform_packed_tb && A.P.deform_code_bias && !A.S.sample_warp_codes)))
+        return launch_field_ws<D, F, H>(A, st);
     const size_t smem = sizeof(Smem);
     static bool configured = false;
     if (!configured) {

@@ -48,6 +48,8 @@ class NativeParams:
     aabb: torch.Tensor            # float [2,3] (cpu copy kept in aabb_list)
     levels: dict
     n_timesteps: int
+    deform_packed_tb: Optional[torch.Tensor] = None   # half, fragment order, no warp-code columns
+    deform_code_bias: Optional[torch.Tensor] = None   # float [T, 2, 128]
 
     def __post_init__(self):
         self.aabb_list = [float(v) for v in self.aabb.detach().cpu().reshape(-1)]
@@ -76,15 +78,23 @@ class NativeParams:
                                          deform["r_w"].to(dev), deform["r_b"].to(dev),
                                          deform["v_w"].to(dev), deform["v_b"].to(dev))
             wc = time_emb_deform.detach().to(dev).half().contiguous()
+            dtb, dcb = packing.pack_deform_tb([w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]],
+                                              deform["r_w"].to(dev), deform["r_b"].to(dev), deform["v_w"].to(dev),
+                                              deform["v_b"].to(dev), wc)
         te = None if time_emb is None else time_emb.detach().to(dev).float().contiguous()
         n_t = int(time_emb.shape[0]) if time_emb is not None else (int(time_emb_deform.shape[0]) if time_emb_deform is not None else 1)
-        return NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
+        P = NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
+        if deform is not None:
+            P.deform_packed_tb, P.deform_code_bias = dtb, dcb
+        return P
 
     def c_params(self) -> _lib.FieldParams:
         p = _lib.FieldParams()
         p.tables = _ptr(self.tables)
         p.deform_packed = _ptr(self.deform_packed)
         p.deform_bias = _ptr(self.deform_bias)
+        p.deform_packed_tb = _ptr(self.deform_packed_tb)
+        p.deform_code_bias = _ptr(self.deform_code_bias)
         p.field_packed = _ptr(self.field_packed)
         p.warp_codes = _ptr(self.warp_codes)
         p.blend_codes = _ptr(self.blend_codes)

@@ -120,6 +120,28 @@ def pack_deform(stem_w: Sequence[torch.Tensor], stem_b: Sequence[torch.Tensor], 
     return packed.contiguous(), bias.contiguous()
 
 
+def pack_deform_tb(stem_w, stem_b, r_w, r_b, v_w, v_b, warp_codes: torch.Tensor):
+    """Time-bias variant: the warp-code columns of layers 0 and 4 multiply a vector that only depends on the
+    timestep, so W_code . code[t] + b is precomputed per timestep (fp16-rounded operands, fp32 accumulate -- the same
+    products the MMA would form) and enters the kernel as a per-row bias.  Returns (packed fp16 without those
+    columns, code_bias float [T,2,128])."""
+    in_map = deform_input_colmap()[:48]                      # posenc part only (kernel order, padded to 48)
+    ident = list(range(128))
+    skip_map = [DEFORM_IN_DIM + k for k in range(128)] + in_map
+    maps = [in_map, ident, ident, ident, skip_map, ident]
+    parts = [pack_mma_b(w, m, 64) for w, m in zip(stem_w, maps)]
+    heads = torch.cat([v_w.detach().float(), r_w.detach().float()], 0)
+    parts.append(pack_mma_b(heads, ident, 16))
+    packed = torch.cat(parts)
+    assert packed.numel() * 2 == 94 * 2048
+    ch = warp_codes.detach().half().float()
+    cb = []
+    for l in (0, 4):
+        wc = stem_w[l].detach()[:, 45:DEFORM_IN_DIM].half().float()          # [128 out, 128 code]
+        cb.append(ch @ wc.t() + stem_b[l].detach().float()[None, :])
+    return packed.contiguous(), torch.stack(cb, 1).contiguous()
+
+
 def head_input_colmap() -> List[int]:
     """Kernel colour-MLP input column -> reference column of [d'(3) | geo(15) | ones(14)]
     (fields/nersemble_nerfacto_field.py:371-377 + tcnn pad-with-1.0).  Kernel order:

@@ -114,3 +114,19 @@ def test_ops_refuse_cpu_tensors():
     from nersemble_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.march_fixed(torch.zeros(2, 3), torch.ones(2, 3), torch.tensor([[0., 0, 0], [1, 1, 1]]), 4, 0.1)
+
+
+def test_time_bias_packing_is_the_same_linear_map():
+    """pack_deform_tb: W_code . code[t] + b moved into a per-timestep bias; layer-0 pre-activation unchanged."""
+    P = pl.random_params(n_timesteps=5, log2_hashmap_size=4)
+    packed, cb = packing.pack_deform_tb(P.deform_w, P.deform_b, P.r_w, P.r_b, P.v_w, P.v_b, P.time_emb_deform)
+    assert packed.numel() * 2 == 94 * 2048 and cb.shape == (5, 2, 128)
+    h = lambda t: t.half().float()
+    enc = torch.randn(7, 45)
+    for l in (0, 4):
+        W, b = P.deform_w[l], P.deform_b[l]
+        for t in range(5):
+            x = torch.cat([enc, P.time_emb_deform[t][None].expand(7, -1)], -1)
+            full = h(x) @ h(W[:, :173]).t() + b
+            split = h(enc) @ h(W[:, :45]).t() + cb[t, 0 if l == 0 else 1]
+            torch.testing.assert_close(split, full, rtol=1e-5, atol=1e-6)
