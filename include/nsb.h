@@ -107,6 +107,8 @@ typedef struct nsb_field_out {
     float *rgb;      /* [n_samples][3]  or NULL (needs compute_rgb) */
     float *offsets;  /* [n_samples][3]  or NULL: p' - p in normalised-aabb units (deformation_field.py:148-166) */
     void *feat;      /* __half [n_samples][32] blended hash features or NULL */
+    float *xs;       /* [n_samples][4] or NULL: normalised warped position fed to the hash grids (0 outside the box),
+                        w = in-box selector.  Saved by the training forward for nsb_field_backward. */
 } nsb_field_out;
 
 int nsb_version(void);
@@ -140,6 +142,45 @@ typedef struct nsb_composite_args {
     uint32_t *workspace;  /* 2 uint32 (ordered-float min/max of sample midpoints) */
 } nsb_composite_args;
 int nsb_composite_forward(const nsb_composite_args *args, void *stream);
+
+/* Backward of nsb_composite_forward (training mode): gradients w.r.t. per-sample sigma and rgb.
+ * d_weights (the losses that act on per-sample weights: empty/near/distortion, models/base.py:136-249)
+ * may be NULL.  `workspace` must be the one nsb_composite_forward filled (depth clip range). */
+typedef struct nsb_composite_bwd_args {
+    int64_t n_rays, n_samples;
+    const int64_t *packed_info;
+    const float *t_starts, *t_ends, *sigma, *rgb;
+    const float *d_out_rgb;    /* [n_rays][3] */
+    const float *d_out_acc;    /* [n_rays]    or NULL */
+    const float *d_out_depth;  /* [n_rays]    or NULL */
+    const float *d_weights;    /* [n_samples] or NULL */
+    const uint32_t *workspace;
+    float *d_sigma;            /* [n_samples] out */
+    float *d_rgb;              /* [n_samples][3] out */
+} nsb_composite_bwd_args;
+int nsb_composite_backward(const nsb_composite_bwd_args *args, void *stream);
+
+/* Backward of the field MLPs + hash ensemble (replaces the autograd of tcnn mlp_base/mlp_head, the einsum blend
+ * and tcnn's kernel_grid_backward: nersemble_nerfacto_field.py:285-301,377; hash_ensemble.py:102-156).
+ * Inputs saved by the training forward: feat, xs, sigma, rgb.  Gradients are ACCUMULATED (+=) into the fp32
+ * outputs, which the caller zeroes.  The deformation field's backward is not part of this entry point. */
+typedef struct nsb_field_bwd_args {
+    const void *field_packed_t;   /* fp16 TRANSPOSED field weights in MMA-B fragment order (python: pack_field_bwd) */
+    const void *feat;             /* __half [n][32] */
+    const float *xs;              /* [n][4] */
+    const float *sigma;           /* [n] */
+    const float *rgb;             /* [n][3] */
+    const float *d_sigma;         /* [n] */
+    const float *d_rgb;           /* [n][3] */
+    float loss_scale;             /* MLP deltas are fp16 MMA operands: incoming grads are multiplied by this, outputs divided */
+    float *d_feat;                /* [n][32] workspace/out: dL/d(blended features) */
+    float *d_base_w;              /* [3072] tcnn mlp_base.params layout, += */
+    float *d_head_w;              /* [7168] tcnn mlp_head.params layout, += */
+    float *d_tables;              /* [total_entries][32][2] fp32, += (NULL: skip the table/code pass) */
+    float *d_blend_codes;         /* [n_timesteps][32], += (NULL: skip) */
+} nsb_field_bwd_args;
+int nsb_field_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
+                       const nsb_field_bwd_args *args, void *stream);
 
 /* Fixed-stride marcher (BASELINE configs 1/2): n_per_ray intervals of `step` from max(t_enter, near). */
 int nsb_march_fixed(const float *origins, const float *directions, int64_t n_rays, const float *aabb6,

@@ -45,7 +45,15 @@ class Samples(C.Structure):
 
 
 class FieldOut(C.Structure):
-    _fields_ = [("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p), ("feat", C.c_void_p)]
+    _fields_ = [("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p), ("feat", C.c_void_p),
+                ("xs", C.c_void_p)]
+
+
+class FieldBwdArgs(C.Structure):
+    _fields_ = [("field_packed_t", C.c_void_p), ("feat", C.c_void_p), ("xs", C.c_void_p), ("sigma", C.c_void_p),
+                ("rgb", C.c_void_p), ("d_sigma", C.c_void_p), ("d_rgb", C.c_void_p), ("loss_scale", C.c_float),
+                ("d_feat", C.c_void_p), ("d_base_w", C.c_void_p), ("d_head_w", C.c_void_p), ("d_tables", C.c_void_p),
+                ("d_blend_codes", C.c_void_p)]
 
 
 class CompositeArgs(C.Structure):
@@ -54,6 +62,13 @@ class CompositeArgs(C.Structure):
                 ("offsets", C.c_void_p), ("training", C.c_int32),
                 ("out_rgb", C.c_void_p), ("out_acc", C.c_void_p), ("out_depth", C.c_void_p),
                 ("out_deform", C.c_void_p), ("out_weights", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+class CompositeBwdArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int64), ("packed_info", C.c_void_p),
+                ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p),
+                ("d_out_rgb", C.c_void_p), ("d_out_acc", C.c_void_p), ("d_out_depth", C.c_void_p),
+                ("d_weights", C.c_void_p), ("workspace", C.c_void_p), ("d_sigma", C.c_void_p), ("d_rgb", C.c_void_p)]
 
 
 class MarchArgs(C.Structure):
@@ -73,9 +88,12 @@ SYMBOLS = {
     "nsb_field_packed_bytes": (C.c_size_t, []),
     "nsb_field_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
                                     C.POINTER(FieldOut), C.c_void_p]),
+    "nsb_field_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
+                                     C.POINTER(FieldBwdArgs), C.c_void_p]),
     "nsb_hash_blend_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "nsb_composite_forward": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),
+    "nsb_composite_backward": (C.c_int, [C.POINTER(CompositeBwdArgs), C.c_void_p]),
     "nsb_march_fixed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsb_march_occupancy": (C.c_int, [C.POINTER(MarchArgs), C.c_void_p]),

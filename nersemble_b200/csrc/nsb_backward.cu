@@ -1,0 +1,397 @@
+// Backward of the density/colour MLPs and of the hash ensemble (training), sm_100a.
+//
+// Replaces the autograd of (reference, relative to /root/reference/src/nersemble/nerfstudio/):
+//   fields/nersemble_nerfacto_field.py:285-293,377   tcnn mlp_base / mlp_head backward, trunc_exp backward
+//   field_components/hash_ensemble.py:102-156        einsum blend backward (-> time-code gradient)
+//   tcnn kernel_grid_backward [3P]                   scatter of dL/dfeat into the hash tables
+//
+// field_mlp_bwd_kernel: 8 warps x 16 rows per 128-sample tile, everything in registers:
+//   * forward activations are recomputed from the saved blended features (80 HMMA per 16 rows);
+//   * deltas flow backwards through mma.sync with TRANSPOSED weight fragments (pack_field_bwd); the
+//     accumulator layout of a delta tile is again the A-fragment layout of the next GEMM;
+//   * weight gradients dW = delta^T . a are mma.sync too: both operands are transposed 8x8-blockwise with
+//     movmatrix, accumulated into a per-CTA fp32 shared-memory copy, flushed once with global atomics.
+//   Deltas are fp16 MMA operands -> a loss scale keeps them in range (tcnn does the same, x128).
+// hash_bwd_kernel: one warp per sample, lane (g,q) = (corner, 8-member group) exactly like the forward
+//   gather; per level one LDG.256 (values, for the time-code gradient) and four 16-byte vector reductions
+//   (red.global.add.v4.f32) into the fp32 gradient line of the table entry.
+#include <algorithm>
+
+#include "nsb_common.cuh"
+#include "nsb_gather.cuh"
+#include "nsb_mlp.cuh"
+
+namespace nsb {
+
+struct FieldBwdKArgs {
+    nsb_field_params P;
+    nsb_field_opts O;
+    nsb_samples S;
+    nsb_field_bwd_args B;
+};
+
+constexpr int kBaseW = 64 * 32 + 16 * 64;             // 3072
+constexpr int kHeadW = 64 * 32 + 64 * 64 + 16 * 64;   // 7168
+
+struct alignas(16) SmemBwd {
+    uint4 wf[kFieldPackedU4];   // forward fragments
+    uint4 wb[kFieldPackedU4];   // transposed fragments (dX GEMMs)
+    float dw[kBaseW + kHeadW];  // per-CTA weight-gradient accumulator, tcnn flat layout [out][in(kernel col order)]
+};
+
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+
+// 32-bit mask of (acc > 0) in accumulator order [nt][4]
+template <int NT>
+__device__ __forceinline__ uint32_t relu_mask(const float (&acc)[NT][4]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m |= (acc[nt][k] > 0.f ? 1u : 0u) << (nt * 4 + k);
+    return m;
+}
+
+// delta (accumulator layout) -> masked -> A fragments of the next GEMM
+template <int NT>
+__device__ __forceinline__ void mask_pack(const float (&acc)[NT][4], uint32_t mask, uint32_t (&out)[NT / 2][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float v0 = (mask >> (nt * 4 + 0)) & 1 ? acc[nt][0] : 0.f, v1 = (mask >> (nt * 4 + 1)) & 1 ? acc[nt][1] : 0.f;
+        const float v2 = (mask >> (nt * 4 + 2)) & 1 ? acc[nt][2] : 0.f, v3 = (mask >> (nt * 4 + 3)) & 1 ? acc[nt][3] : 0.f;
+        out[nt / 2][(nt & 1) * 2 + 0] = pack_h2(v0, v1);
+        out[nt / 2][(nt & 1) * 2 + 1] = pack_h2(v2, v3);
+    }
+}
+
+// dW[o][i] += sum_rows delta[row][o] * x[row][i]   (O = 16*OT outputs, I = 16*IT inputs, 16 rows of this warp)
+template <int OT, int IT>
+__device__ __forceinline__ void dw_accumulate(const uint32_t (&dA)[OT][4], const uint32_t (&xA)[IT][4], float *dw, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    uint32_t xb[IT][4];
+#pragma unroll
+    for (int ib = 0; ib < IT; ++ib)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xb[ib][k] = movmatrix_trans(xA[ib][k]);
+#pragma unroll
+    for (int ob = 0; ob < OT; ++ob) {
+        // A = delta^T block [o 16][rows 16]: blocks (o-lo,r-lo)=T(d0) (o-hi,r-lo)=T(d2) (o-lo,r-hi)=T(d1) (o-hi,r-hi)=T(d3)
+        const uint32_t a[4] = {movmatrix_trans(dA[ob][0]), movmatrix_trans(dA[ob][2]), movmatrix_trans(dA[ob][1]),
+                               movmatrix_trans(dA[ob][3])};
+#pragma unroll
+        for (int ib = 0; ib < IT; ++ib) {
+#pragma unroll
+            for (int hn = 0; hn < 2; ++hn) {   // n-tile i = ib*16 + hn*8 .. +7: B = (T(x[2hn]) rows 0-7, T(x[2hn+1]) rows 8-15)
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                mma16816(c, a, xb[ib][2 * hn], xb[ib][2 * hn + 1]);
+                const int o = ob * 16 + g, i = ib * 16 + hn * 8 + 2 * q;
+                atomicAdd(&dw[o * (16 * IT) + i], c[0]);
+                atomicAdd(&dw[o * (16 * IT) + i + 1], c[1]);
+                atomicAdd(&dw[(o + 8) * (16 * IT) + i], c[2]);
+                atomicAdd(&dw[(o + 8) * (16 * IT) + i + 1], c[3]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_constant__ FieldBwdKArgs K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemBwd &sm = *reinterpret_cast<SmemBwd *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int64_t n = K.S.n_samples;
+    const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
+    {
+        const uint4 *f = reinterpret_cast<const uint4 *>(K.P.field_packed);
+        const uint4 *b = reinterpret_cast<const uint4 *>(K.B.field_packed_t);
+        for (int i = tid; i < kFieldPackedU4; i += 256) { sm.wf[i] = __ldg(f + i); sm.wb[i] = __ldg(b + i); }
+        for (int i = tid; i < kBaseW + kHeadW; i += 256) sm.dw[i] = 0.f;
+    }
+    __syncthreads();
+    const float ls = K.B.loss_scale, inv_ls = 1.0f / K.B.loss_scale;
+    const __half *featp = reinterpret_cast<const __half *>(K.B.feat);
+    // weight-gradient slices inside sm.dw (kernel column order, flat [out][in])
+    float *dw_b0 = sm.dw, *dw_b1 = sm.dw + 2048, *dw_h0 = sm.dw + kBaseW, *dw_h1 = dw_h0 + 2048, *dw_h2 = dw_h1 + 4096;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * NSB_TILE + warp * 16;
+        if (row0 >= n) continue;
+        const int64_t ra = row0 + g, rb = row0 + g + 8;
+        const bool va = ra < n, vb = rb < n;
+        const int64_t sa = va ? ra : n - 1, sb = vb ? rb : n - 1;
+        // ---------------- forward recompute ----------------
+        uint32_t fa[2][4];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+            fa[kt][0] = __ldg(reinterpret_cast<const uint32_t *>(featp + sa * 32 + kt * 16 + 2 * q));
+            fa[kt][1] = __ldg(reinterpret_cast<const uint32_t *>(featp + sb * 32 + kt * 16 + 2 * q));
+            fa[kt][2] = __ldg(reinterpret_cast<const uint32_t *>(featp + sa * 32 + kt * 16 + 2 * q + 8));
+            fa[kt][3] = __ldg(reinterpret_cast<const uint32_t *>(featp + sb * 32 + kt * 16 + 2 * q + 8));
+        }
+        float acc8[8][4];
+        smem_gemm<2, 4>(acc8, fa, sm.wf, lane);
+        const uint32_t m_b0 = relu_mask<8>(acc8);
+        uint32_t h1[4][4];
+        relu_pack_nobias<8>(acc8, h1);
+        float b1acc[2][4];
+        smem_gemm<4, 1>(b1acc, h1, sm.wf + 256, lane);
+        // directions of the two rows
+        float da[3] = {1.f, 1.f, 1.f}, db[3] = {1.f, 1.f, 1.f};
+        if (K.S.origins != nullptr) {
+            const int ria = K.S.ray_indices[sa], rib = K.S.ray_indices[sb];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { da[k] = K.S.directions[3 * (int64_t)ria + k]; db[k] = K.S.directions[3 * (int64_t)rib + k]; }
+        } else if (K.S.sample_directions) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { da[k] = K.S.sample_directions[3 * sa + k]; db[k] = K.S.sample_directions[3 * sb + k]; }
+        }
+        uint32_t ha[2][4];
+        {
+            float g00 = b1acc[0][0], g02 = b1acc[0][2];
+            if (q == 0) { g00 = 1.0f; g02 = 1.0f; }
+            ha[0][0] = pack_h2(g00, b1acc[0][1]);
+            ha[0][1] = pack_h2(g02, b1acc[0][3]);
+            ha[0][2] = pack_h2(b1acc[1][0], b1acc[1][1]);
+            ha[0][3] = pack_h2(b1acc[1][2], b1acc[1][3]);
+            const float ea0 = q == 0 ? (da[0] + 1.f) / 2.f : (q == 1 ? (da[2] + 1.f) / 2.f : 1.f), ea1 = q == 0 ? (da[1] + 1.f) / 2.f : 1.f;
+            const float eb0 = q == 0 ? (db[0] + 1.f) / 2.f : (q == 1 ? (db[2] + 1.f) / 2.f : 1.f), eb1 = q == 0 ? (db[1] + 1.f) / 2.f : 1.f;
+            ha[1][0] = pack_h2(ea0, ea1);
+            ha[1][1] = pack_h2(eb0, eb1);
+            ha[1][2] = pack_h2(1.0f, 1.0f);
+            ha[1][3] = pack_h2(1.0f, 1.0f);
+        }
+        smem_gemm<2, 4>(acc8, ha, sm.wf + 384, lane);
+        const uint32_t m_c0 = relu_mask<8>(acc8);
+        uint32_t c1in[4][4];
+        relu_pack_nobias<8>(acc8, c1in);
+        smem_gemm<4, 4>(acc8, c1in, sm.wf + 640, lane);
+        const uint32_t m_c1 = relu_mask<8>(acc8);
+        uint32_t c2in[4][4];
+        relu_pack_nobias<8>(acc8, c2in);
+        // (the colour pre-activation itself is not needed: sigmoid' comes from the saved rgb)
+
+        // ---------------- deltas ----------------
+        // output delta: d rgb * rgb (1 - rgb) on columns 0..2 (lane q==0: cols 0,1; q==1: col 2)
+        float dout[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        if (K.B.d_rgb && q < 2) {
+            const int c0 = 2 * q;
+            if (va) {
+                const float r0 = K.B.rgb[3 * ra + c0];
+                dout[0][0] = ls * K.B.d_rgb[3 * ra + c0] * r0 * (1.f - r0);
+                if (q == 0) { const float r1 = K.B.rgb[3 * ra + 1]; dout[0][1] = ls * K.B.d_rgb[3 * ra + 1] * r1 * (1.f - r1); }
+            }
+            if (vb) {
+                const float r0 = K.B.rgb[3 * rb + c0];
+                dout[0][2] = ls * K.B.d_rgb[3 * rb + c0] * r0 * (1.f - r0);
+                if (q == 0) { const float r1 = K.B.rgb[3 * rb + 1]; dout[0][3] = ls * K.B.d_rgb[3 * rb + 1] * r1 * (1.f - r1); }
+            }
+        }
+        uint32_t dA1[1][4];
+        mask_pack<2>(dout, 0xffu, dA1);
+        dw_accumulate<1, 4>(dA1, c2in, dw_h2, lane);
+        smem_gemm<1, 4>(acc8, dA1, sm.wb + 1152, lane);          // d c2in  [16 x 64]
+        uint32_t dA4[4][4];
+        mask_pack<8>(acc8, m_c1, dA4);
+        dw_accumulate<4, 4>(dA4, c1in, dw_h1, lane);
+        smem_gemm<4, 4>(acc8, dA4, sm.wb + 640, lane);           // d c1in  [16 x 64]
+        mask_pack<8>(acc8, m_c0, dA4);
+        dw_accumulate<4, 2>(dA4, ha, dw_h0, lane);
+        float dh[4][4];
+        smem_gemm<4, 2>(dh, dA4, sm.wb + 384, lane);             // d head input [16 x 32]; cols 1..15 = geo features
+        // delta of the density-MLP output: col 0 = d sigma * exp(clamp(h0,-15,15)) * selector (trunc_exp backward)
+        float dhb[2][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { dhb[0][k] = dh[0][k]; dhb[1][k] = dh[1][k]; }
+        if (q == 0) {
+            const float sela = va ? K.B.xs[4 * ra + 3] : 0.f, selb = vb ? K.B.xs[4 * rb + 3] : 0.f;
+            const float dsa = (va && K.B.d_sigma) ? K.B.d_sigma[ra] : 0.f, dsb = (vb && K.B.d_sigma) ? K.B.d_sigma[rb] : 0.f;
+            dhb[0][0] = ls * dsa * expf(fminf(fmaxf(b1acc[0][0], -15.f), 15.f)) * sela;
+            dhb[0][2] = ls * dsb * expf(fminf(fmaxf(b1acc[0][2], -15.f), 15.f)) * selb;
+        }
+        mask_pack<2>(dhb, 0xffu, dA1);
+        dw_accumulate<1, 4>(dA1, h1, dw_b1, lane);
+        smem_gemm<1, 4>(acc8, dA1, sm.wb + 256, lane);           // d h1 [16 x 64]
+        mask_pack<8>(acc8, m_b0, dA4);
+        dw_accumulate<4, 2>(dA4, fa, dw_b0, lane);
+        float dfe[4][4];
+        smem_gemm<4, 2>(dfe, dA4, sm.wb, lane);                  // d feat [16 x 32]
+        if (K.B.d_feat) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (va) *reinterpret_cast<float2 *>(K.B.d_feat + ra * 32 + nt * 8 + 2 * q) = make_float2(dfe[nt][0] * inv_ls, dfe[nt][1] * inv_ls);
+                if (vb) *reinterpret_cast<float2 *>(K.B.d_feat + rb * 32 + nt * 8 + 2 * q) = make_float2(dfe[nt][2] * inv_ls, dfe[nt][3] * inv_ls);
+            }
+        }
+    }
+    __syncthreads();
+    // flush: kernel column order -> tcnn flat layout.  Only head layer 0 has permuted input columns:
+    // kernel col k' -> reference col: 0 -> 18, 1..15 -> k'+2, 16..18 -> k'-16, 19..31 -> k'
+    for (int i = tid; i < kBaseW + kHeadW; i += 256) {
+        const float v = sm.dw[i] * inv_ls;
+        if (v == 0.f) continue;
+        if (i < kBaseW) {
+            if (K.B.d_base_w) atomicAdd(K.B.d_base_w + i, v);
+        } else if (K.B.d_head_w) {
+            int j = i - kBaseW;
+            if (j < 2048) {
+                const int o = j >> 5, kp = j & 31;
+                const int ref = kp == 0 ? 18 : (kp < 16 ? kp + 2 : (kp < 19 ? kp - 16 : kp));
+                j = o * 32 + ref;
+            }
+            atomicAdd(K.B.d_head_w + j, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// table + time-code gradients: one warp per sample
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ FieldBwdKArgs K) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const uint32_t dx = g & 1, dy = (g >> 1) & 1, dz = g >> 2;
+    const int64_t n = K.S.n_samples;
+    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // contiguous chunk of samples per warp: consecutive samples share a ray (same time code) and table lines
+    const int64_t per = (n + n_warps - 1) / n_warps;
+    const int64_t s_begin = warp_global * per, s_end = min(n, s_begin + per);
+    const uint8_t *tab = reinterpret_cast<const uint8_t *>(K.P.tables) + q * 32;
+    float code_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int acc_ts = -1;
+    auto flush_codes = [&]() {
+        if (acc_ts >= 0 && K.B.d_blend_codes && g == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = code_acc[j] * K.O.cw_scale[8 * q + j];     // cw = code*scale + bias
+                if (v != 0.f) atomicAdd(K.B.d_blend_codes + (size_t)acc_ts * NSB_MEMBERS + 8 * q + j, v);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) code_acc[j] = 0.f;
+    };
+    for (int64_t s = s_begin; s < s_end; ++s) {
+        const float4 xs = __ldg(reinterpret_cast<const float4 *>(K.B.xs) + s);
+        // timestep of the sample (same rounding as the forward)
+        float tt = 0.f;
+        if (K.S.origins != nullptr) { if (K.S.ray_times) tt = K.S.ray_times[K.S.ray_indices[s]]; }
+        else if (K.S.sample_times) tt = K.S.sample_times[s];
+        int ts = __float2int_rn(__fmul_rn(tt, (float)(K.P.n_timesteps - 1)));
+        ts = min(max(ts, 0), K.P.n_timesteps - 1);
+        if (ts != acc_ts) { flush_codes(); acc_ts = ts; }
+        const float *code_row = K.S.sample_blend_codes ? K.S.sample_blend_codes + s * NSB_MEMBERS
+                                                       : K.P.blend_codes + (size_t)ts * NSB_MEMBERS;
+        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(code_row) + 2 * q);
+        const float4 c1 = __ldg(reinterpret_cast<const float4 *>(code_row) + 2 * q + 1);
+        const float craw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float cw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // the forward rounds the blend weight to fp16 (B operand of the member reduction)
+            cw[j] = __half2float(__float2half_rn(fmaf(craw[j], K.O.cw_scale[8 * q + j], K.O.cw_bias[8 * q + j])));
+        }
+        float dcw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int l = 0; l < NSB_MAX_LEVELS; ++l) {
+            const float2 df = __ldg(reinterpret_cast<const float2 *>(K.B.d_feat + s * 32) + l);
+            const float scale = K.P.levels.scale[l];
+            const uint32_t res = K.P.levels.res[l], ent = K.P.levels.entries[l], off = K.P.levels.offset[l];
+            const float px = fmaf(scale, xs.x, 0.5f), py = fmaf(scale, xs.y, 0.5f), pz = fmaf(scale, xs.z, 0.5f);
+            const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+            const float fx = px - flx, fy = py - fly, fz = pz - flz;
+            const uint32_t cx = (uint32_t)(int)flx + dx, cy = (uint32_t)(int)fly + dy, cz = (uint32_t)(int)flz + dz;
+            const float w = ((dx ? fx : 1.0f - fx) * (dy ? fy : 1.0f - fy)) * (dz ? fz : 1.0f - fz);
+            uint32_t idx;
+            if (K.P.levels.hashed[l]) {
+                idx = (cx ^ (cy * kPrimeY) ^ (cz * kPrimeZ)) & (ent - 1);
+            } else {
+                idx = cx + cy * res + cz * res * res;
+                idx = idx >= ent ? idx - ent : idx;
+            }
+            const size_t entry = (size_t)(off + idx);
+            const float g0 = w * df.x, g1 = w * df.y;
+            if (K.B.d_blend_codes) {
+                uint32_t v[8];
+                ldg256(tab + entry * 128, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 f = unpack_h2(v[j]);
+                    dcw[j] = fmaf(g0, f.x, fmaf(g1, f.y, dcw[j]));
+                }
+            }
+            if (K.B.d_tables && (g0 != 0.f || g1 != 0.f)) {
+                float *gl = K.B.d_tables + entry * 64 + q * 16;     // fp32 gradient line: [member 32][feat 2]
+                red_add_v4(gl + 0, g0 * cw[0], g1 * cw[0], g0 * cw[1], g1 * cw[1]);
+                red_add_v4(gl + 4, g0 * cw[2], g1 * cw[2], g0 * cw[3], g1 * cw[3]);
+                red_add_v4(gl + 8, g0 * cw[4], g1 * cw[4], g0 * cw[5], g1 * cw[5]);
+                red_add_v4(gl + 12, g0 * cw[6], g1 * cw[6], g0 * cw[7], g1 * cw[7]);
+            }
+        }
+        if (K.B.d_blend_codes) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // sum over the 8 corner lanes (lane bits 2..4)
+                float v = dcw[j];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                code_acc[j] += v;
+            }
+        }
+    }
+    flush_codes();
+}
+
+static int g_bwd_sms = 0;
+
+}  // namespace nsb
+
+using namespace nsb;
+
+extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
+                                  const nsb_field_bwd_args *args, void *stream) {
+    if (!params || !opts || !samples || !args) { set_error("nsb_field_backward: null argument"); return 1; }
+    if (samples->n_samples <= 0) return 0;
+    if (!args->field_packed_t || !params->field_packed || !args->feat || !args->xs || !args->sigma || !args->rgb ||
+        !args->d_feat || !(args->loss_scale > 0.f)) {
+        set_error("nsb_field_backward: missing saved tensors / workspace / loss_scale");
+        return 1;
+    }
+    if ((args->d_tables || args->d_blend_codes) && (!params->tables || (!params->blend_codes && !samples->sample_blend_codes))) {
+        set_error("nsb_field_backward: tables / blend codes missing");
+        return 1;
+    }
+    if (params->levels.n_levels != NSB_MAX_LEVELS) { set_error("nsb_field_backward: n_levels must be 16"); return 1; }
+    if (g_bwd_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_bwd_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_bwd_sms <= 0) g_bwd_sms = 148;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    FieldBwdKArgs K;
+    K.P = *params; K.O = *opts; K.S = *samples; K.B = *args;
+    static bool configured = false;
+    const size_t smem = sizeof(SmemBwd);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(field_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(field_mlp_bwd_kernel): %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    const int64_t n_tiles = (samples->n_samples + NSB_TILE - 1) / NSB_TILE;
+    field_mlp_bwd_kernel<<<(int)std::min<int64_t>(n_tiles, g_bwd_sms), 256, smem, st>>>(K);
+    int rc = check_launch("field_mlp_bwd_kernel");
+    if (rc) return rc;
+    if (args->d_tables || args->d_blend_codes) {
+        const int blocks = (int)std::min<int64_t>((samples->n_samples + 7) / 8, (int64_t)g_bwd_sms * 8);
+        hash_bwd_kernel<<<blocks, 256, 0, st>>>(K);
+        rc = check_launch("hash_bwd_kernel");
+    }
+    return rc;
+}

@@ -302,6 +302,97 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// compositing backward (training mode): one warp per ray, two passes over the ray's samples.
+//   w_i = T_i a_i, T_i = exp(-sum_{j<i} sd_j), a_i = 1-exp(-sd_i), sd = sigma*dt
+//   dL/dsd_i = G_i T_i (1-a_i) - sum_{j>i} G_j w_j,  G_i = dL/dw_i (all consumers of w_i)
+// ---------------------------------------------------------------------------------------------
+struct CompBwdArgs {
+    nsb_composite_bwd_args a;
+};
+
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const __grid_constant__ CompBwdArgs C) {
+    const nsb_composite_bwd_args &a = C.a;
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ray >= a.n_rays) return;
+    const int64_t start = a.packed_info[2 * ray], cnt = a.packed_info[2 * ray + 1];
+    if (cnt == 0) return;
+    const float gr = a.d_out_rgb[3 * ray], gg = a.d_out_rgb[3 * ray + 1], gb = a.d_out_rgb[3 * ray + 2];
+    const float gacc = a.d_out_acc ? a.d_out_acc[ray] : 0.f;
+    float gdep = a.d_out_depth ? a.d_out_depth[ray] : 0.f;
+    // pass 1: forward recompute of acc, N = sum w*mid, and of total = sum_j G_j w_j (needs acc, N first -> split)
+    float carry = 0.f, acc = 0.f, N = 0.f;
+    for (int64_t b = 0; b < cnt; b += 32) {
+        const int64_t i = b + lane;
+        const bool ok = i < cnt;
+        const int64_t s = start + (ok ? i : 0);
+        const float ts = ok ? a.t_starts[s] : 0.f, te = ok ? a.t_ends[s] : 0.f;
+        const float sd = ok ? a.sigma[s] * (te - ts) : 0.f;
+        const float incl = warp_incl_scan(sd, lane);
+        const float w = ok ? expf(-(carry + (incl - sd))) * (1.0f - expf(-sd)) : 0.f;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        acc += w;
+        N += w * ((ts + te) / 2.0f);
+    }
+    acc = warp_sum(acc);
+    N = warp_sum(N);
+    const float inv = 1.0f / (acc + 1e-10f);
+    const float draw = N * inv;
+    if (a.workspace[0] != 0xffffffffu) {   // torch.clip backward: gradient only inside [min, max]
+        const float lo = ordered_to_float(a.workspace[0]), hi = ordered_to_float(a.workspace[1]);
+        if (!(draw >= lo && draw <= hi)) gdep = 0.f;
+    }
+    const float gbg = -(gr + gg + gb);     // white background: rgb + (1 - acc)
+    // pass 2a: total = sum_j G_j w_j
+    float total = 0.f;
+    carry = 0.f;
+    for (int64_t b = 0; b < cnt; b += 32) {
+        const int64_t i = b + lane;
+        const bool ok = i < cnt;
+        const int64_t s = start + (ok ? i : 0);
+        const float ts = ok ? a.t_starts[s] : 0.f, te = ok ? a.t_ends[s] : 0.f;
+        const float sd = ok ? a.sigma[s] * (te - ts) : 0.f;
+        const float incl = warp_incl_scan(sd, lane);
+        const float w = ok ? expf(-(carry + (incl - sd))) * (1.0f - expf(-sd)) : 0.f;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (ok) {
+            const float G = (a.d_weights ? a.d_weights[s] : 0.f) + gr * a.rgb[3 * s] + gg * a.rgb[3 * s + 1] +
+                            gb * a.rgb[3 * s + 2] + gbg + gacc + gdep * (((ts + te) / 2.0f) - draw) * inv;
+            total += G * w;
+        }
+    }
+    total = warp_sum(total);
+    // pass 2b: gradients
+    carry = 0.f;
+    float pcarry = 0.f;
+    for (int64_t b = 0; b < cnt; b += 32) {
+        const int64_t i = b + lane;
+        const bool ok = i < cnt;
+        const int64_t s = start + (ok ? i : 0);
+        const float ts = ok ? a.t_starts[s] : 0.f, te = ok ? a.t_ends[s] : 0.f;
+        const float dt = te - ts;
+        const float sd = ok ? a.sigma[s] * dt : 0.f;
+        const float incl = warp_incl_scan(sd, lane);
+        const float T = expf(-(carry + (incl - sd)));
+        const float e = expf(-sd);
+        const float w = ok ? T * (1.0f - e) : 0.f;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        float G = 0.f;
+        if (ok)
+            G = (a.d_weights ? a.d_weights[s] : 0.f) + gr * a.rgb[3 * s] + gg * a.rgb[3 * s + 1] + gb * a.rgb[3 * s + 2] +
+                gbg + gacc + gdep * (((ts + te) / 2.0f) - draw) * inv;
+        const float gw = G * w;
+        const float pin = warp_incl_scan(gw, lane);          // inclusive prefix of G_j w_j
+        const float suffix = total - (pcarry + pin);          // sum_{j>i} G_j w_j
+        pcarry += __shfl_sync(0xffffffffu, pin, 31);
+        if (ok) {
+            a.d_sigma[s] = (G * T * e - suffix) * dt;
+            a.d_rgb[3 * s] = gr * w; a.d_rgb[3 * s + 1] = gg * w; a.d_rgb[3 * s + 2] = gb * w;
+        }
+    }
+}
+
 __global__ void depth_init_kernel(uint32_t *ws) {
     ws[0] = 0xffffffffu;
     ws[1] = 0u;
@@ -365,6 +456,19 @@ extern "C" int nsb_visibility_mask(const int64_t *packed_info, int64_t n_rays, c
     visibility_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(packed_info, n_rays, t_starts, t_ends, sigma,
                                                               early_stop_eps, alpha_thre, mask, kept_counts);
     return check_launch("visibility_kernel");
+}
+
+extern "C" int nsb_composite_backward(const nsb_composite_bwd_args *args, void *stream) {
+    if (!args || !args->packed_info || !args->t_starts || !args->t_ends || !args->sigma || !args->rgb || !args->d_out_rgb ||
+        !args->workspace || !args->d_sigma || !args->d_rgb) {
+        set_error("nsb_composite_backward: null argument");
+        return 1;
+    }
+    if (args->n_rays <= 0) return 0;
+    CompBwdArgs C; C.a = *args;
+    const int blocks = (int)((args->n_rays + 7) / 8);
+    composite_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(C);
+    return check_launch("composite_bwd_kernel");
 }
 
 extern "C" int nsb_composite_forward(const nsb_composite_args *args, void *stream) {

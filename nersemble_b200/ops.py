@@ -48,6 +48,7 @@ class NativeParams:
     aabb: torch.Tensor            # float [2,3] (cpu copy kept in aabb_list)
     levels: dict
     n_timesteps: int
+    field_packed_t: Optional[torch.Tensor] = None     # half, transposed field weights (backward)
     deform_packed_tb: Optional[torch.Tensor] = None   # half, fragment order, no warp-code columns
     deform_code_bias: Optional[torch.Tensor] = None   # float [T, 2, 128]
 
@@ -69,9 +70,11 @@ class NativeParams:
         deform: dict(stem_w, stem_b, r_w, r_b, v_w, v_b) or None."""
         dev = torch.device(device)
         tab = None if tables is None else tables.detach().to(dev).half().contiguous()
-        fp = None
+        fp = fpt = None
         if base_w is not None:
-            fp = packing.pack_field([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
+            bw, hw = [w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w]
+            fp = packing.pack_field(bw, hw)
+            fpt = packing.pack_field_bwd(bw, hw)
         dp = db = wc = None
         if deform is not None:
             dp, db = packing.pack_deform([w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]],
@@ -86,6 +89,7 @@ class NativeParams:
         P = NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
         if deform is not None:
             P.deform_packed_tb, P.deform_code_bias = dtb, dcb
+        P.field_packed_t = fpt
         return P
 
     def c_params(self) -> _lib.FieldParams:
@@ -179,12 +183,76 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
             out["offsets"] = torch.zeros((n, 3), dtype=_F32, device=dev)
     if "feat" in want:
         out["feat"] = torch.empty((n, 32), dtype=torch.float16, device=dev); o.feat = _ptr(out["feat"])
+    if "xs" in want:
+        out["xs"] = torch.empty((n, 4), dtype=_F32, device=dev); o.xs = _ptr(out["xs"])
     if n == 0:
         return out
     opts = make_opts(window_hash, window_deform, use_deformation, "rgb" in want, disable_initial, soft_transition)
     cp = P.c_params()
     rc = lib.nsb_field_forward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(o), _stream())
     _lib.check(rc, "nsb_field_forward")
+    return out
+
+
+def _fill_samples(s, keep, *, origins=None, directions=None, ray_times=None, t_starts=None, t_ends=None, ray_indices=None,
+                  positions=None, sample_times=None, sample_directions=None, sample_blend_codes=None):
+    if origins is not None:
+        origins, directions, t_starts, t_ends = map(_f32c, (origins, directions, t_starts, t_ends))
+        ray_indices = ray_indices.detach().to(torch.int32).contiguous()
+        ray_times = None if ray_times is None else _f32c(ray_times).reshape(-1)
+        _need_cuda(origins, directions, t_starts, t_ends, ray_indices, ray_times)
+        s.origins, s.directions, s.ray_times = _ptr(origins), _ptr(directions), _ptr(ray_times)
+        s.t_starts, s.t_ends, s.ray_indices = _ptr(t_starts), _ptr(t_ends), _ptr(ray_indices)
+        keep += [origins, directions, t_starts, t_ends, ray_indices, ray_times]
+        s.n_samples = int(t_starts.shape[0])
+    else:
+        positions = _f32c(positions).reshape(-1, 3)
+        sample_times = None if sample_times is None else _f32c(sample_times).reshape(-1)
+        sample_directions = None if sample_directions is None else _f32c(sample_directions).reshape(-1, 3)
+        _need_cuda(positions, sample_times, sample_directions)
+        s.positions, s.sample_times, s.sample_directions = _ptr(positions), _ptr(sample_times), _ptr(sample_directions)
+        keep += [positions, sample_times, sample_directions]
+        s.n_samples = int(positions.shape[0])
+    if sample_blend_codes is not None:
+        sample_blend_codes = _f32c(sample_blend_codes)
+        s.sample_blend_codes = _ptr(sample_blend_codes); keep.append(sample_blend_codes)
+    return s.n_samples
+
+
+def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Optional[torch.Tensor],
+                   d_rgb: Optional[torch.Tensor], *, window_hash=None, loss_scale: float = 128.0,
+                   want_tables: bool = True, want_codes: bool = True, disable_initial=True, soft_transition=True,
+                   **sample_kw) -> Dict[str, torch.Tensor]:
+    """Backward of the density/colour MLPs and the hash ensemble (nsb_field_backward).
+    saved: feat, xs, sigma, rgb from field_forward(want=(..., "feat", "xs")).  Returns fp32 gradients:
+    d_base_w [3072], d_head_w [7168] (tcnn flat layouts), d_tables [entries,32,2], d_blend_codes [T,32], d_feat."""
+    lib = _lib.load()
+    keep = []
+    s = _lib.Samples()
+    n = _fill_samples(s, keep, **sample_kw)
+    dev = saved["feat"].device
+    a = _lib.FieldBwdArgs()
+    feat = saved["feat"].contiguous(); xs = _f32c(saved["xs"]); sg = _f32c(saved["sigma"]); cc = _f32c(saved["rgb"])
+    dsg = None if d_sigma is None else _f32c(d_sigma).reshape(-1)
+    drg = None if d_rgb is None else _f32c(d_rgb).reshape(-1, 3)
+    _need_cuda(feat, xs, sg, cc, dsg, drg)
+    a.field_packed_t = _ptr(P.field_packed_t)
+    a.feat, a.xs, a.sigma, a.rgb, a.d_sigma, a.d_rgb = _ptr(feat), _ptr(xs), _ptr(sg), _ptr(cc), _ptr(dsg), _ptr(drg)
+    a.loss_scale = float(loss_scale)
+    out = {"d_feat": torch.zeros((n, 32), dtype=_F32, device=dev),
+           "d_base_w": torch.zeros((3072,), dtype=_F32, device=dev), "d_head_w": torch.zeros((7168,), dtype=_F32, device=dev)}
+    a.d_feat, a.d_base_w, a.d_head_w = _ptr(out["d_feat"]), _ptr(out["d_base_w"]), _ptr(out["d_head_w"])
+    if want_tables:
+        out["d_tables"] = torch.zeros((P.levels["total_entries"], 32, 2), dtype=_F32, device=dev)
+        a.d_tables = _ptr(out["d_tables"])
+    if want_codes:
+        out["d_blend_codes"] = torch.zeros((P.n_timesteps, 32), dtype=_F32, device=dev)
+        a.d_blend_codes = _ptr(out["d_blend_codes"])
+    if n == 0:
+        return out
+    opts = make_opts(window_hash, None, False, True, disable_initial, soft_transition)
+    cp = P.c_params()
+    _lib.check(lib.nsb_field_backward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(a), _stream()), "nsb_field_backward")
     return out
 
 
@@ -230,7 +298,32 @@ def composite(packed_info: torch.Tensor, t_starts, t_ends, sigma, rgb, offsets=N
     a.workspace = _ptr(ws)
     rc = lib.nsb_composite_forward(C.byref(a), _stream())
     _lib.check(rc, "nsb_composite_forward")
+    out["workspace"] = ws
     return out
+
+
+def composite_backward(packed_info, t_starts, t_ends, sigma, rgb, workspace, d_out_rgb, d_out_acc=None, d_out_depth=None,
+                       d_weights=None):
+    """Backward of composite() in training mode -> (d_sigma [S], d_rgb [S,3])."""
+    lib = _lib.load()
+    packed_info = packed_info.to(torch.int64).contiguous()
+    ts, te, sg, cc = map(_f32c, (t_starts, t_ends, sigma, rgb))
+    g_rgb = _f32c(d_out_rgb).reshape(-1, 3)
+    g_acc = None if d_out_acc is None else _f32c(d_out_acc).reshape(-1)
+    g_dep = None if d_out_depth is None else _f32c(d_out_depth).reshape(-1)
+    g_w = None if d_weights is None else _f32c(d_weights).reshape(-1)
+    _need_cuda(packed_info, ts, te, sg, cc, g_rgb, g_acc, g_dep, g_w, workspace)
+    R, n = packed_info.shape[0], ts.shape[0]
+    a = _lib.CompositeBwdArgs()
+    a.n_rays, a.n_samples, a.packed_info = R, n, _ptr(packed_info)
+    a.t_starts, a.t_ends, a.sigma, a.rgb = _ptr(ts), _ptr(te), _ptr(sg), _ptr(cc)
+    a.d_out_rgb, a.d_out_acc, a.d_out_depth, a.d_weights = _ptr(g_rgb), _ptr(g_acc), _ptr(g_dep), _ptr(g_w)
+    a.workspace = _ptr(workspace)
+    d_sigma = torch.zeros((n,), dtype=_F32, device=ts.device)
+    d_rgb = torch.zeros((n, 3), dtype=_F32, device=ts.device)
+    a.d_sigma, a.d_rgb = _ptr(d_sigma), _ptr(d_rgb)
+    _lib.check(lib.nsb_composite_backward(C.byref(a), _stream()), "nsb_composite_backward")
+    return d_sigma, d_rgb
 
 
 def march_fixed(origins, directions, aabb: torch.Tensor, n_per_ray: int, step: float, near_plane: float = 0.0):

@@ -161,6 +161,18 @@ def pack_field(base_w: Sequence[torch.Tensor], head_w: Sequence[torch.Tensor]) -
     return packed.contiguous()
 
 
+def pack_field_bwd(base_w: Sequence[torch.Tensor], head_w: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Transposed weights for the delta GEMMs dX = delta . W (K = out dim, N = in dim), same fragment order and
+    the same per-layer offsets as pack_field.  Head layer 0 keeps the kernel's permuted input column order on N."""
+    hm = head_input_colmap()
+    parts = [pack_mma_b(base_w[0].t(), range(64), 32), pack_mma_b(base_w[1].t(), range(16), 64),
+             pack_mma_b(head_w[0][:, hm].t(), range(64), 32), pack_mma_b(head_w[1].t(), range(64), 64),
+             pack_mma_b(head_w[2].t(), range(16), 64)]
+    packed = torch.cat(parts)
+    assert packed.numel() * 2 == 20480 and [p.numel() // 8 for p in parts] == [256, 128, 256, 512, 128]
+    return packed.contiguous()
+
+
 def split_tcnn_mlp_params(flat: torch.Tensor, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:
     """tcnn Network .params (layers consecutive, each [out,in] row-major) -> list of matrices."""
     out, ofs = [], 0

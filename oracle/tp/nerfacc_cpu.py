@@ -51,12 +51,13 @@ def exclusive_sum(x: torch.Tensor, packed_info: torch.Tensor) -> torch.Tensor:
     """Per-segment exclusive prefix sum (differentiable)."""
     if x.numel() == 0:
         return x
-    inc = torch.cumsum(x, 0)
+    # float64 global cumsum: removes the cancellation error of (global prefix - segment start) in fp32
+    xd = x.double()
+    inc = torch.cumsum(xd, 0)
     seg = _segment_ids(packed_info, x.shape[0])
     starts = packed_info[:, 0]
-    # total before each segment start
-    before = torch.cat([torch.zeros(1, dtype=x.dtype), inc])[starts]
-    return inc - x - before[seg]
+    before = torch.cat([torch.zeros(1, dtype=torch.float64), inc])[starts]
+    return (inc - xd - before[seg]).to(x.dtype)
 
 
 def render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info):
