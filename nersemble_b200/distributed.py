@@ -34,3 +34,27 @@ def gather_rays(local: torch.Tensor, n_total: int) -> torch.Tensor:
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
+
+
+def allreduce_gradients(params, average: bool = True) -> None:
+    """The training collective: ONE all-reduce of the flat gradient buffer per step
+    (403 M table gradients + MLP/embedding gradients), then divide by the world size.  Parameters whose .grad is
+    None on this rank contribute zeros so that every rank issues the same collective."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat /= dist.get_world_size()
+    ofs = 0
+    for p in params:
+        n = p.numel()
+        g = flat[ofs:ofs + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        ofs += n

@@ -82,6 +82,43 @@ class NeRSembleNGPModelConfig(BaseModelConfig):
         return self._target(self, **kwargs)
 
 
+class _RenderFunction(torch.autograd.Function):
+    """Differentiable fused render (training).  Forward = nsb_field_forward (saving the blended features and
+    warped positions) + nsb_composite_forward; backward = nsb_composite_backward -> nsb_field_backward, with the
+    fp32 gradients mapped back to the reference's parameter layouts (8 tcnn grids, flat tcnn MLP params,
+    time embedding).  Round 1: hash-ensemble field only (config.use_deformation_field=False)."""
+
+    @staticmethod
+    def forward(ctx, model, origins, directions, ray_times, starts, ends, ray_indices, packed_info, wh, *params):
+        P = model.native_params()
+        kw = dict(origins=origins, directions=directions, ray_times=ray_times, t_starts=starts, t_ends=ends,
+                  ray_indices=ray_indices)
+        f = ops.field_forward(P, window_hash=wh, window_deform=None, use_deformation=False,
+                              want=("sigma", "rgb", "feat", "xs"), **kw, **model._blend_opts())
+        c = ops.composite(packed_info, starts, ends, f["sigma"], f["rgb"], None, training=True)
+        ctx.model, ctx.P, ctx.kw, ctx.wh = model, P, kw, wh
+        ctx.saved = dict(feat=f["feat"], xs=f["xs"], sigma=f["sigma"], rgb=f["rgb"])
+        ctx.packed_info, ctx.workspace = packed_info, c["workspace"]
+        ctx.mark_non_differentiable(packed_info)
+        return c["rgb"], c["accumulation"], c["depth"], c["weights"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, g_depth, g_weights):
+        model = ctx.model
+        kw = ctx.kw
+        d_sigma, d_rgb = ops.composite_backward(ctx.packed_info, kw["t_starts"], kw["t_ends"], ctx.saved["sigma"],
+                                                ctx.saved["rgb"], ctx.workspace, g_rgb,
+                                                None if g_acc is None else g_acc.reshape(-1),
+                                                None if g_depth is None else g_depth.reshape(-1),
+                                                None if g_weights is None else g_weights.reshape(-1))
+        g = ops.field_backward(ctx.P, ctx.saved, d_sigma, d_rgb, window_hash=ctx.wh,
+                               loss_scale=float(getattr(model, "mlp_loss_scale", 128.0)), **kw, **model._blend_opts())
+        from .. import packing
+        grids = packing.tables_to_tcnn(g["d_tables"])
+        grads = list(grids) + [g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
+        return (None,) * 9 + tuple(grads)
+
+
 def _segment_exclusive_sum(x: Tensor, ray_indices: Tensor, n_rays: int) -> Tensor:
     cnt = torch.zeros(n_rays, dtype=torch.long, device=x.device).index_add_(0, ray_indices, torch.ones_like(ray_indices))
     starts = cnt.cumsum(0) - cnt
@@ -228,7 +265,9 @@ class NeRSembleNGPModel(nn.Module):
         cfg = self.config
         wh, wd = self._windows()
         num_rays = len(ray_bundle)
-        _no_autograd(*self.parameters())
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad and cfg.use_deformation_field:
+            _no_autograd(*self.parameters())     # raises: the deformation-field backward is round-2 work
         with torch.no_grad():
             ray_samples, ray_indices = self.sampler(
                 ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
@@ -245,6 +284,14 @@ class NeRSembleNGPModel(nn.Module):
         cnt = torch.zeros(num_rays, dtype=torch.long, device=starts.device).index_add_(
             0, ray_indices, torch.ones_like(ray_indices))
         packed_info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)           # nerfacc.pack_info (:325)
+        if needs_grad:
+            he = self.field.hash_ensemble
+            params = [m.params for m in he.hash_encodings] + [self.field.mlp_base.params, self.field.mlp_head.params,
+                                                               self.time_embedding.weight]
+            rgb, acc, depth, weights = _RenderFunction.apply(self, ray_bundle.origins, ray_bundle.directions, ray_times, starts,
+                                                             ends, ray_indices, packed_info, wh, *params)
+            return {"rgb": rgb, "accumulation": acc, "depth": depth, "num_samples_per_ray": packed_info[:, 1],
+                    "ray_samples": (ray_samples,), "ray_indices": (ray_indices,), "weights": (weights,)}
         out = ops.render_packed(self.native_params(), ray_bundle.origins, ray_bundle.directions, ray_times, starts, ends,
                                 ray_indices, packed_info, window_hash=wh, window_deform=wd,
                                 use_deformation=cfg.use_deformation_field, training=self.training, **self._blend_opts())

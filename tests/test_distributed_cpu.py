@@ -29,6 +29,26 @@ def _worker(rank, world, port, n):
     dist.destroy_process_group()
 
 
+def _grad_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nersemble_b200.distributed import allreduce_gradients
+    a = torch.nn.Parameter(torch.zeros(5)); b = torch.nn.Parameter(torch.zeros(2, 3)); c = torch.nn.Parameter(torch.zeros(4))
+    a.grad = torch.full((5,), float(rank + 1)); b.grad = torch.arange(6.0).view(2, 3) * (rank + 1)
+    if rank == 0:
+        c.grad = torch.ones(4)            # rank 1 has no gradient for c
+    allreduce_gradients([a, b, c])
+    assert torch.allclose(a.grad, torch.full((5,), 1.5)) and torch.allclose(b.grad, torch.arange(6.0).view(2, 3) * 1.5)
+    assert torch.allclose(c.grad, torch.full((4,), 0.5))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradient_allreduce():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)
+
+
 def test_gloo_world2_shard_and_gather():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, 101), nprocs=2, join=True)

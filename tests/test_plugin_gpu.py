@@ -134,3 +134,77 @@ def test_occupancy_update_and_full_frame_render():
     with torch.no_grad():
         full = m.get_outputs(flat)
     torch.testing.assert_close(img["rgb"].view(-1, 3), full["rgb"], rtol=0, atol=1e-6)   # chunking is exact
+
+
+def test_training_step_gradients_and_descent():
+    """use_deformation_field=False recipe: end-to-end gradients through the plugin model (sampler -> fused field ->
+    composite -> losses) vs autograd through the oracle, then a few Adam steps must reduce the loss."""
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    from oracle.gen_golden import blob_grid, ring_rays
+    from oracle.tp import nerfacc_cpu
+    Precision.mode = "kernel"
+    knobs = dict(seed=19980801, n_timesteps=4, log2_hashmap_size=14, table_scale=0.5, time_std_scale=100.0, deform_last_scale=1e-3)
+    P = pl.random_params(**knobs)
+    m = make_model(T=4, log2T=14, use_deformation_field=False, window_deform_end=0,
+                   lambda_near_loss=0, lambda_empty_loss=0, lambda_depth_loss=0, lambda_dist_loss=1e-2, lambda_alpha_loss=1e-2)
+    with torch.no_grad():
+        from nersemble_b200 import packing
+        for c, gtab in enumerate(packing.tables_to_tcnn(P.tables)):
+            m.field.hash_ensemble.hash_encodings[c].params.copy_(gtab)
+        m.field.mlp_base.params.copy_(torch.cat([w.reshape(-1) for w in P.base_w]))
+        m.field.mlp_head.params.copy_(torch.cat([w.reshape(-1) for w in P.head_w]))
+        m.time_embedding.weight.copy_(P.time_emb)
+    m = m.to(DEV).train()
+    m.sched_window_hash_encodings.value = 32.0
+    occ = blob_grid(3)
+    m.occupancy_grid.binaries[0] = occ.to(DEV)
+    m.occupancy_grid.occs.copy_((occ.flatten().float() * 0.05).to(DEV))
+    R = 64
+    o, d, times, cams = ring_rays(R, 21)
+    gen = torch.Generator().manual_seed(1)
+    batch = {"image": torch.rand((R, 3), generator=gen), "alpha_map": torch.randint(0, 256, (R, 1), generator=gen).float()}
+    rb = RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                   camera_indices=cams.to(DEV), times=times.to(DEV))
+    m.sampler.eval()          # no stratified jitter / pre-pass: same samples as the oracle marcher
+    out = m.get_outputs(rb)
+    ld = m.get_loss_dict(out, batch)
+    loss = sum(ld.values())
+    loss.backward()
+    # ---- oracle: same samples, same losses, autograd
+    ts, te, ri = pl.sample_occupancy(P, o, d, times, occ[None], 0.0, 0.011, 0.2, 1e3, 1e-2, 0.0, training=False)
+    assert torch.equal(ri, out["ray_indices"][0].cpu())
+    P.requires_grad_(True)
+    tsteps = pl.timesteps_from_times(times[ri], 4)
+    pos = o[ri] + d[ri] * ((ts + te)[:, None] / 2)
+    sigma, geo = pl.field_density(P, pos, P.time_emb[tsteps], 32.0)
+    rgb_s = pl.field_rgb(P, d[ri], geo)
+    info = nerfacc_cpu.pack_info(ri, R)
+    w = nerfacc_cpu.render_weight_from_density(ts, te, sigma[:, 0], info)[0]
+    acc = nerfacc_cpu.accumulate_along_rays(w, None, ri, R)
+    comp = nerfacc_cpu.accumulate_along_rays(w, rgb_s, ri, R) + (1.0 - acc)
+    mid = (ts + te)[:, None] / 2
+    depth = torch.clip(nerfacc_cpu.accumulate_along_rays(w, mid, ri, R) / (acc + 1e-10), mid.min(), mid.max())
+    o_ld = pl.loss_dict({"rgb": comp, "accumulation": acc, "depth": depth, "weights": w[:, None]}, ts, te, ri, batch,
+                        eps_depth=0.5, lam_alpha=1e-2, lam_near=0, lam_empty=0, lam_depth=0, lam_dist=1e-2)
+    o_loss = sum(o_ld.values())
+    o_loss.backward()
+    assert abs(loss.item() - o_loss.item()) < 2e-3 * abs(o_loss.item()) + 1e-5
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    assert rel(m.field.mlp_head.params.grad.cpu(), torch.cat([x.grad.reshape(-1) for x in P.head_w])) < 3e-2
+    assert rel(m.field.mlp_base.params.grad.cpu(), torch.cat([x.grad.reshape(-1) for x in P.base_w])) < 3e-2
+    assert rel(m.time_embedding.weight.grad.cpu(), P.time_emb.grad) < 3e-2
+    got_t = packing.tables_from_tcnn([mm.params.grad.cpu() for mm in m.field.hash_ensemble.hash_encodings])
+    cos = torch.nn.functional.cosine_similarity(got_t.reshape(1, -1), P.tables.grad.reshape(1, -1)).item()
+    assert cos > 0.999, cos
+    # ---- a few optimiser steps on the same batch reduce the loss
+    groups = m.get_param_groups()
+    opt = torch.optim.Adam([{"params": groups["fields"], "lr": 5e-3}, {"params": groups["embeddings"], "lr": 5e-3}], eps=1e-15)
+    first = loss.item()
+    for _ in range(20):
+        opt.zero_grad(set_to_none=True)
+        out = m.get_outputs(rb)
+        l = sum(m.get_loss_dict(out, batch).values())
+        l.backward()
+        opt.step()
+    assert l.item() < 0.85 * first, (first, l.item())
+    Precision.mode = "reference"
