@@ -178,6 +178,8 @@ typedef struct nsb_field_bwd_args {
     float *d_head_w;              /* [7168] tcnn mlp_head.params layout, += */
     float *d_tables;              /* [total_entries][32][2] fp32, += (NULL: skip the table/code pass) */
     float *d_blend_codes;         /* [n_timesteps][32], += (NULL: skip) */
+    float *d_xs;                  /* [n][3] out (NULL: skip): dL/d(normalised warped position), tcnn's
+                                     kernel_grid_backward_input; feeds the deformation-field backward */
 } nsb_field_bwd_args;
 int nsb_field_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                        const nsb_field_bwd_args *args, void *stream);

@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
             cw[j] = __half2float(__float2half_rn(fmaf(craw[j], K.O.cw_scale[8 * q + j], K.O.cw_bias[8 * q + j])));
         }
         float dcw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float ex = 0.f, ey = 0.f, ez = 0.f;   // dL/dx partial sums (this lane's corner and members)
 #pragma unroll 2
         for (int l = 0; l < NSB_MAX_LEVELS; ++l) {
             const float2 df = __ldg(reinterpret_cast<const float2 *>(K.B.d_feat + s * 32) + l);
@@ -307,7 +308,8 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
             const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
             const float fx = px - flx, fy = py - fly, fz = pz - flz;
             const uint32_t cx = (uint32_t)(int)flx + dx, cy = (uint32_t)(int)fly + dy, cz = (uint32_t)(int)flz + dz;
-            const float w = ((dx ? fx : 1.0f - fx) * (dy ? fy : 1.0f - fy)) * (dz ? fz : 1.0f - fz);
+            const float wx = dx ? fx : 1.0f - fx, wy = dy ? fy : 1.0f - fy, wz = dz ? fz : 1.0f - fz;
+            const float w = (wx * wy) * wz;
             uint32_t idx;
             if (K.P.levels.hashed[l]) {
                 idx = (cx ^ (cy * kPrimeY) ^ (cz * kPrimeZ)) & (ent - 1);
@@ -317,14 +319,22 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
             }
             const size_t entry = (size_t)(off + idx);
             const float g0 = w * df.x, g1 = w * df.y;
-            if (K.B.d_blend_codes) {
+            if (K.B.d_blend_codes || K.B.d_xs) {
                 uint32_t v[8];
                 ldg256(tab + entry * 128, v);
+                float pb0 = 0.f, pb1 = 0.f;   // this lane's share of the member-blended corner value
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 f = unpack_h2(v[j]);
                     dcw[j] = fmaf(g0, f.x, fmaf(g1, f.y, dcw[j]));
+                    pb0 = fmaf(cw[j], f.x, pb0);
+                    pb1 = fmaf(cw[j], f.y, pb1);
                 }
+                // d w / d x_d = +-scale * (product of the other two factors)   (frac = scale*x + 0.5 - floor)
+                const float t = scale * (df.x * pb0 + df.y * pb1);
+                ex = fmaf(dx ? t : -t, wy * wz, ex);
+                ey = fmaf(dy ? t : -t, wx * wz, ey);
+                ez = fmaf(dz ? t : -t, wx * wy, ez);
             }
             if (K.B.d_tables && (g0 != 0.f || g1 != 0.f)) {
                 float *gl = K.B.d_tables + entry * 64 + q * 16;     // fp32 gradient line: [member 32][feat 2]
@@ -332,6 +342,17 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
                 red_add_v4(gl + 4, g0 * cw[2], g1 * cw[2], g0 * cw[3], g1 * cw[3]);
                 red_add_v4(gl + 8, g0 * cw[4], g1 * cw[4], g0 * cw[5], g1 * cw[5]);
                 red_add_v4(gl + 12, g0 * cw[6], g1 * cw[6], g0 * cw[7], g1 * cw[7]);
+            }
+        }
+        if (K.B.d_xs) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                ey += __shfl_xor_sync(0xffffffffu, ey, o);
+                ez += __shfl_xor_sync(0xffffffffu, ez, o);
+            }
+            if (lane == 0) {   // positions outside the box were zeroed (x * selector): no gradient
+                K.B.d_xs[3 * s + 0] = ex * xs.w; K.B.d_xs[3 * s + 1] = ey * xs.w; K.B.d_xs[3 * s + 2] = ez * xs.w;
             }
         }
         if (K.B.d_blend_codes) {
@@ -363,7 +384,7 @@ extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_fiel
         set_error("nsb_field_backward: missing saved tensors / workspace / loss_scale");
         return 1;
     }
-    if ((args->d_tables || args->d_blend_codes) && (!params->tables || (!params->blend_codes && !samples->sample_blend_codes))) {
+    if ((args->d_tables || args->d_blend_codes || args->d_xs) && (!params->tables || (!params->blend_codes && !samples->sample_blend_codes))) {
         set_error("nsb_field_backward: tables / blend codes missing");
         return 1;
     }
@@ -388,7 +409,7 @@ extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_fiel
     field_mlp_bwd_kernel<<<(int)std::min<int64_t>(n_tiles, g_bwd_sms), 256, smem, st>>>(K);
     int rc = check_launch("field_mlp_bwd_kernel");
     if (rc) return rc;
-    if (args->d_tables || args->d_blend_codes) {
+    if (args->d_tables || args->d_blend_codes || args->d_xs) {
         const int blocks = (int)std::min<int64_t>((samples->n_samples + 7) / 8, (int64_t)g_bwd_sms * 8);
         hash_bwd_kernel<<<blocks, 256, 0, st>>>(K);
         rc = check_launch("hash_bwd_kernel");

@@ -221,7 +221,8 @@ def _fill_samples(s, keep, *, origins=None, directions=None, ray_times=None, t_s
 
 def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Optional[torch.Tensor],
                    d_rgb: Optional[torch.Tensor], *, window_hash=None, loss_scale: float = 128.0,
-                   want_tables: bool = True, want_codes: bool = True, disable_initial=True, soft_transition=True,
+                   want_tables: bool = True, want_codes: bool = True, want_dx: bool = False, disable_initial=True,
+                   soft_transition=True,
                    **sample_kw) -> Dict[str, torch.Tensor]:
     """Backward of the density/colour MLPs and the hash ensemble (nsb_field_backward).
     saved: feat, xs, sigma, rgb from field_forward(want=(..., "feat", "xs")).  Returns fp32 gradients:
@@ -248,6 +249,9 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
     if want_codes:
         out["d_blend_codes"] = torch.zeros((P.n_timesteps, 32), dtype=_F32, device=dev)
         a.d_blend_codes = _ptr(out["d_blend_codes"])
+    if want_dx:
+        out["d_xs"] = torch.zeros((n, 3), dtype=_F32, device=dev)
+        a.d_xs = _ptr(out["d_xs"])
     if n == 0:
         return out
     opts = make_opts(window_hash, None, False, True, disable_initial, soft_transition)

@@ -70,16 +70,21 @@ def test_field_backward_vs_autograd():
     times = tsteps.float()[:, None] / 3
     w_hash = 20.25
     P.requires_grad_(True)
+    pos = pos.clone().requires_grad_(True)
     sigma, geo = pl.field_density(P, pos, P.time_emb[tsteps], w_hash)
     rgb = pl.field_rgb(P, dirs, geo)
     g_sigma = torch.randn((n,), generator=g) * 0.1
     g_rgb = torch.randn((n, 3), generator=g)
     ((sigma[:, 0] * g_sigma).sum() + (rgb * g_rgb).sum()).backward()
 
-    kw = dict(positions=pos.to(DEV), sample_times=times.to(DEV), sample_directions=dirs.to(DEV))
+    kw = dict(positions=pos.detach().to(DEV), sample_times=times.to(DEV), sample_directions=dirs.to(DEV))
     saved = ops.field_forward(NP, window_hash=w_hash, use_deformation=False, want=("sigma", "rgb", "feat", "xs"), **kw)
     torch.testing.assert_close(saved["sigma"].cpu(), sigma[:, 0].detach(), rtol=5e-3, atol=1e-5)
-    grads = ops.field_backward(NP, saved, g_sigma.to(DEV), g_rgb.to(DEV), window_hash=w_hash, loss_scale=128.0, **kw)
+    grads = ops.field_backward(NP, saved, g_sigma.to(DEV), g_rgb.to(DEV), window_hash=w_hash, loss_scale=128.0, want_dx=True, **kw)
+    # dL/d(world position) = dL/d(normalised) / aabb size   (tcnn kernel_grid_backward_input)
+    dpos = grads["d_xs"].cpu() / (hi - lo)
+    assert _relerr(dpos, pos.grad) < 3e-2
+    assert (dpos[saved["xs"].cpu()[:, 3] == 0] == 0).all()
     gb = torch.cat([w.grad.reshape(-1) for w in P.base_w]); gh = torch.cat([w.grad.reshape(-1) for w in P.head_w])
     # deltas are fp16 MMA operands (2^-11 relative each) -> percent-level agreement on the reduced gradients
     assert _relerr(grads["d_head_w"].cpu(), gh) < 2e-2
