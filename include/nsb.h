@@ -109,6 +109,10 @@ typedef struct nsb_field_out {
     void *feat;      /* __half [n_samples][32] blended hash features or NULL */
     float *xs;       /* [n_samples][4] or NULL: normalised warped position fed to the hash grids (0 outside the box),
                         w = in-box selector.  Saved by the training forward for nsb_field_backward. */
+    void *deform_acts; /* NULL or uint4 [n_tiles][8 warps][6 layers][8 k-tiles][32 lanes]: fp16 outputs of the 6 stem
+                        layers in MMA A-fragment order (16 rows per warp), saved by the training forward for
+                        nsb_deform_backward (the reference keeps the same activations for autograd). */
+    void *deform_enc;  /* NULL or uint4 [n_tiles][8 warps][3 k-tiles][32 lanes]: windowed posenc fragments */
 } nsb_field_out;
 
 int nsb_version(void);
@@ -183,6 +187,26 @@ typedef struct nsb_field_bwd_args {
 } nsb_field_bwd_args;
 int nsb_field_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                        const nsb_field_bwd_args *args, void *stream);
+
+/* Backward of the SE(3) deformation field (replaces the autograd of deformation_field.py:77-166, se3_exp_map and the
+ * time_embedding_deformation lookup).  Needs the activations the training forward saved (nsb_field_out.deform_acts /
+ * deform_enc) and dL/d(hash input position) from nsb_field_backward (d_xs).  fp32 gradients are ACCUMULATED (+=) in the
+ * reference's parameter layouts (nn.Linear weight [out][in], input order of nerfstudio's MLP: layer 4 = [input 173 | hidden 128]). */
+typedef struct nsb_deform_bwd_args {
+    const void *deform_packed_t;  /* fp16 TRANSPOSED stem/head weights in MMA-B fragment order (python: pack_deform_bwd) */
+    const void *deform_acts;
+    const void *deform_enc;
+    const float *d_xs;            /* [n][3] */
+    float loss_scale;
+    float *d_stem_w[6];           /* [128][173], 3 x [128][128], [128][301], [128][128] */
+    float *d_stem_b;              /* [6][128] */
+    float *d_r_w, *d_r_b;         /* [3][128], [3] */
+    float *d_v_w, *d_v_b;         /* [3][128], [3] */
+    float *d_warp_codes;          /* [n_timesteps][128] or NULL */
+} nsb_deform_bwd_args;
+size_t nsb_deform_packed_t_bytes(void);
+int nsb_deform_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
+                        const nsb_deform_bwd_args *args, void *stream);
 
 /* Fixed-stride marcher (BASELINE configs 1/2): n_per_ray intervals of `step` from max(t_enter, near). */
 int nsb_march_fixed(const float *origins, const float *directions, int64_t n_rays, const float *aabb6,

@@ -46,7 +46,7 @@ class Samples(C.Structure):
 
 class FieldOut(C.Structure):
     _fields_ = [("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p), ("feat", C.c_void_p),
-                ("xs", C.c_void_p)]
+                ("xs", C.c_void_p), ("deform_acts", C.c_void_p), ("deform_enc", C.c_void_p)]
 
 
 class FieldBwdArgs(C.Structure):
@@ -62,6 +62,13 @@ class CompositeArgs(C.Structure):
                 ("offsets", C.c_void_p), ("training", C.c_int32),
                 ("out_rgb", C.c_void_p), ("out_acc", C.c_void_p), ("out_depth", C.c_void_p),
                 ("out_deform", C.c_void_p), ("out_weights", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+class DeformBwdArgs(C.Structure):
+    _fields_ = [("deform_packed_t", C.c_void_p), ("deform_acts", C.c_void_p), ("deform_enc", C.c_void_p),
+                ("d_xs", C.c_void_p), ("loss_scale", C.c_float), ("d_stem_w", C.c_void_p * 6), ("d_stem_b", C.c_void_p),
+                ("d_r_w", C.c_void_p), ("d_r_b", C.c_void_p), ("d_v_w", C.c_void_p), ("d_v_b", C.c_void_p),
+                ("d_warp_codes", C.c_void_p)]
 
 
 class CompositeBwdArgs(C.Structure):
@@ -90,6 +97,9 @@ SYMBOLS = {
                                     C.POINTER(FieldOut), C.c_void_p]),
     "nsb_field_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
                                      C.POINTER(FieldBwdArgs), C.c_void_p]),
+    "nsb_deform_packed_t_bytes": (C.c_size_t, []),
+    "nsb_deform_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
+                                      C.POINTER(DeformBwdArgs), C.c_void_p]),
     "nsb_hash_blend_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "nsb_composite_forward": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),

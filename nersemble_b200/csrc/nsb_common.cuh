@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "nsb.h"
 
@@ -47,10 +48,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // Spin with back-off: a waiting warp must not burn issue slots the gather warps need
 // (ncu r1a: 26% of all issued instructions were TRYWAIT/YIELD/BRA of the idle producer).
+#ifndef NSB_SPIN_LIMIT
+#define NSB_SPIN_LIMIT (1u << 27)   // ~several seconds: a protocol bug traps instead of hanging the GPU
+#endif
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if (++spins > NSB_SPIN_LIMIT) {
+            printf("nsb: mbarrier wait timed out (smem 0x%x parity %u block %d thread %d)\n", smem_u32(bar), parity,
+                   (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
     }
 }
 // global -> shared bulk async copy (UBLKCP), completion signalled on an mbarrier

@@ -936,6 +936,9 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                         }
                     }
                     ts.enc[m][kt][lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    if (kMT == 1 && A.out.deform_enc)
+                        reinterpret_cast<uint4 *>(A.out.deform_enc)[((tile * kTensorWarps + warp) * 3 + kt) * 32 + lane] =
+                            make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
             // per-row bias pointers: layers 0/4 use the per-timestep code bias, the others the layer bias
             const float *cb[kMT][2];
@@ -960,6 +963,13 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             auto skip_a = [&](int m, int kt, uint32_t(&a)[4]) {
                 if (kt < 8) hid1(m, kt, a); else in_a(m, kt - 8, a);
             };
+            auto save_act = [&](int layer, int buf) {   // training: keep the layer output for the backward pass
+                if (kMT == 1 && A.out.deform_acts) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(A.out.deform_acts) + (((size_t)tile * kTensorWarps + warp) * 6 + layer) * 256;
+#pragma unroll
+                    for (int kt = 0; kt < 8; ++kt) dst[kt * 32 + lane] = ts.act[buf][0][kt][lane];
+                }
+            };
             const float *b0[kMT][2], *b4[kMT][2], *bl[kMT][2];
 #pragma unroll
             for (int m = 0; m < kMT; ++m)
@@ -972,25 +982,31 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             // layer 0: posenc (48) -> act[0]; the 128 warp-code columns are in the bias
             zero_acc2(acc); ring_gemm2(acc, kT_L0, 3, in_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], b0, q, lane);
             zero_acc2(acc); ring_gemm2(acc, kT_L0 + 3, 3, in_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], b0, q, lane);
+            save_act(0, 0);
             // layer 1: act[0] -> act[1]
             layer_bias(1);
             zero_acc2(acc); ring_gemm2(acc, kT_L1, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
             zero_acc2(acc); ring_gemm2(acc, kT_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            save_act(1, 1);
             // layer 2: act[1] -> act[0]
             layer_bias(2);
             zero_acc2(acc); ring_gemm2(acc, kT_L2, 8, hid1, sm, rf, lane); relu_store2<0>(acc, ts.act[0], bl, q, lane);
             zero_acc2(acc); ring_gemm2(acc, kT_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1>(acc, ts.act[0], bl, q, lane);
+            save_act(2, 0);
             // layer 3: act[0] -> act[1]
             layer_bias(3);
             zero_acc2(acc); ring_gemm2(acc, kT_L3, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
             zero_acc2(acc); ring_gemm2(acc, kT_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            save_act(3, 1);
             // layer 4 (skip): [act[1] | posenc] -> act[0]
             zero_acc2(acc); ring_gemm2(acc, kT_L4, 11, skip_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], b4, q, lane);
             zero_acc2(acc); ring_gemm2(acc, kT_L4 + 11, 11, skip_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], b4, q, lane);
+            save_act(4, 0);
             // layer 5: act[0] -> act[1]
             layer_bias(5);
             zero_acc2(acc); ring_gemm2(acc, kT_L5, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
             zero_acc2(acc); ring_gemm2(acc, kT_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            save_act(5, 1);
             // heads (last chunk: slabs 92,93)
             float hacc[kMT][2][4];
 #pragma unroll

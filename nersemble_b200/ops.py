@@ -49,6 +49,7 @@ class NativeParams:
     levels: dict
     n_timesteps: int
     field_packed_t: Optional[torch.Tensor] = None     # half, transposed field weights (backward)
+    deform_packed_t: Optional[torch.Tensor] = None    # half, transposed deformation weights (backward)
     deform_packed_tb: Optional[torch.Tensor] = None   # half, fragment order, no warp-code columns
     deform_code_bias: Optional[torch.Tensor] = None   # float [T, 2, 128]
 
@@ -89,6 +90,8 @@ class NativeParams:
         P = NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
         if deform is not None:
             P.deform_packed_tb, P.deform_code_bias = dtb, dcb
+            P.deform_packed_t = packing.pack_deform_bwd([w.to(dev) for w in deform["stem_w"]], deform["r_w"].to(dev),
+                                                        deform["v_w"].to(dev))
         P.field_packed_t = fpt
         return P
 
@@ -185,6 +188,11 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
         out["feat"] = torch.empty((n, 32), dtype=torch.float16, device=dev); o.feat = _ptr(out["feat"])
     if "xs" in want:
         out["xs"] = torch.empty((n, 4), dtype=_F32, device=dev); o.xs = _ptr(out["xs"])
+    if "deform_acts" in want:   # training forward: stem activations + posenc fragments for nsb_deform_backward
+        n_tiles = (n + 127) // 128
+        out["deform_acts"] = torch.empty((n_tiles, 8, 6, 8, 32, 4), dtype=torch.int32, device=dev)
+        out["deform_enc"] = torch.empty((n_tiles, 8, 3, 32, 4), dtype=torch.int32, device=dev)
+        o.deform_acts, o.deform_enc = _ptr(out["deform_acts"]), _ptr(out["deform_enc"])
     if n == 0:
         return out
     opts = make_opts(window_hash, window_deform, use_deformation, "rgb" in want, disable_initial, soft_transition)
@@ -257,6 +265,39 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
     opts = make_opts(window_hash, None, False, True, disable_initial, soft_transition)
     cp = P.c_params()
     _lib.check(lib.nsb_field_backward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(a), _stream()), "nsb_field_backward")
+    return out
+
+
+def deform_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_xs: torch.Tensor, *, window_deform=None,
+                    loss_scale: float = 128.0, **sample_kw) -> Dict[str, torch.Tensor]:
+    """Backward of the SE(3) deformation field (nsb_deform_backward).  saved: deform_acts, deform_enc from
+    field_forward(want=(..., "deform_acts")); d_xs from field_backward(want_dx=True).  Returns fp32 gradients in
+    the reference layouts: d_stem_w (list of 6), d_stem_b [6,128], d_r_w, d_r_b, d_v_w, d_v_b, d_warp_codes [T,128]."""
+    lib = _lib.load()
+    keep = []
+    s = _lib.Samples()
+    n = _fill_samples(s, keep, **sample_kw)
+    dev = d_xs.device
+    a = _lib.DeformBwdArgs()
+    dxs = _f32c(d_xs).reshape(-1, 3)
+    a.deform_packed_t = _ptr(P.deform_packed_t)
+    a.deform_acts, a.deform_enc, a.d_xs = _ptr(saved["deform_acts"]), _ptr(saved["deform_enc"]), _ptr(dxs)
+    a.loss_scale = float(loss_scale)
+    dims = [(128, 173), (128, 128), (128, 128), (128, 128), (128, 301), (128, 128)]
+    out = {"d_stem_w": [torch.zeros(d, dtype=_F32, device=dev) for d in dims],
+           "d_stem_b": torch.zeros((6, 128), dtype=_F32, device=dev),
+           "d_r_w": torch.zeros((3, 128), dtype=_F32, device=dev), "d_r_b": torch.zeros((3,), dtype=_F32, device=dev),
+           "d_v_w": torch.zeros((3, 128), dtype=_F32, device=dev), "d_v_b": torch.zeros((3,), dtype=_F32, device=dev),
+           "d_warp_codes": torch.zeros((P.n_timesteps, 128), dtype=_F32, device=dev)}
+    for l in range(6):
+        a.d_stem_w[l] = _ptr(out["d_stem_w"][l])
+    a.d_stem_b, a.d_r_w, a.d_r_b = _ptr(out["d_stem_b"]), _ptr(out["d_r_w"]), _ptr(out["d_r_b"])
+    a.d_v_w, a.d_v_b, a.d_warp_codes = _ptr(out["d_v_w"]), _ptr(out["d_v_b"]), _ptr(out["d_warp_codes"])
+    if n == 0:
+        return out
+    opts = make_opts(None, window_deform, True, False)
+    cp = P.c_params()
+    _lib.check(lib.nsb_deform_backward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(a), _stream()), "nsb_deform_backward")
     return out
 
 

@@ -142,6 +142,24 @@ def pack_deform_tb(stem_w, stem_b, r_w, r_b, v_w, v_b, warp_codes: torch.Tensor)
     return packed.contiguous(), torch.stack(cb, 1).contiguous()
 
 
+def pack_deform_bwd(stem_w, r_w, v_w) -> torch.Tensor:
+    """Transposed weights for the delta GEMMs of nsb_deform_backward, in order of use:
+    heads, L5, L4[:, hidden], L4[:, code], L3, L2, L1, L0[:, code]  (K = 128 outputs; N = 128 columns in two halves).
+    Hidden columns of layer 4 are the reference columns 173.., code columns are 45..172 of layers 0 and 4."""
+    o128 = list(range(128))
+    heads = torch.cat([v_w.detach().float(), r_w.detach().float()], 0)            # [6, 128]: rows = (v, r) outputs
+    parts = [pack_mma_b(heads.t(), list(range(6)) + [-1] * 10, 64)]
+    def T(w, cols):
+        return pack_mma_b(w.detach().float()[:, cols].t(), o128, 64)
+    code = list(range(45, DEFORM_IN_DIM))
+    hidden4 = list(range(DEFORM_IN_DIM, DEFORM_IN_DIM + 128))
+    parts += [T(stem_w[5], o128), T(stem_w[4], hidden4), T(stem_w[4], code), T(stem_w[3], o128), T(stem_w[2], o128),
+              T(stem_w[1], o128), T(stem_w[0], code)]
+    packed = torch.cat(parts)
+    assert packed.numel() * 2 == 114 * 2048
+    return packed.contiguous()
+
+
 def head_input_colmap() -> List[int]:
     """Kernel colour-MLP input column -> reference column of [d'(3) | geo(15) | ones(14)]
     (fields/nersemble_nerfacto_field.py:371-377 + tcnn pad-with-1.0).  Kernel order:

@@ -96,3 +96,35 @@ def test_field_backward_vs_autograd():
     assert ((dt != 0) == (P.tables.grad != 0)).float().mean() > 0.999        # same entries touched
     cos = torch.nn.functional.cosine_similarity(dt.reshape(1, -1), P.tables.grad.reshape(1, -1)).item()
     assert cos > 0.9995, cos
+
+
+def test_deform_backward_vs_autograd():
+    """SE(3) deformation field: gradients of the 6 stem layers, mlp_r/mlp_v and the warp-code embedding."""
+    from nersemble_b200 import ops
+    knobs = dict(TRAINED); knobs["deform_last_scale"] = 0.05        # |r| above the 1e-2 clamp: exercises d theta / d r
+    P = pl.random_params(**knobs)
+    NP = native_from_oracle(P, DEV)
+    g = torch.Generator().manual_seed(9)
+    n = 333
+    lo, hi = P.aabb[0], P.aabb[1]
+    pos = lo + (torch.rand((n, 3), generator=g) * 0.9 + 0.05) * (hi - lo)
+    tsteps = torch.sort(torch.randint(0, 4, (n,), generator=g))[0]
+    times = tsteps.float()[:, None] / 3
+    w_deform = 5.5
+    P.requires_grad_(True)
+    off = pl.compute_offsets(P, pos, P.time_emb_deform[tsteps], w_deform)
+    g_off = torch.randn((n, 3), generator=g)
+    (off * g_off).sum().backward()
+
+    kw = dict(positions=pos.to(DEV), sample_times=times.to(DEV))
+    saved = ops.field_forward(NP, window_hash=None, window_deform=w_deform, use_deformation=True,
+                              want=("offsets", "deform_acts"), **kw)
+    torch.testing.assert_close(saved["offsets"].cpu(), off.detach(), rtol=5e-3, atol=5e-5)
+    d_xs = (g_off * (hi - lo)).to(DEV)                               # offsets enter the hash input as offset / size
+    gr = ops.deform_backward(NP, saved, d_xs, window_deform=w_deform, loss_scale=64.0, **kw)
+    for l in range(6):
+        assert _relerr(gr["d_stem_w"][l].cpu(), P.deform_w[l].grad) < 4e-2, l
+        assert _relerr(gr["d_stem_b"][l].cpu(), P.deform_b[l].grad) < 4e-2, l
+    assert _relerr(gr["d_r_w"].cpu(), P.r_w.grad) < 3e-2 and _relerr(gr["d_v_w"].cpu(), P.v_w.grad) < 3e-2
+    assert _relerr(gr["d_r_b"].cpu(), P.r_b.grad) < 3e-2 and _relerr(gr["d_v_b"].cpu(), P.v_b.grad) < 3e-2
+    assert _relerr(gr["d_warp_codes"].cpu(), P.time_emb_deform.grad) < 4e-2
