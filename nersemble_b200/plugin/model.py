@@ -83,40 +83,52 @@ class NeRSembleNGPModelConfig(BaseModelConfig):
 
 
 class _RenderFunction(torch.autograd.Function):
-    """Differentiable fused render (training).  Forward = nsb_field_forward (saving the blended features and
-    warped positions) + nsb_composite_forward; backward = nsb_composite_backward -> nsb_field_backward, with the
-    fp32 gradients mapped back to the reference's parameter layouts (8 tcnn grids, flat tcnn MLP params,
-    time embedding).  Round 1: hash-ensemble field only (config.use_deformation_field=False)."""
+    """Differentiable fused render (training).  Forward = nsb_field_forward (saving the blended features, the warped
+    positions and the deformation activations) + nsb_composite_forward; backward = nsb_composite_backward ->
+    nsb_field_backward -> nsb_deform_backward, with the fp32 gradients mapped back to the reference's parameter
+    layouts (8 tcnn grids, flat tcnn MLP params, nn.Linear weights/biases, the two time embeddings)."""
 
     @staticmethod
-    def forward(ctx, model, origins, directions, ray_times, starts, ends, ray_indices, packed_info, wh, *params):
+    def forward(ctx, model, origins, directions, ray_times, starts, ends, ray_indices, packed_info, wh, wd, *params):
         P = model.native_params()
+        deform = model.config.use_deformation_field
         kw = dict(origins=origins, directions=directions, ray_times=ray_times, t_starts=starts, t_ends=ends,
                   ray_indices=ray_indices)
-        f = ops.field_forward(P, window_hash=wh, window_deform=None, use_deformation=False,
-                              want=("sigma", "rgb", "feat", "xs"), **kw, **model._blend_opts())
-        c = ops.composite(packed_info, starts, ends, f["sigma"], f["rgb"], None, training=True)
-        ctx.model, ctx.P, ctx.kw, ctx.wh = model, P, kw, wh
-        ctx.saved = dict(feat=f["feat"], xs=f["xs"], sigma=f["sigma"], rgb=f["rgb"])
+        want = ("sigma", "rgb", "feat", "xs") + (("offsets", "deform_acts") if deform else ())
+        f = ops.field_forward(P, window_hash=wh, window_deform=wd, use_deformation=deform, want=want, **kw,
+                              **model._blend_opts())
+        c = ops.composite(packed_info, starts, ends, f["sigma"], f["rgb"], f["offsets"] if deform else None, training=True)
+        ctx.model, ctx.P, ctx.kw, ctx.wh, ctx.wd, ctx.deform = model, P, kw, wh, wd, deform
+        ctx.saved = {k: f[k] for k in ("feat", "xs", "sigma", "rgb")}
+        if deform:
+            ctx.saved.update(deform_acts=f["deform_acts"], deform_enc=f["deform_enc"])
         ctx.packed_info, ctx.workspace = packed_info, c["workspace"]
-        ctx.mark_non_differentiable(packed_info)
-        return c["rgb"], c["accumulation"], c["depth"], c["weights"]
+        outs = (c["rgb"], c["accumulation"], c["depth"], c["weights"])
+        if deform:
+            ctx.mark_non_differentiable(f["offsets"], c["deformation"])
+            outs += (c["deformation"], f["offsets"])
+        return outs
 
     @staticmethod
-    def backward(ctx, g_rgb, g_acc, g_depth, g_weights):
-        model = ctx.model
-        kw = ctx.kw
+    def backward(ctx, g_rgb, g_acc, g_depth, g_weights, *unused):
+        from .. import packing
+        model, kw = ctx.model, ctx.kw
+        ls = float(getattr(model, "mlp_loss_scale", 128.0))
         d_sigma, d_rgb = ops.composite_backward(ctx.packed_info, kw["t_starts"], kw["t_ends"], ctx.saved["sigma"],
                                                 ctx.saved["rgb"], ctx.workspace, g_rgb,
                                                 None if g_acc is None else g_acc.reshape(-1),
                                                 None if g_depth is None else g_depth.reshape(-1),
                                                 None if g_weights is None else g_weights.reshape(-1))
-        g = ops.field_backward(ctx.P, ctx.saved, d_sigma, d_rgb, window_hash=ctx.wh,
-                               loss_scale=float(getattr(model, "mlp_loss_scale", 128.0)), **kw, **model._blend_opts())
-        from .. import packing
-        grids = packing.tables_to_tcnn(g["d_tables"])
-        grads = list(grids) + [g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
-        return (None,) * 9 + tuple(grads)
+        g = ops.field_backward(ctx.P, ctx.saved, d_sigma, d_rgb, window_hash=ctx.wh, loss_scale=ls, want_dx=ctx.deform,
+                               **kw, **model._blend_opts())
+        grads = list(packing.tables_to_tcnn(g["d_tables"])) + [g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
+        if ctx.deform:
+            d = ops.deform_backward(ctx.P, ctx.saved, g["d_xs"], window_deform=ctx.wd, loss_scale=ls, **kw)
+            grads.append(d["d_warp_codes"])
+            for l in range(6):
+                grads += [d["d_stem_w"][l], d["d_stem_b"][l]]
+            grads += [d["d_r_w"], d["d_r_b"], d["d_v_w"], d["d_v_b"]]
+        return (None,) * 10 + tuple(grads)
 
 
 def _segment_exclusive_sum(x: Tensor, ray_indices: Tensor, n_rays: int) -> Tensor:
@@ -266,8 +278,6 @@ class NeRSembleNGPModel(nn.Module):
         wh, wd = self._windows()
         num_rays = len(ray_bundle)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_grad and cfg.use_deformation_field:
-            _no_autograd(*self.parameters())     # raises: the deformation-field backward is round-2 work
         with torch.no_grad():
             ray_samples, ray_indices = self.sampler(
                 ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
@@ -288,10 +298,23 @@ class NeRSembleNGPModel(nn.Module):
             he = self.field.hash_ensemble
             params = [m.params for m in he.hash_encodings] + [self.field.mlp_base.params, self.field.mlp_head.params,
                                                                self.time_embedding.weight]
-            rgb, acc, depth, weights = _RenderFunction.apply(self, ray_bundle.origins, ray_bundle.directions, ray_times, starts,
-                                                             ends, ray_indices, packed_info, wh, *params)
-            return {"rgb": rgb, "accumulation": acc, "depth": depth, "num_samples_per_ray": packed_info[:, 1],
-                    "ray_samples": (ray_samples,), "ray_indices": (ray_indices,), "weights": (weights,)}
+            if cfg.use_deformation_field:
+                if not cfg.use_separate_deformation_time_embedding:
+                    raise NotImplementedError("training with a shared time embedding (use_separate_deformation_time_embedding=False)")
+                se3 = self.deformation_field.se3_field
+                params.append(self.time_embedding_deformation.weight)
+                for layer in se3.mlp_stem.layers:
+                    params += [layer.weight, layer.bias]
+                params += [se3.mlp_r.layers[0].weight, se3.mlp_r.layers[0].bias, se3.mlp_v.layers[0].weight, se3.mlp_v.layers[0].bias]
+            res = _RenderFunction.apply(self, ray_bundle.origins, ray_bundle.directions, ray_times, starts, ends, ray_indices,
+                                        packed_info, wh, wd, *params)
+            rgb, acc, depth, weights = res[:4]
+            outputs = {"rgb": rgb, "accumulation": acc, "depth": depth, "num_samples_per_ray": packed_info[:, 1],
+                       "ray_samples": (ray_samples,), "ray_indices": (ray_indices,), "weights": (weights,)}
+            if cfg.use_deformation_field:
+                outputs["deformation"] = res[4]
+                ray_samples.frustums.set_offsets(res[5])
+            return outputs
         out = ops.render_packed(self.native_params(), ray_bundle.origins, ray_bundle.directions, ray_times, starts, ends,
                                 ray_indices, packed_info, window_hash=wh, window_deform=wd,
                                 use_deformation=cfg.use_deformation_field, training=self.training, **self._blend_opts())

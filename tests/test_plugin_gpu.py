@@ -208,3 +208,68 @@ def test_training_step_gradients_and_descent():
         opt.step()
     assert l.item() < 0.85 * first, (first, l.item())
     Precision.mode = "reference"
+
+
+def test_full_recipe_training_step_gradients():
+    """The full recipe (deformation field + hash ensemble): end-to-end parameter gradients through the plugin model vs
+    autograd through the oracle, then Adam steps over all three parameter groups reduce the loss."""
+    from nersemble_b200 import packing
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    from oracle.gen_golden import blob_grid, ring_rays
+    from oracle.tp import nerfacc_cpu
+    Precision.mode = "kernel"
+    knobs = dict(seed=19980801, n_timesteps=4, log2_hashmap_size=14, table_scale=0.5, time_std_scale=100.0, deform_last_scale=0.02)
+    P = pl.random_params(**knobs)
+    m = make_model(T=4, log2T=14, lambda_near_loss=0, lambda_empty_loss=0, lambda_depth_loss=0, lambda_dist_loss=1e-2,
+                   lambda_alpha_loss=1e-2)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).train()
+    m.sched_window_hash_encodings.value = 32.0
+    m.sched_window_deform.value = 5.5
+    occ = blob_grid(3)
+    m.occupancy_grid.binaries[0] = occ.to(DEV)
+    R = 64
+    o, d, times, cams = ring_rays(R, 21)
+    gen = torch.Generator().manual_seed(1)
+    batch = {"image": torch.rand((R, 3), generator=gen), "alpha_map": torch.randint(0, 256, (R, 1), generator=gen).float()}
+    rb = RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                   camera_indices=cams.to(DEV), times=times.to(DEV))
+    m.sampler.eval()
+    out = m.get_outputs(rb)
+    assert "deformation" in out and out["ray_samples"][0].frustums.offsets is not None
+    loss = sum(m.get_loss_dict(out, batch).values())
+    loss.backward()
+    # ---- oracle
+    ts, te, ri = pl.sample_occupancy(P, o, d, times, occ[None], 0.0, 0.011, 0.2, 1e3, 1e-2, 0.0, training=False)
+    assert torch.equal(ri, out["ray_indices"][0].cpu())
+    P.requires_grad_(True)
+    r = pl.render(P, o, d, times, ts, te, ri, window_hash=32.0, window_deform=5.5, training=True)
+    o_ld = pl.loss_dict(r, ts, te, ri, batch, eps_depth=0.5, lam_alpha=1e-2, lam_near=0, lam_empty=0, lam_depth=0, lam_dist=1e-2)
+    o_loss = sum(o_ld.values())
+    o_loss.backward()
+    assert abs(loss.item() - o_loss.item()) < 3e-3 * abs(o_loss.item()) + 1e-5
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    se3 = m.deformation_field.se3_field
+    for l, layer in enumerate(se3.mlp_stem.layers):
+        assert rel(layer.weight.grad.cpu(), P.deform_w[l].grad) < 6e-2, l
+        assert rel(layer.bias.grad.cpu(), P.deform_b[l].grad) < 6e-2, l
+    assert rel(se3.mlp_r.layers[0].weight.grad.cpu(), P.r_w.grad) < 5e-2
+    assert rel(se3.mlp_v.layers[0].weight.grad.cpu(), P.v_w.grad) < 5e-2
+    assert rel(m.time_embedding_deformation.weight.grad.cpu(), P.time_emb_deform.grad) < 6e-2
+    assert rel(m.time_embedding.weight.grad.cpu(), P.time_emb.grad) < 4e-2
+    assert rel(m.field.mlp_head.params.grad.cpu(), torch.cat([x.grad.reshape(-1) for x in P.head_w])) < 4e-2
+    got_t = packing.tables_from_tcnn([mm.params.grad.cpu() for mm in m.field.hash_ensemble.hash_encodings])
+    assert torch.nn.functional.cosine_similarity(got_t.reshape(1, -1), P.tables.grad.reshape(1, -1)).item() > 0.999
+    # ---- optimiser steps over the reference's three parameter groups (train_nersemble.py:243-256)
+    groups = m.get_param_groups()
+    opt = torch.optim.Adam([{"params": groups["fields"], "lr": 5e-3}, {"params": groups["embeddings"], "lr": 5e-3},
+                            {"params": [p for p in groups["deformation_field"] if p.requires_grad], "lr": 1e-3}], eps=1e-15)
+    first = loss.item()
+    for _ in range(20):
+        opt.zero_grad(set_to_none=True)
+        out = m.get_outputs(rb)
+        l = sum(m.get_loss_dict(out, batch).values())
+        l.backward()
+        opt.step()
+    assert l.item() < 0.85 * first, (first, l.item())
+    Precision.mode = "reference"
