@@ -2,10 +2,9 @@
 
 Same class names, constructor/forward signatures, config dataclasses, output keys and
 state_dict keys as /root/reference/src/nersemble/nerfstudio/** (cited per class), with all
-arithmetic behind libnsb (CUDA, sm_100a).  Forward / inference path (eval render, density_fn,
-sampler incl. the no-grad training pre-pass, occupancy update).  The backward kernels are
-round-2 work: calling these modules with autograd enabled raises instead of silently
-returning graph-less tensors.
+arithmetic behind libnsb (CUDA, sm_100a).  NeRSembleNGPModel.get_outputs is differentiable
+(fused forward + backward kernels); the stand-alone component modules are forward-only and
+raise when called with autograd enabled instead of silently returning graph-less tensors.
 """
 from .components import (HashEnsemble, HashEnsembleConfig, SE3DeformationField, SE3DeformationFieldConfig,
                          TCNNHashEncodingConfig, GenericScheduler)

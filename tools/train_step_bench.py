@@ -1,0 +1,55 @@
+"""Time one full training step (fwd + losses + bwd + Adam [+ gradient all-reduce]) of the plugin model at the
+BASELINE config-3/5 shape: 4096 rays, dense 256 samples/ray (2^20 samples), full-size tables, T = 24.
+    python tools/train_step_bench.py [--steps 5]            (1 GPU)
+    torchrun --nproc-per-node N tools/train_step_bench.py   (N GPUs: + one NCCL all-reduce of all gradients)"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+import torch.distributed as dist
+import bench
+from test_plugin_cpu import make_model
+from nersemble_b200.nerfstudio_shim import RayBundle
+from nersemble_b200.distributed import allreduce_gradients
+
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); args = ap.parse_args()
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr_ = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr_); dev = torch.device("cuda", lr_)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+torch.manual_seed(0)
+m = make_model(T=24, log2T=19, lambda_near_loss=0, lambda_empty_loss=0, lambda_depth_loss=0).to(dev).train()
+with torch.no_grad():   # trained-like scale so that densities are non-trivial
+    for g in m.field.hash_ensemble.hash_encodings:
+        g.params.uniform_(-0.5, 0.5)
+    m.time_embedding.weight.normal_(0, 0.18); m.time_embedding_deformation.weight.normal_(0, 0.09)
+m.occupancy_grid.binaries[:] = True           # dense march (config 5: --disable_occupancy_grid-like sample count)
+m.config.far_plane = 1e3
+o, d, t = bench.synthetic_rays(4096, 1000 + rank, dev)
+rb = RayBundle(origins=o, directions=d, pixel_area=torch.ones(4096, 1, device=dev),
+               camera_indices=torch.zeros(4096, 1, dtype=torch.long, device=dev), times=t)
+batch = {"image": torch.rand(4096, 3, device=dev), "alpha_map": torch.randint(0, 256, (4096, 1), device=dev).float()}
+groups = m.get_param_groups()
+opt = torch.optim.Adam([{"params": groups["fields"], "lr": 5e-3}, {"params": groups["embeddings"], "lr": 5e-3},
+                        {"params": [p for p in groups["deformation_field"] if p.requires_grad], "lr": 1e-3}], eps=1e-15)
+m.sampler.eval()
+def ev(): e = torch.cuda.Event(enable_timing=True); e.record(); return e
+rows = []
+for step in range(args.steps + 2):
+    e0 = ev(); opt.zero_grad(set_to_none=True)
+    out = m.get_outputs(rb); e1 = ev()
+    loss = sum(m.get_loss_dict(out, batch).values()); e2 = ev()
+    loss.backward(); e3 = ev()
+    allreduce_gradients([p for gr in groups.values() for p in gr]); e4 = ev()
+    opt.step(); e5 = ev()
+    torch.cuda.synchronize()
+    if step >= 2:
+        rows.append([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e3.elapsed_time(e4), e4.elapsed_time(e5)])
+avg = [sum(r[i] for r in rows) / len(rows) for i in range(5)]
+n_samples = int(out["num_samples_per_ray"].sum().item())
+if rank == 0:
+    print(json.dumps({"n_gpus": world, "samples_per_gpu": n_samples, "loss": loss.item(),
+                      "ms": dict(forward=avg[0], losses=avg[1], backward=avg[2], allreduce=avg[3], adam=avg[4], total=sum(avg)),
+                      "it_per_s": 1000.0 / sum(avg), "M_samples_per_s": n_samples * world / sum(avg) / 1e3}))
+if world > 1:
+    dist.destroy_process_group()
