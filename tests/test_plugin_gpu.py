@@ -273,3 +273,50 @@ def test_full_recipe_training_step_gradients():
         opt.step()
     assert l.item() < 0.85 * first, (first, l.item())
     Precision.mode = "reference"
+
+
+def test_loss_curve_agrees_with_oracle_for_first_steps():
+    """the first optimiser steps of the CUDA training path follow the oracle's loss curve
+    (same parameters, rays, losses and Adam hyper-parameters; oracle = autograd through oracle/pipeline.py on CPU)."""
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    from oracle.gen_golden import blob_grid, ring_rays
+    Precision.mode = "kernel"
+    knobs = dict(seed=19980801, n_timesteps=4, log2_hashmap_size=12, table_scale=0.5, time_std_scale=100.0, deform_last_scale=0.02)
+    P = pl.random_params(**knobs)
+    m = make_model(T=4, log2T=12, lambda_near_loss=0, lambda_empty_loss=0, lambda_depth_loss=0, lambda_dist_loss=1e-2,
+                   lambda_alpha_loss=1e-2)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).train()
+    m.sched_window_hash_encodings.value = 32.0
+    m.sched_window_deform.value = 5.5
+    occ = blob_grid(3)
+    m.occupancy_grid.binaries[0] = occ.to(DEV)
+    m.sampler.eval()
+    R = 48
+    o, d, times, cams = ring_rays(R, 33)
+    gen = torch.Generator().manual_seed(2)
+    batch = {"image": torch.rand((R, 3), generator=gen), "alpha_map": torch.randint(0, 256, (R, 1), generator=gen).float()}
+    rb = RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                   camera_indices=cams.to(DEV), times=times.to(DEV))
+    groups = m.get_param_groups()
+    opt = torch.optim.Adam([{"params": groups["fields"], "lr": 5e-3}, {"params": groups["embeddings"], "lr": 5e-3},
+                            {"params": [p for p in groups["deformation_field"] if p.requires_grad], "lr": 1e-3}], eps=1e-15)
+    P.requires_grad_(True)
+    o_opt = torch.optim.Adam([{"params": [P.tables] + P.base_w + P.head_w, "lr": 5e-3},
+                              {"params": [P.time_emb, P.time_emb_deform], "lr": 5e-3},
+                              {"params": P.deform_w + P.deform_b + [P.r_w, P.r_b, P.v_w, P.v_b], "lr": 1e-3}], eps=1e-15)
+    ts, te, ri = pl.sample_occupancy(P, o, d, times, occ[None], 0.0, 0.011, 0.2, 1e3, 1e-2, 0.0, training=False)
+    got, want = [], []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        l = sum(m.get_loss_dict(m.get_outputs(rb), batch).values())
+        l.backward(); opt.step(); got.append(l.item())
+        o_opt.zero_grad(set_to_none=True)
+        r = pl.render(P, o, d, times, ts, te, ri, window_hash=32.0, window_deform=5.5, training=True)
+        ol = sum(pl.loss_dict(r, ts, te, ri, batch, eps_depth=0.5, lam_alpha=1e-2, lam_near=0, lam_empty=0, lam_depth=0,
+                              lam_dist=1e-2).values())
+        ol.backward(); o_opt.step(); want.append(ol.item())
+    assert want[-1] < want[0]
+    for a, b in zip(got, want):
+        assert abs(a - b) < 2e-2 * abs(b), (got, want)
+    Precision.mode = "reference"

@@ -12,7 +12,7 @@ from test_plugin_cpu import make_model
 from nersemble_b200.nerfstudio_shim import RayBundle
 from nersemble_b200.distributed import allreduce_gradients
 
-ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); args = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true"); args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr_ = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr_); dev = torch.device("cuda", lr_)
 if world > 1:
@@ -45,6 +45,16 @@ for step in range(args.steps + 2):
     torch.cuda.synchronize()
     if step >= 2:
         rows.append([e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), e3.elapsed_time(e4), e4.elapsed_time(e5)])
+if args.profile and rank == 0:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        opt.zero_grad(set_to_none=True)
+        out = m.get_outputs(rb)
+        loss = sum(m.get_loss_dict(out, batch).values())
+        loss.backward()
+        opt.step()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
 avg = [sum(r[i] for r in rows) / len(rows) for i in range(5)]
 n_samples = int(out["num_samples_per_ray"].sum().item())
 if rank == 0:
