@@ -277,7 +277,8 @@ class NeRSembleNGPModel(nn.Module):
         cfg = self.config
         wh, wd = self._windows()
         num_rays = len(ray_bundle)
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # the differentiable path is the TRAINING path (training-mode compositing); eval renders are inference-only
+        needs_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         with torch.no_grad():
             ray_samples, ray_indices = self.sampler(
                 ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
