@@ -184,6 +184,13 @@ typedef struct nsb_field_bwd_args {
     float *d_blend_codes;         /* [n_timesteps][32], += (NULL: skip) */
     float *d_xs;                  /* [n][3] out (NULL: skip): dL/d(normalised warped position), tcnn's
                                      kernel_grid_backward_input; feeds the deformation-field backward */
+    /* Rank-1 table-gradient path (table-indexed blend codes only).  The gradient of a table line is
+     * cw_t[member] x (w_corner * dfeat[level, feat]): all samples of one timestep share cw_t, so the scatter only
+     * accumulates the 2-vector per (timestep slot, line) -- 32x fewer atomics -- and nsb expands
+     * d_tables[line][m][f] = sum_t cw_t[m] G[t][line][f] (and the time-code gradient) in one dense pass. */
+    float *g_rank1;               /* workspace [n_slots][total_entries][2], zeroed by the caller; NULL: direct scatter */
+    const int32_t *ts_slot;       /* [n_timesteps] -> slot in [0, n_slots) or -1 (timestep absent from this batch) */
+    int32_t n_slots;
 } nsb_field_bwd_args;
 int nsb_field_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                        const nsb_field_bwd_args *args, void *stream);

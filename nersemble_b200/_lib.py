@@ -53,7 +53,8 @@ class FieldBwdArgs(C.Structure):
     _fields_ = [("field_packed_t", C.c_void_p), ("feat", C.c_void_p), ("xs", C.c_void_p), ("sigma", C.c_void_p),
                 ("rgb", C.c_void_p), ("d_sigma", C.c_void_p), ("d_rgb", C.c_void_p), ("loss_scale", C.c_float),
                 ("d_feat", C.c_void_p), ("d_base_w", C.c_void_p), ("d_head_w", C.c_void_p), ("d_tables", C.c_void_p),
-                ("d_blend_codes", C.c_void_p), ("d_xs", C.c_void_p)]
+                ("d_blend_codes", C.c_void_p), ("d_xs", C.c_void_p), ("g_rank1", C.c_void_p), ("ts_slot", C.c_void_p),
+                ("n_slots", C.c_int32)]
 
 
 class CompositeArgs(C.Structure):

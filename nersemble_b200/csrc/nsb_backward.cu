@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // table + time-code gradients: one warp per sample
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -286,6 +289,12 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
         int ts = __float2int_rn(__fmul_rn(tt, (float)(K.P.n_timesteps - 1)));
         ts = min(max(ts, 0), K.P.n_timesteps - 1);
         if (ts != acc_ts) { flush_codes(); acc_ts = ts; }
+        const bool rank1 = K.B.g_rank1 != nullptr;
+        float *gslot = nullptr;
+        if (rank1) {
+            const int slot = K.B.ts_slot[ts];
+            gslot = K.B.g_rank1 + (size_t)slot * ((size_t)K.P.levels.offset[NSB_MAX_LEVELS - 1] + K.P.levels.entries[NSB_MAX_LEVELS - 1]) * 2;
+        }
         const float *code_row = K.S.sample_blend_codes ? K.S.sample_blend_codes + s * NSB_MEMBERS
                                                        : K.P.blend_codes + (size_t)ts * NSB_MEMBERS;
         const float4 c0 = __ldg(reinterpret_cast<const float4 *>(code_row) + 2 * q);
@@ -319,7 +328,10 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
             }
             const size_t entry = (size_t)(off + idx);
             const float g0 = w * df.x, g1 = w * df.y;
-            if (K.B.d_blend_codes || K.B.d_xs) {
+            if (rank1) {   // 2-vector per (timestep, line); member expansion and code gradient happen in hash_expand_kernel
+                if (q == 0 && (g0 != 0.f || g1 != 0.f)) red_add_v2(gslot + entry * 2, g0, g1);
+            }
+            if ((K.B.d_blend_codes && !rank1) || K.B.d_xs) {
                 uint32_t v[8];
                 ldg256(tab + entry * 128, v);
                 float pb0 = 0.f, pb1 = 0.f;   // this lane's share of the member-blended corner value
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
                 ey = fmaf(dy ? t : -t, wx * wz, ey);
                 ez = fmaf(dz ? t : -t, wx * wy, ez);
             }
-            if (K.B.d_tables && (g0 != 0.f || g1 != 0.f)) {
+            if (!rank1 && K.B.d_tables && (g0 != 0.f || g1 != 0.f)) {
                 float *gl = K.B.d_tables + entry * 64 + q * 16;     // fp32 gradient line: [member 32][feat 2]
                 red_add_v4(gl + 0, g0 * cw[0], g1 * cw[0], g0 * cw[1], g1 * cw[1]);
                 red_add_v4(gl + 4, g0 * cw[2], g1 * cw[2], g0 * cw[3], g1 * cw[3]);
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
                 K.B.d_xs[3 * s + 0] = ex * xs.w; K.B.d_xs[3 * s + 1] = ey * xs.w; K.B.d_xs[3 * s + 2] = ez * xs.w;
             }
         }
-        if (K.B.d_blend_codes) {
+        if (K.B.d_blend_codes && !rank1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {   // sum over the 8 corner lanes (lane bits 2..4)
                 float v = dcw[j];
@@ -367,6 +379,71 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
         }
     }
     flush_codes();
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank-1 expansion: d_tables[line][m][f] += sum_slots cw_slot[m] * G[slot][line][f];
+//                   d_codes[t][m]       += scale[m] * sum_lines sum_f V[line][m][f] * G[slot(t)][line][f]
+// one warp per table line (lane = member), grid-stride; G lines that were never touched are skipped.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxSlots = 32;
+
+__global__ void __launch_bounds__(256) hash_expand_kernel(const __grid_constant__ FieldBwdKArgs K, size_t total_entries) {
+    __shared__ float cw_s[kMaxSlots][NSB_MEMBERS];
+    __shared__ int slot_ts[kMaxSlots];
+    const int lane = threadIdx.x & 31, n_slots = K.B.n_slots;
+    for (int i = threadIdx.x; i < kMaxSlots; i += blockDim.x) slot_ts[i] = -1;
+    __syncthreads();
+    for (int t = threadIdx.x; t < K.P.n_timesteps; t += blockDim.x) {
+        const int sl = K.B.ts_slot[t];
+        if (sl >= 0) slot_ts[sl] = t;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_slots * NSB_MEMBERS; i += blockDim.x) {
+        const int sl = i / NSB_MEMBERS, m = i % NSB_MEMBERS, t = slot_ts[sl];
+        float c = 0.f;
+        if (t >= 0) c = __half2float(__float2half_rn(fmaf(K.P.blend_codes[(size_t)t * NSB_MEMBERS + m], K.O.cw_scale[m], K.O.cw_bias[m])));
+        cw_s[sl][m] = c;
+    }
+    __syncthreads();
+    float dcode[kMaxSlots];
+#pragma unroll
+    for (int sl = 0; sl < kMaxSlots; ++sl) dcode[sl] = 0.f;
+    const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    const __half2 *tab = reinterpret_cast<const __half2 *>(K.P.tables);
+    for (size_t e = warp_global; e < total_entries; e += n_warps) {
+        // lane sl reads the 2-vector of slot sl
+        float2 gv = make_float2(0.f, 0.f);
+        if (lane < n_slots) gv = *reinterpret_cast<const float2 *>(K.B.g_rank1 + ((size_t)lane * total_entries + e) * 2);
+        const unsigned touched = __ballot_sync(0xffffffffu, gv.x != 0.f || gv.y != 0.f);
+        if (touched == 0) continue;
+        const float2 v = K.B.d_blend_codes ? __half22float2(tab[e * NSB_MEMBERS + lane]) : make_float2(0.f, 0.f);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < kMaxSlots; ++sl) {
+            if (!((touched >> sl) & 1)) continue;     // warp-uniform
+            const float gx = __shfl_sync(0xffffffffu, gv.x, sl), gy = __shfl_sync(0xffffffffu, gv.y, sl);
+            const float c = cw_s[sl][lane];
+            a0 = fmaf(c, gx, a0);
+            a1 = fmaf(c, gy, a1);
+            dcode[sl] = fmaf(v.x, gx, fmaf(v.y, gy, dcode[sl]));
+        }
+        if (K.B.d_tables) {
+            float2 *dst = reinterpret_cast<float2 *>(K.B.d_tables + (e * NSB_MEMBERS + lane) * 2);
+            float2 cur = *dst;
+            cur.x += a0; cur.y += a1;
+            *dst = cur;
+        }
+    }
+    if (K.B.d_blend_codes) {
+#pragma unroll
+        for (int sl = 0; sl < kMaxSlots; ++sl) {
+            const int t = sl < n_slots ? slot_ts[sl] : -1;
+            if (t >= 0 && dcode[sl] != 0.f)
+                atomicAdd(K.B.d_blend_codes + (size_t)t * NSB_MEMBERS + lane, dcode[sl] * K.O.cw_scale[lane]);
+        }
+    }
 }
 
 static int g_bwd_sms = 0;
@@ -411,8 +488,20 @@ extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_fiel
     if (rc) return rc;
     if (args->d_tables || args->d_blend_codes || args->d_xs) {
         const int blocks = (int)std::min<int64_t>((samples->n_samples + 7) / 8, (int64_t)g_bwd_sms * 8);
+        if (args->g_rank1) {
+            if (!args->ts_slot || args->n_slots < 1 || args->n_slots > kMaxSlots || samples->sample_blend_codes) {
+                set_error("nsb_field_backward: rank-1 path needs ts_slot, 1 <= n_slots <= 32 and table-indexed blend codes");
+                return 1;
+            }
+        }
         hash_bwd_kernel<<<blocks, 256, 0, st>>>(K);
         rc = check_launch("hash_bwd_kernel");
+        if (rc) return rc;
+        if (args->g_rank1 && (args->d_tables || args->d_blend_codes)) {
+            const size_t total = (size_t)params->levels.offset[NSB_MAX_LEVELS - 1] + params->levels.entries[NSB_MAX_LEVELS - 1];
+            hash_expand_kernel<<<g_bwd_sms * 8, 256, 0, st>>>(K, total);
+            rc = check_launch("hash_expand_kernel");
+        }
     }
     return rc;
 }

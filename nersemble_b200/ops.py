@@ -229,8 +229,8 @@ def _fill_samples(s, keep, *, origins=None, directions=None, ray_times=None, t_s
 
 def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Optional[torch.Tensor],
                    d_rgb: Optional[torch.Tensor], *, window_hash=None, loss_scale: float = 128.0,
-                   want_tables: bool = True, want_codes: bool = True, want_dx: bool = False, disable_initial=True,
-                   soft_transition=True,
+                   want_tables: bool = True, want_codes: bool = True, want_dx: bool = False, rank1: bool = True,
+                   disable_initial=True, soft_transition=True,
                    **sample_kw) -> Dict[str, torch.Tensor]:
     """Backward of the density/colour MLPs and the hash ensemble (nsb_field_backward).
     saved: feat, xs, sigma, rgb from field_forward(want=(..., "feat", "xs")).  Returns fp32 gradients:
@@ -262,6 +262,25 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
         a.d_xs = _ptr(out["d_xs"])
     if n == 0:
         return out
+    # rank-1 scatter (32x fewer atomics): needs table-indexed codes and <= 32 distinct timesteps in the batch
+    if rank1 and (want_tables or want_codes) and sample_kw.get("sample_blend_codes") is None:
+        T = P.n_timesteps
+        slot = None
+        if T <= 32:
+            slot, n_slots = torch.arange(T, dtype=torch.int32, device=dev), T
+        else:
+            tt = sample_kw.get("ray_times") if sample_kw.get("origins") is not None else sample_kw.get("sample_times")
+            if tt is not None:
+                ts_idx = (tt.reshape(-1).float() * (T - 1)).round().clamp_(0, T - 1).long()
+                uniq = torch.unique(ts_idx)                       # host sync: the slot count is data dependent
+                if uniq.numel() <= 32:
+                    slot = torch.full((T,), -1, dtype=torch.int32, device=dev)
+                    slot[uniq] = torch.arange(uniq.numel(), dtype=torch.int32, device=dev)
+                    n_slots = int(uniq.numel())
+        if slot is not None:
+            g1 = torch.zeros((n_slots, P.levels["total_entries"], 2), dtype=_F32, device=dev)
+            a.g_rank1, a.ts_slot, a.n_slots = _ptr(g1), _ptr(slot), n_slots
+            keep += [g1, slot]
     opts = make_opts(window_hash, None, False, True, disable_initial, soft_transition)
     cp = P.c_params()
     _lib.check(lib.nsb_field_backward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(a), _stream()), "nsb_field_backward")

@@ -56,8 +56,10 @@ def test_composite_backward_vs_autograd():
     assert _relerr(d_sigma.cpu(), sigma.grad) < 2e-4
 
 
-def test_field_backward_vs_autograd():
-    """Gradients of the hash tables, time codes and both tiny MLPs (no deformation field)."""
+@pytest.mark.parametrize("rank1", [True, False])
+def test_field_backward_vs_autograd(rank1):
+    """Gradients of the hash tables, time codes and both tiny MLPs (no deformation field); rank1 = the
+    per-timestep 2-vector scatter + dense expansion, else the direct 64-float-per-line scatter."""
     from nersemble_b200 import ops
     P = pl.random_params(**TRAINED)
     NP = native_from_oracle(P, DEV)
@@ -80,7 +82,7 @@ def test_field_backward_vs_autograd():
     kw = dict(positions=pos.detach().to(DEV), sample_times=times.to(DEV), sample_directions=dirs.to(DEV))
     saved = ops.field_forward(NP, window_hash=w_hash, use_deformation=False, want=("sigma", "rgb", "feat", "xs"), **kw)
     torch.testing.assert_close(saved["sigma"].cpu(), sigma[:, 0].detach(), rtol=5e-3, atol=1e-5)
-    grads = ops.field_backward(NP, saved, g_sigma.to(DEV), g_rgb.to(DEV), window_hash=w_hash, loss_scale=128.0, want_dx=True, **kw)
+    grads = ops.field_backward(NP, saved, g_sigma.to(DEV), g_rgb.to(DEV), window_hash=w_hash, loss_scale=128.0, want_dx=True, rank1=rank1, **kw)
     # dL/d(world position) = dL/d(normalised) / aabb size   (tcnn kernel_grid_backward_input)
     dpos = grads["d_xs"].cpu() / (hi - lo)
     assert _relerr(dpos, pos.grad) < 3e-2
