@@ -295,7 +295,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "M ray-samples/s", "h2d_bytes_per_step": RAYS * 7 * 4 * world,
                     "d2h_bytes_per_step": RAYS * 3 * 4 * world},
             "gpu_launches": 5 * K,
-            "roofline": {"bound": "hbm", "kernel": "nsb::field_kernel<true,true,true>", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "nsb::field_kernel_ws<deform,field,head>", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "kernel_ms": field_ms},
             "clocks": sampler.summary(),

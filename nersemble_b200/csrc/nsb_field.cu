@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#define NSB_NO_SPIN_GUARD 1   // see nsb_common.cuh mbar_wait
 #include "nsb_common.cuh"
 #include "nsb_gather.cuh"
 #include "nsb_mlp.cuh"
@@ -585,7 +586,7 @@ constexpr int kThreadsWS = (kTensorWarps + kGatherWarps) * 32;
 // enough -- an inc that exceeds the pool hangs the kernel), so
 //   kTensorWarps*32*kTensorRegs + kGatherWarps*32*kGatherRegs <= 64512.
 constexpr int kGatherRegs = 64;
-constexpr int kTensorRegs = kMT == 1 ? 88 : 120;
+constexpr int kTensorRegs = kMT == 1 ? 80 : 120;
 static_assert(kTensorWarps * 32 * kTensorRegs + kGatherWarps * 32 * kGatherRegs <= kThreadsWS * 72, "register pool");
 constexpr int kLaunchBoundWS = kThreadsWS;
 // Slab layout of deform_packed_tb: layers 0 and 4 without their 128 warp-code columns (those enter as the
@@ -621,6 +622,7 @@ struct alignas(128) SmemWS {
     alignas(16) float xs[2][NSB_TILE][4];  // normalised warped position (0 outside the box), w = timestep bits
     alignas(16) __half feat[2][NSB_TILE * kFeatStride];
     TensorScratch ts[kTensorWarps];
+    uint2 blend_b[kGatherWarps][4 * 32];   // per gather warp: the current timestep's B fragments (lane-private columns)
 };
 
 struct RingRefill {
@@ -673,11 +675,14 @@ __device__ __forceinline__ void ring_gemm2(float (&acc)[kMT][8][4], const int j0
     }
 }
 
-// bias + ReLU + pack one N-half straight into the ping-pong activation buffer.  bias[m][0|1] = bias row of
-// the m-tile's rows g / g+8 (a shared layer bias, or the per-timestep code bias of layers 0 and 4).
-template <int HALF>
-__device__ __forceinline__ void relu_store2(const float (&acc)[kMT][8][4], uint4 (*dst)[8][32],
-                                            const float *const (&bias)[kMT][2], int q, int lane) {
+// bias + ReLU + pack one N-half straight into the ping-pong activation buffer.
+//   CODE = false: `sbias` is the layer's shared bias row (smem), one load serves both row halves.
+//   CODE = true : layers 0 / 4 -- `gbias` is the per-timestep code-bias table (global, L1/L2 resident: 24 x 1 KB) and
+//                 off[m][0|1] the float offset of the bias row of the m-tile's rows g / g+8.  Offsets instead of
+//                 pointers: four 64-bit row pointers per m-tile cost 8 registers for the whole MLP.
+template <int HALF, bool CODE>
+__device__ __forceinline__ void relu_store2(const float (&acc)[kMT][8][4], uint4 (*dst)[8][32], const float *sbias,
+                                            const float *gbias, const uint32_t (&off)[kMT][2], int q, int lane) {
 #pragma unroll
     for (int m = 0; m < kMT; ++m) {
 #pragma unroll
@@ -686,8 +691,14 @@ __device__ __forceinline__ void relu_store2(const float (&acc)[kMT][8][4], uint4
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
                 const int nt = 2 * kt + o, col = HALF * 64 + nt * 8 + 2 * q;
-                const float2 b0 = *reinterpret_cast<const float2 *>(bias[m][0] + col);
-                const float2 b1 = *reinterpret_cast<const float2 *>(bias[m][1] + col);
+                float2 b0, b1;
+                if (CODE) {
+                    b0 = __ldg(reinterpret_cast<const float2 *>(gbias + off[m][0] + col));
+                    b1 = __ldg(reinterpret_cast<const float2 *>(gbias + off[m][1] + col));
+                } else {
+                    b0 = *reinterpret_cast<const float2 *>(sbias + col);
+                    b1 = b0;
+                }
                 r[o * 2 + 0] = pack_h2(fmaxf(acc[m][nt][0] + b0.x, 0.f), fmaxf(acc[m][nt][1] + b0.y, 0.f));
                 r[o * 2 + 1] = pack_h2(fmaxf(acc[m][nt][2] + b1.x, 0.f), fmaxf(acc[m][nt][3] + b1.y, 0.f));
             }
@@ -770,14 +781,16 @@ __device__ __forceinline__ void field_mlp_tile(const FieldArgs &A, const uint4 *
     }
 }
 
-template <bool DEFORM, bool FIELD, bool HEAD>
+// SAVE: training instantiation, additionally stores the warped positions and the deformation activations the
+// backward kernels read; compiled out of the inference instantiation (the stores cost ~40 B of spills there).
+template <bool DEFORM, bool FIELD, bool HEAD, bool SAVE>
 __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __grid_constant__ FieldArgs A) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n = A.S.n_samples;
-    const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // NOTE: nothing is computed ahead of the role split on purpose.  Values shared by both roles get registers that
+    // suit the 88-register tensor role, and the 64-register gather role then pays for them with spills inside its
+    // sample loop (measured: 2.59 -> 2.77 ms).  Each role derives its loop bounds itself.
 
     if (FIELD) {
         const uint4 *src = reinterpret_cast<const uint4 *>(A.P.field_packed);
@@ -805,32 +818,52 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
         if (!FIELD) return;
         const int g = lane >> 2, q = lane & 3;
         const uint8_t *tab = reinterpret_cast<const uint8_t *>(A.P.tables) + q * 32;
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            const int64_t tile = blockIdx.x + it * gridDim.x;
-            const int b = (int)(it & 1);
-            const int rows_valid = (int)min((int64_t)NSB_TILE, n - tile * NSB_TILE);
+        // 32-bit loop state: the gather role runs in 64 registers (n_tiles < 2^31 for any n_samples < 2^38)
+        uint32_t bid, nct;
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));     // volatile: not CSE'd with the tensor role's copy
+        asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(nct));
+        const int n_tiles32 = (int)((A.S.n_samples + NSB_TILE - 1) / NSB_TILE);
+        uint2 *bslot = sm.blend_b[warp - kTensorWarps];   // lane-private columns: no synchronisation needed
+        const BlendBSmem Bf{bslot + lane};
+        int cur_ts = -1;
+        for (int tile = (int)bid, it = 0; tile < n_tiles32; tile += (int)nct, ++it) {
+            const int b = it & 1;
+            const int rows_valid = (int)min((int64_t)NSB_TILE, A.S.n_samples - (int64_t)tile * NSB_TILE);
             mbar_wait<20>(&sm.xs_full[b], (uint32_t)(it >> 1) & 1);
             int row = 0, nrow = 0;
             if (lane == 0) { row = atomicAdd(&sm.tile_ctr[b], 1); nrow = atomicAdd(&sm.tile_ctr[b], 1); }
             row = __shfl_sync(0xffffffffu, row, 0);
             nrow = __shfl_sync(0xffffffffu, nrow, 0);
             GatherTile Ga;
+            QuadIdx Q;
+            Q.entry = 0; Q.w = 0.f;
             float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < rows_valid) {
                 xs = *reinterpret_cast<const float4 *>(sm.xs[b][row]);
-                gather_issue<0>(A.P, tab, xs.x, xs.y, xs.z, g & 1, (g >> 1) & 1, g >> 2, Ga);
+                Q = quad_compute<0>(A.P, xs.x, xs.y, xs.z, lane);
+                gather_issue_q<0, 0>(A.P, tab, Q, g, Ga);
             }
             while (row < rows_valid) {
-                const float *code_row = A.S.sample_blend_codes
-                                            ? A.S.sample_blend_codes + (tile * NSB_TILE + row) * NSB_MEMBERS
-                                            : A.P.blend_codes + (size_t)__float_as_int(xs.w) * NSB_MEMBERS;
-                const BlendB Bf = make_blend_b(A.O, code_row, lane);
+                // blend-weight fragments: rebuilt only when the timestep changes (a tile is 128 consecutive samples,
+                // i.e. one or two rays = one or two timesteps; the code row is a global load through an L1 that the
+                // table lines flood, at the head of the sample's dependent chain)
+                if (A.S.sample_blend_codes) {
+                    park_blend_b(make_blend_b(A.O, A.S.sample_blend_codes + ((int64_t)tile * NSB_TILE + row) * NSB_MEMBERS, lane),
+                                 bslot, lane);
+                } else if (__float_as_int(xs.w) != cur_ts) {
+                    cur_ts = __float_as_int(xs.w);
+                    park_blend_b(make_blend_b(A.O, A.P.blend_codes + (size_t)cur_ts * NSB_MEMBERS, lane), bslot, lane);
+                }
                 const bool has_next = nrow < rows_valid;
-                const float4 nx = *reinterpret_cast<const float4 *>(sm.xs[b][has_next ? nrow : row]);
-                const float val = gather_sample_pipelined(A.P, tab, xs.x, xs.y, xs.z, has_next, nx.x, nx.y, nx.z, Bf, Ga, lane);
-                sm.feat[b][row * kFeatStride + lane] = __float2half_rn(val);
-                if (A.out.feat)
-                    reinterpret_cast<__half *>(A.out.feat)[(tile * NSB_TILE + row) * 32 + lane] = __float2half_rn(val);
+                __half *feat_row = &sm.feat[b][row * kFeatStride];
+                float4 nx = xs;
+                gather_sample_quad(A.P, tab, xs.x, xs.y, xs.z,
+                                   has_next ? reinterpret_cast<const float4 *>(sm.xs[b][nrow]) : nullptr, nx, Bf, Ga, Q,
+                                   feat_row, lane);
+                if (A.out.feat) {   // feature output / training: the row goes to global too
+                    __syncwarp();
+                    reinterpret_cast<__half *>(A.out.feat)[((int64_t)tile * NSB_TILE + row) * 32 + lane] = feat_row[lane];
+                }
                 row = nrow;
                 xs = nx;
                 if (has_next) {
@@ -847,6 +880,9 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
 
     // =============================== TENSOR warps ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+    const int64_t n = A.S.n_samples;
+    const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     TensorScratch &ts = sm.ts[warp];
     const int g = lane >> 2, q = lane & 3;
     const float amin0 = A.P.aabb[0], amin1 = A.P.aabb[1], amin2 = A.P.aabb[2];
@@ -922,7 +958,8 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                             float e0 = 0.f, e1 = 0.f;
                             if (i < 21) {
                                 const int d = i / 7, j = i - d * 7;
-                                const float arg = (6.283185307179586f * pn[m][h][d]) * (float)(1 << j);
+                                const float pd = d == 0 ? pn[m][h][0] : (d == 1 ? pn[m][h][1] : pn[m][h][2]);   // no local-memory indexing
+                                const float arg = (6.283185307179586f * pd) * (float)(1 << j);
                                 const float wj = A.O.pe_window[j];
                                 e0 = wj * sinf(arg);
                                 e1 = wj * sinf(arg + 1.5707963267948966f);
@@ -936,17 +973,17 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                         }
                     }
                     ts.enc[m][kt][lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                    if (kMT == 1 && A.out.deform_enc)
+                    if (SAVE && kMT == 1 && A.out.deform_enc)
                         reinterpret_cast<uint4 *>(A.out.deform_enc)[((tile * kTensorWarps + warp) * 3 + kt) * 32 + lane] =
                             make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
-            // per-row bias pointers: layers 0/4 use the per-timestep code bias, the others the layer bias
-            const float *cb[kMT][2];
+            // layers 0/4 read the per-timestep code bias: float offset of the bias row of rows g / g+8
+            uint32_t cb[kMT][2];
 #pragma unroll
             for (int m = 0; m < kMT; ++m)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    cb[m][h] = A.P.deform_code_bias + (size_t)__float_as_int(ts.pos[m * 16 + g + 8 * h][3]) * 256;
+                for (int h = 0; h < 2; ++h) cb[m][h] = (uint32_t)__float_as_int(ts.pos[m * 16 + g + 8 * h][3]) * 256u;
+            const float *const gcb = A.P.deform_code_bias;
             auto in_a = [&](int m, int kt, uint32_t(&a)[4]) {
                 const uint4 v = ts.enc[m][kt][lane];
                 a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
@@ -964,48 +1001,35 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                 if (kt < 8) hid1(m, kt, a); else in_a(m, kt - 8, a);
             };
             auto save_act = [&](int layer, int buf) {   // training: keep the layer output for the backward pass
-                if (kMT == 1 && A.out.deform_acts) {
+                if (SAVE && kMT == 1 && A.out.deform_acts) {
                     uint4 *dst = reinterpret_cast<uint4 *>(A.out.deform_acts) + (((size_t)tile * kTensorWarps + warp) * 6 + layer) * 256;
 #pragma unroll
                     for (int kt = 0; kt < 8; ++kt) dst[kt * 32 + lane] = ts.act[buf][0][kt][lane];
                 }
             };
-            const float *b0[kMT][2], *b4[kMT][2], *bl[kMT][2];
-#pragma unroll
-            for (int m = 0; m < kMT; ++m)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) { b0[m][h] = cb[m][h]; b4[m][h] = cb[m][h] + 128; }
-            auto layer_bias = [&](int l) {
-#pragma unroll
-                for (int m = 0; m < kMT; ++m) { bl[m][0] = sm.bias + l * 128; bl[m][1] = sm.bias + l * 128; }
-            };
             // layer 0: posenc (48) -> act[0]; the 128 warp-code columns are in the bias
-            zero_acc2(acc); ring_gemm2(acc, kT_L0, 3, in_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], b0, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L0 + 3, 3, in_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], b0, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L0, 3, in_a, sm, rf, lane); relu_store2<0, true>(acc, ts.act[0], nullptr, gcb, cb, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L0 + 3, 3, in_a, sm, rf, lane); relu_store2<1, true>(acc, ts.act[0], nullptr, gcb, cb, q, lane);
             save_act(0, 0);
             // layer 1: act[0] -> act[1]
-            layer_bias(1);
-            zero_acc2(acc); ring_gemm2(acc, kT_L1, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L1, 8, hid0, sm, rf, lane); relu_store2<0, false>(acc, ts.act[1], sm.bias + 1 * 128, nullptr, cb, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1, false>(acc, ts.act[1], sm.bias + 1 * 128, nullptr, cb, q, lane);
             save_act(1, 1);
             // layer 2: act[1] -> act[0]
-            layer_bias(2);
-            zero_acc2(acc); ring_gemm2(acc, kT_L2, 8, hid1, sm, rf, lane); relu_store2<0>(acc, ts.act[0], bl, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1>(acc, ts.act[0], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L2, 8, hid1, sm, rf, lane); relu_store2<0, false>(acc, ts.act[0], sm.bias + 2 * 128, nullptr, cb, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1, false>(acc, ts.act[0], sm.bias + 2 * 128, nullptr, cb, q, lane);
             save_act(2, 0);
             // layer 3: act[0] -> act[1]
-            layer_bias(3);
-            zero_acc2(acc); ring_gemm2(acc, kT_L3, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L3, 8, hid0, sm, rf, lane); relu_store2<0, false>(acc, ts.act[1], sm.bias + 3 * 128, nullptr, cb, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1, false>(acc, ts.act[1], sm.bias + 3 * 128, nullptr, cb, q, lane);
             save_act(3, 1);
             // layer 4 (skip): [act[1] | posenc] -> act[0]
-            zero_acc2(acc); ring_gemm2(acc, kT_L4, 11, skip_a, sm, rf, lane); relu_store2<0>(acc, ts.act[0], b4, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L4 + 11, 11, skip_a, sm, rf, lane); relu_store2<1>(acc, ts.act[0], b4, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L4, 11, skip_a, sm, rf, lane); relu_store2<0, true>(acc, ts.act[0], nullptr, gcb + 128, cb, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L4 + 11, 11, skip_a, sm, rf, lane); relu_store2<1, true>(acc, ts.act[0], nullptr, gcb + 128, cb, q, lane);
             save_act(4, 0);
             // layer 5: act[0] -> act[1]
-            layer_bias(5);
-            zero_acc2(acc); ring_gemm2(acc, kT_L5, 8, hid0, sm, rf, lane); relu_store2<0>(acc, ts.act[1], bl, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1>(acc, ts.act[1], bl, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L5, 8, hid0, sm, rf, lane); relu_store2<0, false>(acc, ts.act[1], sm.bias + 5 * 128, nullptr, cb, q, lane);
+            zero_acc2(acc); ring_gemm2(acc, kT_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1, false>(acc, ts.act[1], sm.bias + 5 * 128, nullptr, cb, q, lane);
             save_act(5, 1);
             // heads (last chunk: slabs 92,93)
             float hacc[kMT][2][4];
@@ -1050,10 +1074,14 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                     vr[2 * k + 1] = rsel ? b1 : a1;
                 }
                 const int r = m * 16 + g + 8 * rsel;
-                const float p[3] = {rsel ? pn[m][1][0] : pn[m][0][0], rsel ? pn[m][1][1] : pn[m][0][1], rsel ? pn[m][1][2] : pn[m][0][2]};
+                // recomputed (same ops => same bits as pn above): keeping pn live across the MLP costs 6 registers
+                const float p[3] = {__fdiv_rn(__fsub_rn(ts.pos[r][0], amin0), A.aabb_size[0]),
+                                    __fdiv_rn(__fsub_rn(ts.pos[r][1], amin1), A.aabb_size[1]),
+                                    __fdiv_rn(__fsub_rn(ts.pos[r][2], amin2), A.aabb_size[2])};
                 const float v[3] = {vr[0], vr[1], vr[2]}, rr[3] = {vr[3], vr[4], vr[5]};
                 float pw[3];
                 se3_apply(p, rr, v, pw);
+                __syncwarp();   // lanes q = 2, 3 read the rows lanes q = 0, 1 update below
                 if (q < 2) {
                     const float o0 = pw[0] - p[0], o1 = pw[1] - p[1], o2 = pw[2] - p[2];
                     const int64_t s = row0 + r;
@@ -1074,7 +1102,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             const bool sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
             float4 o4 = make_float4(sel ? x : 0.f, sel ? y : 0.f, sel ? z : 0.f, ts.pos[lane][3]);
             *reinterpret_cast<float4 *>(sm.xs[b][warp * kTRows + lane]) = o4;
-            if (A.out.xs && row0 + lane < n)
+            if (SAVE && A.out.xs && row0 + lane < n)
                 *reinterpret_cast<float4 *>(A.out.xs + 4 * (row0 + lane)) = make_float4(o4.x, o4.y, o4.z, sel ? 1.f : 0.f);
             ts.dirsel[b][lane][3] = sel ? 1.f : 0.f;
             if (warp == 0 && lane == 0) sm.tile_ctr[b] = 0;
@@ -1085,10 +1113,11 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
         }
     };
 
-    if (my_tiles > 0) deform_stage(0);
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    // it = -1 is the pipeline prologue: ONE inlined copy of deform_stage (two copies doubled the kernel's code size)
+#pragma unroll 1
+    for (int64_t it = -1; it < my_tiles; ++it) {
         if (it + 1 < my_tiles) deform_stage(it + 1);
-        if (FIELD) {
+        if (FIELD && it >= 0) {
             const int64_t tile = blockIdx.x + it * gridDim.x;
             const int b = (int)(it & 1);
             mbar_wait<100>(&sm.feat_full[b], (uint32_t)(it >> 1) & 1);
@@ -1163,12 +1192,12 @@ static int kernel_version() {
     return v;
 }
 
-template <bool D, bool F, bool H>
-static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
+template <bool D, bool F, bool H, bool SV>
+static int launch_field_ws_(const FieldArgs &A, cudaStream_t st) {
     const size_t smem = sizeof(SmemWS);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(field_kernel_ws<D, F, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(field_kernel_ws<D, F, H, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(field_kernel_ws): %s", cudaGetErrorString(e));
             return 1;
@@ -1177,8 +1206,13 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
     }
     const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms());
-    field_kernel_ws<D, F, H><<<grid, kThreadsWS, smem, st>>>(A);
+    field_kernel_ws<D, F, H, SV><<<grid, kThreadsWS, smem, st>>>(A);
     return check_launch("field_kernel_ws");
+}
+template <bool D, bool F, bool H>
+static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
+    const bool save = A.out.xs || A.out.deform_acts || A.out.deform_enc;
+    return save ? launch_field_ws_<D, F, H, true>(A, st) : launch_field_ws_<D, F, H, false>(A, st);
 }
 
 template <bool D, bool F, bool H>

@@ -2,6 +2,10 @@
 #pragma once
 #include "nsb_common.cuh"
 
+#ifndef NSB_STREAM_HASHED
+#define NSB_STREAM_HASHED 0   // measured r1e: 2.78 vs 2.27 ms with L1::no_allocate on the hashed levels (they DO hit in L1: 4 lanes share a sector pair, neighbouring samples share corners)
+#endif
+
 namespace nsb {
 
 // -------------------------------------------------------------------------------------------
@@ -138,6 +142,14 @@ __device__ __forceinline__ void ldg256(const void *p, uint32_t (&r)[8]) {
                  : "l"(p));
 }
 
+// same, streaming: the line is not allocated in L1.  Hashed (fine) levels have no reuse between samples, and keeping
+// them out of L1 leaves it to the dense levels' lines, the code rows and the stack.
+__device__ __forceinline__ void ldg256_stream(const void *p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
 template <int T>
 __device__ __forceinline__ void gather_issue(const nsb_field_params &P, const uint8_t *tab, float x, float y, float z,
                                              uint32_t dx, uint32_t dy, uint32_t dz, GatherTile &G) {
@@ -212,6 +224,120 @@ __device__ __forceinline__ float gather_blend_mma(const nsb_field_params &P, flo
     GatherTile Ga;
     gather_issue<0>(P, tab, x, y, z, g & 1, (g >> 1) & 1, g >> 2, Ga);
     return gather_sample_pipelined(P, tab, x, y, z, false, 0.f, 0.f, 0.f, B, Ga, lane);
+}
+
+// -------------------------------------------------------------------------------------------
+// Quad-cooperative index computation (warp-specialised kernel).
+// In gather_issue every lane of a quad (q = 0..3, the four 32 B pieces of one 128 B line) repeats the same
+// position -> corner -> hash/stride -> trilinear-weight arithmetic for its corner g: 4x redundant, ~80 instructions per
+// level and lane, and the gather warps are issue-limited (ncu r1: 64 % issue-active, 1 instruction per 11 cycles and
+// warp).  Here the 32 lanes compute 32 DISTINCT (level, corner) pairs -- lane L: level 4U + (L >> 3), corner L & 7 --
+// once per four levels, and each tile's issue fetches the two (entry, weight) pairs it needs with shuffles.
+// Same per-pair arithmetic in the same order as gather_issue: bit-identical results.
+// -------------------------------------------------------------------------------------------
+struct QuadIdx {
+    uint32_t entry;   // offset[level] + index: absolute table line of (level 4U + (lane >> 3), corner lane & 7)
+    float w;          // its trilinear weight
+};
+
+template <int U>
+__device__ __forceinline__ QuadIdx quad_compute(const nsb_field_params &P, float x, float y, float z, int lane) {
+    const int l = 4 * U + (lane >> 3);   // dynamic index into the __grid_constant__ level table: LDC, no local copy
+    const uint32_t dx = lane & 1, dy = (lane >> 1) & 1, dz = (lane >> 2) & 1;
+    const float scale = P.levels.scale[l];
+    const uint32_t res = P.levels.res[l], ent = P.levels.entries[l], off = P.levels.offset[l];
+    const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+    const float fx = px - flx, fy = py - fly, fz = pz - flz;
+    const uint32_t cx = (uint32_t)(int)flx + dx, cy = (uint32_t)(int)fly + dy, cz = (uint32_t)(int)flz + dz;
+    QuadIdx Q;
+    Q.w = ((dx ? fx : 1.0f - fx) * (dy ? fy : 1.0f - fy)) * (dz ? fz : 1.0f - fz);
+    const uint32_t ih = (cx ^ (cy * kPrimeY) ^ (cz * kPrimeZ)) & (ent - 1);   // hashed levels: entries = 2^log2T
+    uint32_t id = cx + cy * res + cz * res * res;                              // < 2*entries: `% entries` is one subtract
+    id = id >= ent ? id - ent : id;
+    Q.entry = off + (P.levels.hashed[l] ? ih : id);
+    return Q;
+}
+
+// loads of tile J (0/1) of the quad: line 0 <- level 4U+2J, line 1 <- level 4U+2J+1, corner g
+template <int U, int J>
+__device__ __forceinline__ void gather_issue_q(const nsb_field_params &P, const uint8_t *tab, const QuadIdx &Q, int g,
+                                               GatherTile &G) {
+    const uint32_t e0 = __shfl_sync(0xffffffffu, Q.entry, (2 * J) * 8 + g);
+    const uint32_t e1 = __shfl_sync(0xffffffffu, Q.entry, (2 * J + 1) * 8 + g);
+    G.w[0] = __shfl_sync(0xffffffffu, Q.w, (2 * J) * 8 + g);
+    G.w[1] = __shfl_sync(0xffffffffu, Q.w, (2 * J + 1) * 8 + g);
+#if NSB_STREAM_HASHED
+    if (P.levels.hashed[4 * U + 2 * J]) ldg256_stream(tab + (size_t)e0 * 128, G.v[0]);   // uniform (constant bank)
+    else ldg256(tab + (size_t)e0 * 128, G.v[0]);
+    if (P.levels.hashed[4 * U + 2 * J + 1]) ldg256_stream(tab + (size_t)e1 * 128, G.v[1]);
+    else ldg256(tab + (size_t)e1 * 128, G.v[1]);
+#else
+    ldg256(tab + (size_t)e0 * 128, G.v[0]);
+    ldg256(tab + (size_t)e1 * 128, G.v[1]);
+#endif
+}
+
+// Software-pipelined gather of one sample, quad-cooperative.  On entry Ga holds the loads of this sample's tile 0
+// and Q its quad 0; on return they hold the NEXT sample's (when next_xs != nullptr; next_out = that sample's smem row).
+// The 8 lanes (q == 0) that own a level quad's features store them to the shared-memory feature row as soon as the
+// quad is reduced (no yv[4] carried to a final 4-shuffle delivery), and the next sample's position is read from
+// shared memory when its first loads are issued (not held across the body): the gather role runs in 64 registers,
+// and a spill inside this loop is very expensive (L1 is flooded by the streaming table lines: 48 spill instructions
+// per sample took the kernel from 2.6 to 4.0 ms).
+// (Tried and dropped, r1e: feeding the HMMA A fragment straight from the LDG.256 registers -- m16 row halves = even /
+// odd members of ONE line, B in 4 registers, no IMAD.MOV -- 790 instead of 980 instructions per sample but 2.56 vs
+// 2.20 ms: the extra shuffle per level sits on the per-warp dependent chain, and the loop is latency-, not issue-bound.)
+// B fragments parked in a lane-private shared-memory column ([k-step][lane] uint2 = {b0, b1}) and fetched one k-step
+// at a time: rebuilt only when the timestep changes, and 8 registers that are not live across the sample loop.
+struct BlendBSmem {
+    const uint2 *col;   // this lane's column: col[s * 32]
+};
+__device__ __forceinline__ void park_blend_b(const BlendB &B, uint2 *warp_slot, int lane) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) warp_slot[s * 32 + lane] = make_uint2(B.lo[s], B.hi[s]);
+}
+__device__ __forceinline__ float gather_consume(const GatherTile &G, const BlendBSmem &B, int lane) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint2 b = B.col[s * 32];
+        const uint32_t a[4] = {G.v[0][s], G.v[1][s], G.v[0][4 + s], G.v[1][4 + s]};
+        mma16816(c, a, b.x, b.y);
+    }
+    const float u0 = butterfly(c[0] * G.w[0], c[1] * G.w[0], 2, lane);
+    const float u1 = butterfly(c[2] * G.w[1], c[3] * G.w[1], 2, lane);
+    return butterfly(u0, u1, 3, lane);
+}
+
+template <class BT>
+__device__ __forceinline__ void gather_sample_quad(const nsb_field_params &P, const uint8_t *tab, float x, float y,
+                                                   float z, const float4 *next_xs, float4 &next_out, const BT &B,
+                                                   GatherTile &Ga, QuadIdx &Q, __half *feat_row, int lane) {
+    const int g = lane >> 2;
+    const bool owner = (lane & 3) == 0;
+    GatherTile Gb;
+    float e, o, yv;
+    gather_issue_q<0, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    Q = quad_compute<1>(P, x, y, z, lane);
+    gather_issue_q<1, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[g] = __float2half_rn(yv);
+    gather_issue_q<1, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    Q = quad_compute<2>(P, x, y, z, lane);
+    gather_issue_q<2, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[8 + g] = __float2half_rn(yv);
+    gather_issue_q<2, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    Q = quad_compute<3>(P, x, y, z, lane);
+    gather_issue_q<3, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[16 + g] = __float2half_rn(yv);
+    gather_issue_q<3, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    if (next_xs) {
+        next_out = *next_xs;
+        Q = quad_compute<0>(P, next_out.x, next_out.y, next_out.z, lane);
+        gather_issue_q<0, 0>(P, tab, Q, g, Ga);
+    }
+    o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[24 + g] = __float2half_rn(yv);
 }
 
 }  // namespace nsb
