@@ -113,6 +113,9 @@ typedef struct nsb_field_out {
                         layers in MMA A-fragment order (16 rows per warp), saved by the training forward for
                         nsb_deform_backward (the reference keeps the same activations for autograd). */
     void *deform_enc;  /* NULL or uint4 [n_tiles][8 warps][3 k-tiles][32 lanes]: windowed posenc fragments */
+    void *corner_vals; /* NULL or __half2 [n_samples][16 levels][8 corners]: member-blended (f0, f1) of every gathered
+                          corner before the trilinear weight; saved by the training forward so that nsb_field_backward
+                          computes the position gradient without gathering the table lines again */
 } nsb_field_out;
 
 int nsb_version(void);
@@ -191,6 +194,10 @@ typedef struct nsb_field_bwd_args {
     float *g_rank1;               /* workspace [n_slots][total_entries][2], zeroed by the caller; NULL: direct scatter */
     const int32_t *ts_slot;       /* [n_timesteps] -> slot in [0, n_slots) or -1 (timestep absent from this batch) */
     int32_t n_slots;
+    const void *corner_vals;      /* NULL or nsb_field_out.corner_vals of the forward (rank-1 path: skips the re-gather) */
+    float *cw_slots_out;          /* NULL or [n_slots][32] out: the effective (fp16-rounded) blend weights of each slot's
+                                     timestep, exactly as the expansion uses them -- input of nsb_table_adam_step /
+                                     nsb_rank1_expand when the caller defers the table gradient (d_tables == NULL) */
 } nsb_field_bwd_args;
 int nsb_field_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                        const nsb_field_bwd_args *args, void *stream);
@@ -214,6 +221,35 @@ typedef struct nsb_deform_bwd_args {
 size_t nsb_deform_packed_t_bytes(void);
 int nsb_deform_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                         const nsb_deform_bwd_args *args, void *stream);
+
+/* Fused hash-table optimiser step.  Replaces, for the table parameter only, what the reference's training loop does
+ * with torch: materialise the dense fp32 gradient of the 8 tcnn grids, run torch.optim.Adam over it (nerfstudio
+ * AdamOptimizerConfig, eps 1e-15: train_nersemble.py optimizers["fields"]) and let tcnn re-read the parameters.  One
+ * pass over the table: gradient line = sum_slots cw_slot[member] x G[slot][line][feat] (rank-1 expansion of the
+ * scatter workspace nsb_field_backward filled) and/or a dense fp32 gradient, times grad_scale; torch.optim.Adam's
+ * update (lerp form of exp_avg, bias corrections passed in, no amsgrad); the fp16 copy the forward kernels gather is
+ * rewritten in the same pass.  Every line is updated (Adam's moments decay where the gradient is zero, like torch). */
+typedef struct nsb_table_adam_args {
+    int64_t total_entries;
+    float *tables;            /* fp32 master [E][32][2], in place */
+    float *exp_avg;           /* [E][32][2], in place */
+    float *exp_avg_sq;        /* [E][32][2], in place */
+    void *tables_half;        /* __half [E][32][2] out, or NULL */
+    const float *grad;        /* dense fp32 gradient [E][32][2] or NULL */
+    const float *g_rank1;     /* [n_slots][E][2] or NULL */
+    const float *cw_slots;    /* [n_slots][32] (nsb_field_bwd_args.cw_slots_out) */
+    int32_t n_slots;          /* <= 32 */
+    float grad_scale;         /* e.g. 1 / world_size */
+    float lr, beta1, beta2, eps, weight_decay;
+    float bias_correction1;   /* 1 - beta1^step */
+    float bias_correction2;   /* 1 - beta2^step */
+} nsb_table_adam_args;
+int nsb_table_adam_step(const nsb_table_adam_args *args, void *stream);
+
+/* d_tables[line][m][f] += grad_scale * sum_slots cw_slot[m] * G[slot][line][f]: the deferred expansion alone (used when
+ * a deferred gradient has to become a dense .grad after all: gradient accumulation, dense all-reduce). */
+int nsb_rank1_expand(const float *g_rank1, const float *cw_slots, int32_t n_slots, int64_t total_entries,
+                     float grad_scale, float *d_tables, void *stream);
 
 /* Fixed-stride marcher (BASELINE configs 1/2): n_per_ray intervals of `step` from max(t_enter, near). */
 int nsb_march_fixed(const float *origins, const float *directions, int64_t n_rays, const float *aabb6,

@@ -46,7 +46,7 @@ class Samples(C.Structure):
 
 class FieldOut(C.Structure):
     _fields_ = [("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p), ("feat", C.c_void_p),
-                ("xs", C.c_void_p), ("deform_acts", C.c_void_p), ("deform_enc", C.c_void_p)]
+                ("xs", C.c_void_p), ("deform_acts", C.c_void_p), ("deform_enc", C.c_void_p), ("corner_vals", C.c_void_p)]
 
 
 class FieldBwdArgs(C.Structure):
@@ -54,7 +54,15 @@ class FieldBwdArgs(C.Structure):
                 ("rgb", C.c_void_p), ("d_sigma", C.c_void_p), ("d_rgb", C.c_void_p), ("loss_scale", C.c_float),
                 ("d_feat", C.c_void_p), ("d_base_w", C.c_void_p), ("d_head_w", C.c_void_p), ("d_tables", C.c_void_p),
                 ("d_blend_codes", C.c_void_p), ("d_xs", C.c_void_p), ("g_rank1", C.c_void_p), ("ts_slot", C.c_void_p),
-                ("n_slots", C.c_int32)]
+                ("n_slots", C.c_int32), ("corner_vals", C.c_void_p), ("cw_slots_out", C.c_void_p)]
+
+
+class TableAdamArgs(C.Structure):
+    _fields_ = [("total_entries", C.c_int64), ("tables", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("tables_half", C.c_void_p), ("grad", C.c_void_p), ("g_rank1", C.c_void_p), ("cw_slots", C.c_void_p),
+                ("n_slots", C.c_int32), ("grad_scale", C.c_float), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float), ("bias_correction1", C.c_float),
+                ("bias_correction2", C.c_float)]
 
 
 class CompositeArgs(C.Structure):
@@ -101,6 +109,8 @@ SYMBOLS = {
     "nsb_deform_packed_t_bytes": (C.c_size_t, []),
     "nsb_deform_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
                                       C.POINTER(DeformBwdArgs), C.c_void_p]),
+    "nsb_table_adam_step": (C.c_int, [C.POINTER(TableAdamArgs), C.c_void_p]),
+    "nsb_rank1_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "nsb_hash_blend_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "nsb_composite_forward": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),

@@ -382,16 +382,106 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ F
 }
 
 // ---------------------------------------------------------------------------------------------
+// Rank-1 scatter with the corner values the training forward saved (nsb_field_out.corner_vals): no table reads.
+// One warp per sample, FOUR rounds: in round U lane L owns (level 4U + (L >> 3), corner L & 7) -- 32 distinct pairs per
+// round, every index / weight computed once (the kernel above repeats them in the 4 lanes of a quad).  Per pair:
+//   table gradient   G[slot][line] += w * dfeat[level]          (red.v2)
+//   position gradient dL/dx_d += +-scale * (dfeat . blended corner value) * (product of the other two weight factors)
+// A warp walks a contiguous run of samples (consecutive samples of a ray), so at the coarse levels a lane meets the
+// same line again and again: it keeps the running 2-vector in registers and issues the atomic only when the line
+// (or the slot) changes -- levels 0..5 need 9x..1.5x fewer atomics (cell size / sample spacing).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hash_bwd_cv_kernel(const __grid_constant__ FieldBwdKArgs K) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t dx = lane & 1, dy = (lane >> 1) & 1, dz = (lane >> 2) & 1;
+    const int lsub = lane >> 3;
+    const int64_t n = K.S.n_samples;
+    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t per = (n + n_warps - 1) / n_warps;
+    const int64_t s_begin = warp_global * per, s_end = min(n, s_begin + per);
+    const size_t total = (size_t)K.P.levels.offset[NSB_MAX_LEVELS - 1] + K.P.levels.entries[NSB_MAX_LEVELS - 1];
+    const __half2 *cv = reinterpret_cast<const __half2 *>(K.B.corner_vals);
+    float scale[4];
+    uint32_t res[4], ent[4], off[4], hashed[4];
+#pragma unroll
+    for (int U = 0; U < 4; ++U) {
+        const int l = 4 * U + lsub;
+        scale[U] = K.P.levels.scale[l]; res[U] = K.P.levels.res[l]; ent[U] = K.P.levels.entries[l];
+        off[U] = K.P.levels.offset[l]; hashed[U] = K.P.levels.hashed[l];
+    }
+    float *run_ptr[4] = {nullptr, nullptr, nullptr, nullptr};   // pending (slot, line) of each round and its running sum
+    float run0[4] = {0.f, 0.f, 0.f, 0.f}, run1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t s = s_begin; s < s_end; ++s) {
+        const float4 xs = __ldg(reinterpret_cast<const float4 *>(K.B.xs) + s);
+        float tt = 0.f;
+        if (K.S.origins != nullptr) { if (K.S.ray_times) tt = K.S.ray_times[K.S.ray_indices[s]]; }
+        else if (K.S.sample_times) tt = K.S.sample_times[s];
+        int ts = __float2int_rn(__fmul_rn(tt, (float)(K.P.n_timesteps - 1)));
+        ts = min(max(ts, 0), K.P.n_timesteps - 1);
+        float *gslot = K.B.g_rank1 + (size_t)K.B.ts_slot[ts] * total * 2;
+        float ex = 0.f, ey = 0.f, ez = 0.f;
+#pragma unroll
+        for (int U = 0; U < 4; ++U) {
+            const float2 df = __ldg(reinterpret_cast<const float2 *>(K.B.d_feat + s * 32) + 4 * U + lsub);
+            const float px = fmaf(scale[U], xs.x, 0.5f), py = fmaf(scale[U], xs.y, 0.5f), pz = fmaf(scale[U], xs.z, 0.5f);
+            const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+            const float fx = px - flx, fy = py - fly, fz = pz - flz;
+            const uint32_t cx = (uint32_t)(int)flx + dx, cy = (uint32_t)(int)fly + dy, cz = (uint32_t)(int)flz + dz;
+            const float wx = dx ? fx : 1.0f - fx, wy = dy ? fy : 1.0f - fy, wz = dz ? fz : 1.0f - fz;
+            const float w = (wx * wy) * wz;
+            const uint32_t ih = (cx ^ (cy * kPrimeY) ^ (cz * kPrimeZ)) & (ent[U] - 1);
+            uint32_t id = cx + cy * res[U] + cz * res[U] * res[U];
+            id = id >= ent[U] ? id - ent[U] : id;
+            float *dst = gslot + (size_t)(off[U] + (hashed[U] ? ih : id)) * 2;
+            const float g0 = w * df.x, g1 = w * df.y;
+            if (dst == run_ptr[U]) {
+                run0[U] += g0; run1[U] += g1;
+            } else {
+                if (run_ptr[U] && (run0[U] != 0.f || run1[U] != 0.f)) red_add_v2(run_ptr[U], run0[U], run1[U]);
+                run_ptr[U] = dst; run0[U] = g0; run1[U] = g1;
+            }
+            if (K.B.d_xs) {
+                const float2 pb = __half22float2(cv[s * 128 + (4 * U + lsub) * 8 + (lane & 7)]);
+                const float t = scale[U] * (df.x * pb.x + df.y * pb.y);   // frac = scale*x + 0.5 - floor
+                ex = fmaf(dx ? t : -t, wy * wz, ex);
+                ey = fmaf(dy ? t : -t, wx * wz, ey);
+                ez = fmaf(dz ? t : -t, wx * wy, ez);
+            }
+        }
+        if (K.B.d_xs) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                ey += __shfl_xor_sync(0xffffffffu, ey, o);
+                ez += __shfl_xor_sync(0xffffffffu, ez, o);
+            }
+            if (lane == 0) {   // positions outside the box were zeroed (x * selector): no gradient
+                K.B.d_xs[3 * s + 0] = ex * xs.w; K.B.d_xs[3 * s + 1] = ey * xs.w; K.B.d_xs[3 * s + 2] = ez * xs.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int U = 0; U < 4; ++U)
+        if (run_ptr[U] && (run0[U] != 0.f || run1[U] != 0.f)) red_add_v2(run_ptr[U], run0[U], run1[U]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // rank-1 expansion: d_tables[line][m][f] += sum_slots cw_slot[m] * G[slot][line][f];
 //                   d_codes[t][m]       += scale[m] * sum_lines sum_f V[line][m][f] * G[slot(t)][line][f]
 // one warp per table line (lane = member), grid-stride; G lines that were never touched are skipped.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 32;
+constexpr int kExpWarps = 4, kExpLines = 32;
 
-__global__ void __launch_bounds__(256) hash_expand_kernel(const __grid_constant__ FieldBwdKArgs K, size_t total_entries) {
+// Block form (same as table_step_kernel, nsb_optim.cu): a warp owns 32 consecutive lines per iteration, reads every
+// slot's 2-vectors of those lines with one coalesced 256 B load per slot into a shared-memory panel, and then visits
+// only the lines some slot touched (lane = member; the fp16 table line is one coalesced 128 B read, four lines in flight).
+__global__ void __launch_bounds__(kExpWarps * 32) hash_expand_kernel(const __grid_constant__ FieldBwdKArgs K, size_t total_entries) {
     __shared__ float cw_s[kMaxSlots][NSB_MEMBERS];
     __shared__ int slot_ts[kMaxSlots];
-    const int lane = threadIdx.x & 31, n_slots = K.B.n_slots;
+    __shared__ float2 gs[kExpWarps][kMaxSlots][kExpLines];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_slots = K.B.n_slots;
     for (int i = threadIdx.x; i < kMaxSlots; i += blockDim.x) slot_ts[i] = -1;
     __syncthreads();
     for (int t = threadIdx.x; t < K.P.n_timesteps; t += blockDim.x) {
@@ -404,37 +494,70 @@ __global__ void __launch_bounds__(256) hash_expand_kernel(const __grid_constant_
         float c = 0.f;
         if (t >= 0) c = __half2float(__float2half_rn(fmaf(K.P.blend_codes[(size_t)t * NSB_MEMBERS + m], K.O.cw_scale[m], K.O.cw_bias[m])));
         cw_s[sl][m] = c;
+        if (K.B.cw_slots_out && blockIdx.x == 0) K.B.cw_slots_out[i] = c;
     }
     __syncthreads();
-    float dcode[kMaxSlots];
+    if (!K.B.d_tables && !K.B.d_blend_codes) return;    // launched only to publish cw_slots_out
+    float cw[kMaxSlots], dcode[kMaxSlots];
 #pragma unroll
-    for (int sl = 0; sl < kMaxSlots; ++sl) dcode[sl] = 0.f;
-    const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (int sl = 0; sl < kMaxSlots; ++sl) { dcode[sl] = 0.f; cw[sl] = sl < n_slots ? cw_s[sl][lane] : 0.f; }
     const __half2 *tab = reinterpret_cast<const __half2 *>(K.P.tables);
-    for (size_t e = warp_global; e < total_entries; e += n_warps) {
-        // lane sl reads the 2-vector of slot sl
-        float2 gv = make_float2(0.f, 0.f);
-        if (lane < n_slots) gv = *reinterpret_cast<const float2 *>(K.B.g_rank1 + ((size_t)lane * total_entries + e) * 2);
-        const unsigned touched = __ballot_sync(0xffffffffu, gv.x != 0.f || gv.y != 0.f);
-        if (touched == 0) continue;
-        const float2 v = K.B.d_blend_codes ? __half22float2(tab[e * NSB_MEMBERS + lane]) : make_float2(0.f, 0.f);
-        float a0 = 0.f, a1 = 0.f;
+    const int64_t E = (int64_t)total_entries;
+    const int64_t n_blocks = (E + kExpLines - 1) / kExpLines;
+    for (int64_t blk = (int64_t)blockIdx.x * kExpWarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kExpWarps) {
+        const int64_t e0 = blk * kExpLines;
+        unsigned any_slot = 0;
+        bool mine = false;      // line e0 + lane touched in some slot
+        for (int s0 = 0; s0 < n_slots; s0 += 8) {      // 8 slot rows in flight (a ballot per load serialises them)
+            float2 v[8];
 #pragma unroll
-        for (int sl = 0; sl < kMaxSlots; ++sl) {
-            if (!((touched >> sl) & 1)) continue;     // warp-uniform
-            const float gx = __shfl_sync(0xffffffffu, gv.x, sl), gy = __shfl_sync(0xffffffffu, gv.y, sl);
-            const float c = cw_s[sl][lane];
-            a0 = fmaf(c, gx, a0);
-            a1 = fmaf(c, gy, a1);
-            dcode[sl] = fmaf(v.x, gx, fmaf(v.y, gy, dcode[sl]));
+            for (int u = 0; u < 8; ++u) {
+                v[u] = make_float2(0.f, 0.f);
+                if (s0 + u < n_slots && e0 + lane < E)
+                    v[u] = __ldg(reinterpret_cast<const float2 *>(K.B.g_rank1 + ((size_t)(s0 + u) * E + e0 + lane) * 2));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (s0 + u >= n_slots) break;
+                gs[warp][s0 + u][lane] = v[u];
+                const bool nz = v[u].x != 0.f || v[u].y != 0.f;
+                mine |= nz;
+                if (__ballot_sync(0xffffffffu, nz)) any_slot |= 1u << (s0 + u);
+            }
         }
-        if (K.B.d_tables) {
-            float2 *dst = reinterpret_cast<float2 *>(K.B.d_tables + (e * NSB_MEMBERS + lane) * 2);
-            float2 cur = *dst;
-            cur.x += a0; cur.y += a1;
-            *dst = cur;
+        __syncwarp();
+        unsigned todo = __ballot_sync(0xffffffffu, mine);
+        while (todo) {
+            int js[4];
+            float2 vs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {       // up to four touched lines in flight
+                js[u] = todo ? __ffs(todo) - 1 : -1;
+                if (todo) todo &= todo - 1;
+                vs[u] = make_float2(0.f, 0.f);
+                if (js[u] >= 0 && K.B.d_blend_codes) vs[u] = __half22float2(tab[(size_t)(e0 + js[u]) * NSB_MEMBERS + lane]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (js[u] < 0) continue;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int sl = 0; sl < kMaxSlots; ++sl) {
+                    if (!((any_slot >> sl) & 1)) continue;     // warp-uniform
+                    const float2 gv = gs[warp][sl][js[u]];
+                    a0 = fmaf(cw[sl], gv.x, a0);
+                    a1 = fmaf(cw[sl], gv.y, a1);
+                    dcode[sl] = fmaf(vs[u].x, gv.x, fmaf(vs[u].y, gv.y, dcode[sl]));
+                }
+                if (K.B.d_tables) {
+                    float2 *dst = reinterpret_cast<float2 *>(K.B.d_tables + ((size_t)(e0 + js[u]) * NSB_MEMBERS + lane) * 2);
+                    float2 cur = *dst;
+                    cur.x += a0; cur.y += a1;
+                    *dst = cur;
+                }
+            }
         }
+        __syncwarp();
     }
     if (K.B.d_blend_codes) {
 #pragma unroll
@@ -494,12 +617,17 @@ extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_fiel
                 return 1;
             }
         }
-        hash_bwd_kernel<<<blocks, 256, 0, st>>>(K);
-        rc = check_launch("hash_bwd_kernel");
+        if (args->g_rank1 && args->corner_vals && !samples->sample_blend_codes) {
+            hash_bwd_cv_kernel<<<blocks, 256, 0, st>>>(K);
+            rc = check_launch("hash_bwd_cv_kernel");
+        } else {
+            hash_bwd_kernel<<<blocks, 256, 0, st>>>(K);
+            rc = check_launch("hash_bwd_kernel");
+        }
         if (rc) return rc;
-        if (args->g_rank1 && (args->d_tables || args->d_blend_codes)) {
+        if (args->g_rank1 && (args->d_tables || args->d_blend_codes || args->cw_slots_out)) {
             const size_t total = (size_t)params->levels.offset[NSB_MAX_LEVELS - 1] + params->levels.entries[NSB_MAX_LEVELS - 1];
-            hash_expand_kernel<<<g_bwd_sms * 8, 256, 0, st>>>(K, total);
+            hash_expand_kernel<<<g_bwd_sms * 6, kExpWarps * 32, 0, st>>>(K, total);
             rc = check_launch("hash_expand_kernel");
         }
     }

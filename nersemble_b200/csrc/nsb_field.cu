@@ -623,6 +623,7 @@ struct alignas(128) SmemWS {
     alignas(16) __half feat[2][NSB_TILE * kFeatStride];
     TensorScratch ts[kTensorWarps];
     uint2 blend_b[kGatherWarps][4 * 32];   // per gather warp: the current timestep's B fragments (lane-private columns)
+    uint4 cv_stage[kGatherWarps][32];      // per gather warp: the current sample's corner values (training forward)
 };
 
 struct RingRefill {
@@ -857,9 +858,18 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
                 const bool has_next = nrow < rows_valid;
                 __half *feat_row = &sm.feat[b][row * kFeatStride];
                 float4 nx = xs;
-                gather_sample_quad(A.P, tab, xs.x, xs.y, xs.z,
-                                   has_next ? reinterpret_cast<const float4 *>(sm.xs[b][nrow]) : nullptr, nx, Bf, Ga, Q,
-                                   feat_row, lane);
+                // training: corner values are staged in this warp's 512 B of shared memory (one 32-bit address live across
+                // the sample instead of a 64-bit global pointer) and leave as ONE coalesced 16 B-per-lane store
+                __half2 *cv_row = SAVE ? reinterpret_cast<__half2 *>(sm.cv_stage[warp - kTensorWarps]) : nullptr;
+                gather_sample_quad<SAVE>(A.P, tab, xs.x, xs.y, xs.z,
+                                         has_next ? reinterpret_cast<const float4 *>(sm.xs[b][nrow]) : nullptr, nx, Bf, Ga, Q,
+                                         feat_row, cv_row, lane);
+                if (SAVE && A.out.corner_vals) {
+                    __syncwarp();
+                    reinterpret_cast<uint4 *>(A.out.corner_vals)[((int64_t)tile * NSB_TILE + row) * 32 + lane] =
+                        sm.cv_stage[warp - kTensorWarps][lane];
+                    __syncwarp();
+                }
                 if (A.out.feat) {   // feature output / training: the row goes to global too
                     __syncwarp();
                     reinterpret_cast<__half *>(A.out.feat)[((int64_t)tile * NSB_TILE + row) * 32 + lane] = feat_row[lane];
@@ -1003,7 +1013,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             auto save_act = [&](int layer, int buf) {   // training: keep the layer output for the backward pass
                 if (SAVE && kMT == 1 && A.out.deform_acts) {
                     uint4 *dst = reinterpret_cast<uint4 *>(A.out.deform_acts) + (((size_t)tile * kTensorWarps + warp) * 6 + layer) * 256;
-#pragma unroll
+#pragma unroll 2      // fully unrolled = 32 transient registers in the 80-register tensor role
                     for (int kt = 0; kt < 8; ++kt) dst[kt * 32 + lane] = ts.act[buf][0][kt][lane];
                 }
             };
@@ -1211,7 +1221,7 @@ static int launch_field_ws_(const FieldArgs &A, cudaStream_t st) {
 }
 template <bool D, bool F, bool H>
 static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
-    const bool save = A.out.xs || A.out.deform_acts || A.out.deform_enc;
+    const bool save = A.out.xs || A.out.deform_acts || A.out.deform_enc || A.out.corner_vals;
     return save ? launch_field_ws_<D, F, H, true>(A, st) : launch_field_ws_<D, F, H, false>(A, st);
 }
 

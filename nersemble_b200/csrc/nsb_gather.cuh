@@ -297,7 +297,10 @@ __device__ __forceinline__ void park_blend_b(const BlendB &B, uint2 *warp_slot, 
 #pragma unroll
     for (int s = 0; s < 4; ++s) warp_slot[s * 32 + lane] = make_uint2(B.lo[s], B.hi[s]);
 }
-__device__ __forceinline__ float gather_consume(const GatherTile &G, const BlendBSmem &B, int lane) {
+// cv (training forward only): the member-blended value of each corner BEFORE the trilinear weight, fp16 pairs
+// [level][corner] -- what the position gradient needs (d w / d x times the blended corner value), saved so that
+// the backward does not gather the table lines a second time.  cv points at this tile's two levels.
+__device__ __forceinline__ float gather_consume(const GatherTile &G, const BlendBSmem &B, int lane, __half2 *cv = nullptr) {
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -305,38 +308,42 @@ __device__ __forceinline__ float gather_consume(const GatherTile &G, const Blend
         const uint32_t a[4] = {G.v[0][s], G.v[1][s], G.v[0][4 + s], G.v[1][4 + s]};
         mma16816(c, a, b.x, b.y);
     }
+    if (cv && (lane & 3) == 0) {
+        cv[lane >> 2] = __floats2half2_rn(c[0], c[1]);
+        cv[8 + (lane >> 2)] = __floats2half2_rn(c[2], c[3]);
+    }
     const float u0 = butterfly(c[0] * G.w[0], c[1] * G.w[0], 2, lane);
     const float u1 = butterfly(c[2] * G.w[1], c[3] * G.w[1], 2, lane);
     return butterfly(u0, u1, 3, lane);
 }
 
-template <class BT>
+template <bool CV, class BT>
 __device__ __forceinline__ void gather_sample_quad(const nsb_field_params &P, const uint8_t *tab, float x, float y,
                                                    float z, const float4 *next_xs, float4 &next_out, const BT &B,
-                                                   GatherTile &Ga, QuadIdx &Q, __half *feat_row, int lane) {
+                                                   GatherTile &Ga, QuadIdx &Q, __half *feat_row, __half2 *cv_row, int lane) {
     const int g = lane >> 2;
     const bool owner = (lane & 3) == 0;
     GatherTile Gb;
     float e, o, yv;
-    gather_issue_q<0, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue_q<0, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane, CV ? cv_row + 0 : nullptr);
     Q = quad_compute<1>(P, x, y, z, lane);
-    gather_issue_q<1, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    gather_issue_q<1, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane, CV ? cv_row + 16 : nullptr); yv = butterfly(e, o, 4, lane);
     if (owner) feat_row[g] = __float2half_rn(yv);
-    gather_issue_q<1, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue_q<1, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane, CV ? cv_row + 32 : nullptr);
     Q = quad_compute<2>(P, x, y, z, lane);
-    gather_issue_q<2, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    gather_issue_q<2, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane, CV ? cv_row + 48 : nullptr); yv = butterfly(e, o, 4, lane);
     if (owner) feat_row[8 + g] = __float2half_rn(yv);
-    gather_issue_q<2, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue_q<2, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane, CV ? cv_row + 64 : nullptr);
     Q = quad_compute<3>(P, x, y, z, lane);
-    gather_issue_q<3, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    gather_issue_q<3, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane, CV ? cv_row + 80 : nullptr); yv = butterfly(e, o, 4, lane);
     if (owner) feat_row[16 + g] = __float2half_rn(yv);
-    gather_issue_q<3, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane);
+    gather_issue_q<3, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane, CV ? cv_row + 96 : nullptr);
     if (next_xs) {
         next_out = *next_xs;
         Q = quad_compute<0>(P, next_out.x, next_out.y, next_out.z, lane);
         gather_issue_q<0, 0>(P, tab, Q, g, Ga);
     }
-    o = gather_consume(Gb, B, lane); yv = butterfly(e, o, 4, lane);
+    o = gather_consume(Gb, B, lane, CV ? cv_row + 112 : nullptr); yv = butterfly(e, o, 4, lane);
     if (owner) feat_row[24 + g] = __float2half_rn(yv);
 }
 

@@ -36,21 +36,53 @@ def gather_rays(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
 
 
-def allreduce_gradients(params, average: bool = True) -> None:
-    """The training collective: ONE all-reduce of the flat gradient buffer per step
-    (403 M table gradients + MLP/embedding gradients), then divide by the world size.  Parameters whose .grad is
-    None on this rank contribute zeros so that every rank issues the same collective."""
+_BIG = 1 << 24   # elements: tensors this large are reduced in place, not copied into the flat bucket
+
+
+def allreduce_gradients(params, average: bool = True, hash_ensembles=()) -> None:
+    """The training collective: gradients summed over ranks once per step, then divided by the world size.
+    Small gradients (MLPs, embeddings) travel in ONE flat bucket; the table gradient (1.6 GB dense) is reduced in place
+    -- copying it into a bucket and back costs three extra passes over it.  With the fused optimiser
+    (nersemble_b200.optim) the table gradient is still in rank-1 form [slots][entries][2] when this runs: when the
+    slot map is the same on every rank (n_timesteps <= 32: slot = timestep) that workspace is reduced directly
+    (n_timesteps/32 of the dense volume) and the 1/world factor is folded into the optimiser step; otherwise it is
+    expanded to a dense .grad first.  Parameters whose .grad is None on this rank contribute zeros so that every rank
+    issues the same collectives."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
+    world = dist.get_world_size()
+    for he in hash_ensembles:
+        pend = he.pending_table_grad
+        if pend is None:
+            continue
+        if pend.get("slots_are_timesteps"):
+            dist.all_reduce(pend["g_rank1"], op=dist.ReduceOp.SUM)
+            pend["scale"] = float(pend.get("scale", 1.0)) / (world if average else 1)
+        else:
+            he.materialize_pending()
     params = [p for p in params if p.requires_grad]
+    deferred = {id(he.tables) for he in hash_ensembles if he.pending_table_grad is not None}
+    params = [p for p in params if id(p) not in deferred]
     if not params:
         return
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    small = []
+    for p in params:
+        if p.numel() >= _BIG:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+            if average:
+                p.grad /= world
+        else:
+            small.append(p)
+    if not small:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in small])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     if average:
-        flat /= dist.get_world_size()
+        flat /= world
     ofs = 0
-    for p in params:
+    for p in small:
         n = p.numel()
         g = flat[ofs:ofs + n].view_as(p)
         if p.grad is None:

@@ -73,25 +73,19 @@ class NativeParams:
         tab = None if tables is None else tables.detach().to(dev).half().contiguous()
         fp = fpt = None
         if base_w is not None:
-            bw, hw = [w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w]
-            fp = packing.pack_field(bw, hw)
-            fpt = packing.pack_field_bwd(bw, hw)
+            fp, fpt = packing.pack_field_fast([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
         dp = db = wc = None
         if deform is not None:
-            dp, db = packing.pack_deform([w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]],
-                                         deform["r_w"].to(dev), deform["r_b"].to(dev),
-                                         deform["v_w"].to(dev), deform["v_b"].to(dev))
+            sw, sb = [w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]]
+            dp, dtb, dpt = packing.pack_deform_weights_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
+            db = packing.deform_bias_vector(sb, deform["r_b"].to(dev), deform["v_b"].to(dev))
             wc = time_emb_deform.detach().to(dev).half().contiguous()
-            dtb, dcb = packing.pack_deform_tb([w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]],
-                                              deform["r_w"].to(dev), deform["r_b"].to(dev), deform["v_w"].to(dev),
-                                              deform["v_b"].to(dev), wc)
+            dcb = packing.deform_code_bias(sw, sb, wc)
         te = None if time_emb is None else time_emb.detach().to(dev).float().contiguous()
         n_t = int(time_emb.shape[0]) if time_emb is not None else (int(time_emb_deform.shape[0]) if time_emb_deform is not None else 1)
         P = NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
         if deform is not None:
-            P.deform_packed_tb, P.deform_code_bias = dtb, dcb
-            P.deform_packed_t = packing.pack_deform_bwd([w.to(dev) for w in deform["stem_w"]], deform["r_w"].to(dev),
-                                                        deform["v_w"].to(dev))
+            P.deform_packed_tb, P.deform_code_bias, P.deform_packed_t = dtb, dcb, dpt
         P.field_packed_t = fpt
         return P
 
@@ -188,6 +182,9 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
         out["feat"] = torch.empty((n, 32), dtype=torch.float16, device=dev); o.feat = _ptr(out["feat"])
     if "xs" in want:
         out["xs"] = torch.empty((n, 4), dtype=_F32, device=dev); o.xs = _ptr(out["xs"])
+    if "corner_vals" in want:   # training forward: blended corner values, so the backward does not re-gather the tables
+        out["corner_vals"] = torch.empty((n, 16, 8, 2), dtype=torch.float16, device=dev)
+        o.corner_vals = _ptr(out["corner_vals"])
     if "deform_acts" in want:   # training forward: stem activations + posenc fragments for nsb_deform_backward
         n_tiles = (n + 127) // 128
         out["deform_acts"] = torch.empty((n_tiles, 8, 6, 8, 32, 4), dtype=torch.int32, device=dev)
@@ -230,7 +227,7 @@ def _fill_samples(s, keep, *, origins=None, directions=None, ray_times=None, t_s
 def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Optional[torch.Tensor],
                    d_rgb: Optional[torch.Tensor], *, window_hash=None, loss_scale: float = 128.0,
                    want_tables: bool = True, want_codes: bool = True, want_dx: bool = False, rank1: bool = True,
-                   disable_initial=True, soft_transition=True,
+                   defer_tables: bool = False, disable_initial=True, soft_transition=True,
                    **sample_kw) -> Dict[str, torch.Tensor]:
     """Backward of the density/colour MLPs and the hash ensemble (nsb_field_backward).
     saved: feat, xs, sigma, rgb from field_forward(want=(..., "feat", "xs")).  Returns fp32 gradients:
@@ -248,10 +245,16 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
     a.field_packed_t = _ptr(P.field_packed_t)
     a.feat, a.xs, a.sigma, a.rgb, a.d_sigma, a.d_rgb = _ptr(feat), _ptr(xs), _ptr(sg), _ptr(cc), _ptr(dsg), _ptr(drg)
     a.loss_scale = float(loss_scale)
+    if saved.get("corner_vals") is not None:
+        a.corner_vals = _ptr(saved["corner_vals"])
     out = {"d_feat": torch.zeros((n, 32), dtype=_F32, device=dev),
            "d_base_w": torch.zeros((3072,), dtype=_F32, device=dev), "d_head_w": torch.zeros((7168,), dtype=_F32, device=dev)}
     a.d_feat, a.d_base_w, a.d_head_w = _ptr(out["d_feat"]), _ptr(out["d_base_w"]), _ptr(out["d_head_w"])
-    if want_tables:
+    # defer_tables: leave the table gradient in its rank-1 form (out["pending"]) for table_adam_step / rank1_expand
+    # instead of expanding it to a dense 1.6 GB tensor here; falls back to dense when the rank-1 path is unavailable.
+    slot, n_slots = _rank1_slots(P, dev, sample_kw) if (rank1 and (want_tables or want_codes)) else (None, 0)
+    defer = bool(defer_tables and want_tables and slot is not None)
+    if want_tables and not defer:
         out["d_tables"] = torch.zeros((P.levels["total_entries"], 32, 2), dtype=_F32, device=dev)
         a.d_tables = _ptr(out["d_tables"])
     if want_codes:
@@ -262,28 +265,79 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
         a.d_xs = _ptr(out["d_xs"])
     if n == 0:
         return out
-    # rank-1 scatter (32x fewer atomics): needs table-indexed codes and <= 32 distinct timesteps in the batch
-    if rank1 and (want_tables or want_codes) and sample_kw.get("sample_blend_codes") is None:
-        T = P.n_timesteps
-        slot = None
-        if T <= 32:
-            slot, n_slots = torch.arange(T, dtype=torch.int32, device=dev), T
-        else:
-            tt = sample_kw.get("ray_times") if sample_kw.get("origins") is not None else sample_kw.get("sample_times")
-            if tt is not None:
-                ts_idx = (tt.reshape(-1).float() * (T - 1)).round().clamp_(0, T - 1).long()
-                uniq = torch.unique(ts_idx)                       # host sync: the slot count is data dependent
-                if uniq.numel() <= 32:
-                    slot = torch.full((T,), -1, dtype=torch.int32, device=dev)
-                    slot[uniq] = torch.arange(uniq.numel(), dtype=torch.int32, device=dev)
-                    n_slots = int(uniq.numel())
-        if slot is not None:
-            g1 = torch.zeros((n_slots, P.levels["total_entries"], 2), dtype=_F32, device=dev)
-            a.g_rank1, a.ts_slot, a.n_slots = _ptr(g1), _ptr(slot), n_slots
-            keep += [g1, slot]
+    if slot is not None:
+        g1 = torch.zeros((n_slots, P.levels["total_entries"], 2), dtype=_F32, device=dev)
+        a.g_rank1, a.ts_slot, a.n_slots = _ptr(g1), _ptr(slot), n_slots
+        keep += [g1, slot]
+        if defer:
+            cw = torch.zeros((n_slots, 32), dtype=_F32, device=dev)
+            a.cw_slots_out = _ptr(cw)
+            out["pending"] = {"g_rank1": g1, "cw_slots": cw, "n_slots": n_slots,
+                              "slots_are_timesteps": P.n_timesteps <= 32}
     opts = make_opts(window_hash, None, False, True, disable_initial, soft_transition)
     cp = P.c_params()
     _lib.check(lib.nsb_field_backward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(a), _stream()), "nsb_field_backward")
+    return out
+
+
+def _rank1_slots(P: "NativeParams", dev, sample_kw):
+    """Timestep -> slot map of the rank-1 table-gradient scatter (32x fewer atomics than the direct one): needs
+    table-indexed blend codes and <= 32 distinct timesteps in the batch.  Returns (slot [T] int32 | None, n_slots)."""
+    if sample_kw.get("sample_blend_codes") is not None:
+        return None, 0
+    T = P.n_timesteps
+    if T <= 32:
+        return torch.arange(T, dtype=torch.int32, device=dev), T
+    tt = sample_kw.get("ray_times") if sample_kw.get("origins") is not None else sample_kw.get("sample_times")
+    if tt is None:
+        return None, 0
+    ts_idx = (tt.reshape(-1).float() * (T - 1)).round().clamp_(0, T - 1).long()
+    uniq = torch.unique(ts_idx)                       # host sync: the slot count is data dependent
+    if uniq.numel() > 32:
+        return None, 0
+    slot = torch.full((T,), -1, dtype=torch.int32, device=dev)
+    slot[uniq] = torch.arange(uniq.numel(), dtype=torch.int32, device=dev)
+    return slot, int(uniq.numel())
+
+
+def table_adam_step(tables: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                    tables_half: Optional[torch.Tensor], *, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                    weight_decay: float = 0.0, grad: Optional[torch.Tensor] = None, pending: Optional[dict] = None,
+                    grad_scale: float = 1.0) -> None:
+    """torch.optim.Adam's update of the native fp32 table [E,32,2] in one fused pass (nsb_table_adam_step): the gradient
+    is a dense tensor and/or the deferred rank-1 form from field_backward(defer_tables=True); the fp16 copy the forward
+    kernels read is rewritten in the same pass.  In place; `step` is the 1-based step count."""
+    lib = _lib.load()
+    _need_cuda(tables, exp_avg, exp_avg_sq, tables_half, grad)
+    for t in (tables, exp_avg, exp_avg_sq):
+        assert t.dtype == _F32 and t.is_contiguous() and t.shape == tables.shape
+    a = _lib.TableAdamArgs()
+    a.total_entries = tables.shape[0]
+    a.tables, a.exp_avg, a.exp_avg_sq = _ptr(tables), _ptr(exp_avg), _ptr(exp_avg_sq)
+    if tables_half is not None:
+        assert tables_half.dtype == torch.float16 and tables_half.is_contiguous() and tables_half.shape == tables.shape
+        a.tables_half = _ptr(tables_half)
+    if grad is not None:
+        assert grad.dtype == _F32 and grad.is_contiguous() and grad.shape == tables.shape
+        a.grad = _ptr(grad)
+    if pending is not None:
+        a.g_rank1, a.cw_slots, a.n_slots = _ptr(pending["g_rank1"]), _ptr(pending["cw_slots"]), int(pending["n_slots"])
+    a.grad_scale = float(grad_scale)
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay)
+    a.bias_correction1 = 1.0 - float(betas[0]) ** step
+    a.bias_correction2 = 1.0 - float(betas[1]) ** step
+    _lib.check(lib.nsb_table_adam_step(C.byref(a), _stream()), "nsb_table_adam_step")
+
+
+def rank1_expand(pending: dict, total_entries: int, grad_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dense fp32 table gradient [E,32,2] (+= into `out`) from the deferred rank-1 form (nsb_rank1_expand)."""
+    lib = _lib.load()
+    g1 = pending["g_rank1"]
+    if out is None:
+        out = torch.zeros((total_entries, 32, 2), dtype=_F32, device=g1.device)
+    _need_cuda(g1, out)
+    _lib.check(lib.nsb_rank1_expand(_ptr(g1), _ptr(pending["cw_slots"]), int(pending["n_slots"]), int(total_entries),
+                                    float(grad_scale), _ptr(out), _stream()), "nsb_rank1_expand")
     return out
 
 

@@ -61,6 +61,11 @@ def tables_to_tcnn(tables: torch.Tensor) -> List[torch.Tensor]:
 
 
 # ------------------------------------------------------------------ MMA B-fragment packing
+def _f(t: torch.Tensor) -> torch.Tensor:
+    """fp32 view of a weight -- or the tensor itself when it carries int64 element ids (gather-plan tracing)."""
+    return t if t.dtype == torch.int64 else t.detach().float()
+
+
 def pack_mma_b(W: torch.Tensor, colmap: Sequence[int], group_cols: int) -> torch.Tensor:
     """W [N_out, K_in] -> fp16 tensor in order [group][k-tile][n-tile pair][lane][ntsel][hi][e]:
     lane = g*4+q holds, for n = group*group_cols + pair*16 + ntsel*8 + g and
@@ -70,10 +75,11 @@ def pack_mma_b(W: torch.Tensor, colmap: Sequence[int], group_cols: int) -> torch
     assert Kp % 16 == 0 and group_cols % 16 == 0
     Np = ((N + group_cols - 1) // group_cols) * group_cols
     cm = torch.as_tensor(list(colmap), dtype=torch.long, device=W.device)
-    Wp = torch.zeros((Np, Kp), dtype=torch.float32, device=W.device)
+    ids = W.dtype == torch.int64                     # gather-plan tracing (gather_plan below): element ids, 0 = zero
+    Wp = torch.zeros((Np, Kp), dtype=torch.int64 if ids else torch.float32, device=W.device)
     valid = cm >= 0
-    Wp[:N][:, valid] = W.detach().float()[:, cm[valid]]
-    Wh = Wp.half()
+    Wp[:N][:, valid] = _f(W)[:, cm[valid]]
+    Wh = Wp if ids else Wp.half()
     G, NPR, KT = Np // group_cols, group_cols // 16, Kp // 16
     t = Wh.view(G, NPR, 2, 8, KT, 2, 4, 2)          # (grp, pair, ntsel, g, kt, hi, q, e)
     t = t.permute(0, 4, 1, 3, 6, 2, 5, 7)           # (grp, kt, pair, g, q, ntsel, hi, e)
@@ -104,20 +110,10 @@ def pack_deform(stem_w: Sequence[torch.Tensor], stem_b: Sequence[torch.Tensor], 
     """mlp_stem (6 Linear, skip at 4: input [in(173) | hidden(128)]), mlp_r, mlp_v
     (field_components/deformation_field.py:50-75) -> (packed fp16 weights, fp32 bias[776])."""
     assert len(stem_w) == 6 and stem_w[0].shape == (128, DEFORM_IN_DIM) and stem_w[4].shape == (128, DEFORM_IN_DIM + 128)
-    in_map = deform_input_colmap()
-    ident = list(range(128))
-    skip_map = [DEFORM_IN_DIM + k for k in range(128)] + in_map      # kernel order: [hidden | input]
-    maps = [in_map, ident, ident, ident, skip_map, ident]
-    parts = [pack_mma_b(w, m, 64) for w, m in zip(stem_w, maps)]
-    heads = torch.cat([v_w.detach().float(), r_w.detach().float()], 0)    # cols 0..2 = v, 3..5 = r
-    parts.append(pack_mma_b(heads, ident, 16))
-    packed = torch.cat(parts)
-    dev = stem_b[0].device
-    bias = torch.cat([b.detach().float().reshape(-1) for b in stem_b] +
-                     [v_b.detach().float().reshape(-1), r_b.detach().float().reshape(-1),
-                      torch.zeros(2, device=dev)])
+    packed = _deform_weights(stem_w, r_w, v_w, deform_input_colmap())
+    bias = deform_bias_vector(stem_b, r_b, v_b)
     assert packed.numel() * 2 == 258048 and bias.numel() == 776
-    return packed.contiguous(), bias.contiguous()
+    return packed.contiguous(), bias
 
 
 def pack_deform_tb(stem_w, stem_b, r_w, r_b, v_w, v_b, warp_codes: torch.Tensor):
@@ -125,21 +121,9 @@ def pack_deform_tb(stem_w, stem_b, r_w, r_b, v_w, v_b, warp_codes: torch.Tensor)
     timestep, so W_code . code[t] + b is precomputed per timestep (fp16-rounded operands, fp32 accumulate -- the same
     products the MMA would form) and enters the kernel as a per-row bias.  Returns (packed fp16 without those
     columns, code_bias float [T,2,128])."""
-    in_map = deform_input_colmap()[:48]                      # posenc part only (kernel order, padded to 48)
-    ident = list(range(128))
-    skip_map = [DEFORM_IN_DIM + k for k in range(128)] + in_map
-    maps = [in_map, ident, ident, ident, skip_map, ident]
-    parts = [pack_mma_b(w, m, 64) for w, m in zip(stem_w, maps)]
-    heads = torch.cat([v_w.detach().float(), r_w.detach().float()], 0)
-    parts.append(pack_mma_b(heads, ident, 16))
-    packed = torch.cat(parts)
+    packed = _deform_weights(stem_w, r_w, v_w, deform_input_colmap()[:48])   # posenc part only (kernel order, padded to 48)
     assert packed.numel() * 2 == 94 * 2048
-    ch = warp_codes.detach().half().float()
-    cb = []
-    for l in (0, 4):
-        wc = stem_w[l].detach()[:, 45:DEFORM_IN_DIM].half().float()          # [128 out, 128 code]
-        cb.append(ch @ wc.t() + stem_b[l].detach().float()[None, :])
-    return packed.contiguous(), torch.stack(cb, 1).contiguous()
+    return packed.contiguous(), deform_code_bias(stem_w, stem_b, warp_codes)
 
 
 def pack_deform_bwd(stem_w, r_w, v_w) -> torch.Tensor:
@@ -147,10 +131,10 @@ def pack_deform_bwd(stem_w, r_w, v_w) -> torch.Tensor:
     heads, L5, L4[:, hidden], L4[:, code], L3, L2, L1, L0[:, code]  (K = 128 outputs; N = 128 columns in two halves).
     Hidden columns of layer 4 are the reference columns 173.., code columns are 45..172 of layers 0 and 4."""
     o128 = list(range(128))
-    heads = torch.cat([v_w.detach().float(), r_w.detach().float()], 0)            # [6, 128]: rows = (v, r) outputs
+    heads = torch.cat([_f(v_w), _f(r_w)], 0)            # [6, 128]: rows = (v, r) outputs
     parts = [pack_mma_b(heads.t(), list(range(6)) + [-1] * 10, 64)]
     def T(w, cols):
-        return pack_mma_b(w.detach().float()[:, cols].t(), o128, 64)
+        return pack_mma_b(_f(w)[:, cols].t(), o128, 64)
     code = list(range(45, DEFORM_IN_DIM))
     hidden4 = list(range(DEFORM_IN_DIM, DEFORM_IN_DIM + 128))
     parts += [T(stem_w[5], o128), T(stem_w[4], hidden4), T(stem_w[4], code), T(stem_w[3], o128), T(stem_w[2], o128),
@@ -189,6 +173,89 @@ def pack_field_bwd(base_w: Sequence[torch.Tensor], head_w: Sequence[torch.Tensor
     packed = torch.cat(parts)
     assert packed.numel() * 2 == 20480 and [p.numel() // 8 for p in parts] == [256, 128, 256, 512, 128]
     return packed.contiguous()
+
+
+# ------------------------------------------------------------------ gather plans
+# Training re-packs the MLP weights every step (they change every step).  The packers above are the definition of the
+# layouts but cost ~300 small torch ops per step (advanced indexing per layer: r1d profile, 9 ms of CPU time, more than
+# the GPU time of the forward).  A plan is the same packer traced once on int64 element ids: afterwards packing is
+# cat(sources) -> one gather -> half.
+_PLANS: dict = {}
+
+
+def gather_plan(name: str, fn, shapes: Sequence[Sequence[int]], device) -> torch.Tensor:
+    """Index tensor `idx` such that fn(*ws) == cat([0], *[w.reshape(-1) for w in ws])[idx].half() for weights of the
+    given shapes.  fn must build its result from _f()/pack_mma_b/slicing/cat only."""
+    key = (name, str(device))
+    if key not in _PLANS:
+        ids, ofs = [], 1
+        for shp in shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            ids.append(torch.arange(ofs, ofs + n, dtype=torch.int64, device=device).view(*shp))
+            ofs += n
+        idx = fn(*ids)
+        assert idx.dtype == torch.int64
+        _PLANS[key] = idx.contiguous()
+    return _PLANS[key]
+
+
+def apply_plan(idx: torch.Tensor, sources: Sequence[torch.Tensor]) -> torch.Tensor:
+    flat = torch.cat([torch.zeros(1, dtype=torch.float32, device=idx.device)] + [_f(w).reshape(-1) for w in sources])
+    return flat[idx].half()
+
+
+_STEM_SHAPES = [(128, DEFORM_IN_DIM), (128, 128), (128, 128), (128, 128), (128, DEFORM_IN_DIM + 128), (128, 128)]
+_FIELD_SHAPES = [(64, 32), (16, 64), (64, 32), (64, 64), (16, 64)]
+
+
+def pack_deform_weights_fast(stem_w, r_w, v_w):
+    """(pack_deform weights, pack_deform_tb weights, pack_deform_bwd) through cached gather plans."""
+    dev = stem_w[0].device
+    shapes = _STEM_SHAPES + [(3, 128), (3, 128)]
+    src = list(stem_w) + [r_w, v_w]
+    z6 = [torch.zeros(128) for _ in range(6)]
+    z3 = torch.zeros(3)
+    p_fwd = gather_plan("deform", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()), shapes, dev)
+    p_tb = gather_plan("deform_tb", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()[:48]), shapes, dev)
+    p_bwd = gather_plan("deform_bwd", lambda *w: pack_deform_bwd(w[:6], w[6], w[7]), shapes, dev)
+    return apply_plan(p_fwd, src), apply_plan(p_tb, src), apply_plan(p_bwd, src)
+
+
+def pack_field_fast(base_w, head_w):
+    """(pack_field, pack_field_bwd) through cached gather plans."""
+    dev = base_w[0].device
+    src = list(base_w) + list(head_w)
+    p_f = gather_plan("field", lambda *w: pack_field(w[:2], w[2:]), _FIELD_SHAPES, dev)
+    p_b = gather_plan("field_bwd", lambda *w: pack_field_bwd(w[:2], w[2:]), _FIELD_SHAPES, dev)
+    return apply_plan(p_f, src), apply_plan(p_b, src)
+
+
+def _deform_weights(stem_w, r_w, v_w, in_map):
+    """The weight part shared by pack_deform (in_map = 176 columns) and pack_deform_tb (48 posenc columns)."""
+    ident = list(range(128))
+    skip_map = [DEFORM_IN_DIM + k for k in range(128)] + list(in_map)
+    maps = [in_map, ident, ident, ident, skip_map, ident]
+    parts = [pack_mma_b(w, m, 64) for w, m in zip(stem_w, maps)]
+    parts.append(pack_mma_b(torch.cat([_f(v_w), _f(r_w)], 0), ident, 16))
+    return torch.cat(parts)
+
+
+def deform_bias_vector(stem_b, r_b, v_b) -> torch.Tensor:
+    dev = stem_b[0].device
+    return torch.cat([b.detach().float().reshape(-1) for b in stem_b] +
+                     [v_b.detach().float().reshape(-1), r_b.detach().float().reshape(-1), torch.zeros(2, device=dev)]).contiguous()
+
+
+def deform_code_bias(stem_w, stem_b, warp_codes: torch.Tensor) -> torch.Tensor:
+    """[T, 2, 128]: W_code(layer 0 | 4) . warp_code[t] + bias (see pack_deform_tb)."""
+    ch = warp_codes.detach().half().float()
+    cb = []
+    for l in (0, 4):
+        wc = stem_w[l].detach()[:, 45:DEFORM_IN_DIM].half().float()
+        cb.append(ch @ wc.t() + stem_b[l].detach().float()[None, :])
+    return torch.stack(cb, 1).contiguous()
 
 
 def split_tcnn_mlp_params(flat: torch.Tensor, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:

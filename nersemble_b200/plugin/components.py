@@ -4,6 +4,7 @@ engine/generic_scheduler.py of the reference, computing through libnsb."""
 from __future__ import annotations
 
 import math
+import weakref
 from dataclasses import dataclass
 from math import ceil
 from typing import Dict, List, Literal, Optional, Tuple
@@ -77,9 +78,28 @@ class HashEnsembleConfig:
     use_soft_transition: bool = False
 
 
+class _GridView:
+    """Read/write shim with the reference's `hash_encodings[c].params` spelling.  `.params` is a copy of grid c in tcnn's
+    flat layout; the storage is HashEnsemble.tables (native layout)."""
+
+    def __init__(self, owner: "HashEnsemble", c: int):
+        self._owner, self._c = owner, c
+
+    @property
+    def params(self) -> torch.Tensor:
+        t = self._owner.tables.detach()
+        return t[:, 4 * self._c:4 * self._c + 4, :].reshape(-1)
+
+
 class HashEnsemble(nn.Module):
-    """hash_ensemble.py:69-168.  Parameters are kept in the reference's layout (8 flat tcnn grids of 8
-    features/level); the 128-byte-per-entry fp16 table the kernels read is a cache rebuilt when they change."""
+    """hash_ensemble.py:69-168.
+
+    Storage.  The reference holds 8 tcnn grids of 8 features/level (`hash_encodings.{c}.params`, flat fp32).  Here the
+    ONE trainable tensor is `tables`, fp32 [total_entries, 32 members, 2 feats] -- the layout the kernels gather (one
+    128-byte fp16 line per entry) and scatter gradients into, so a training step never permutes 1.6 GB between
+    layouts (r1d profile: ~13 ms of index/cat/copy glue per step).  state_dict()/load_state_dict() still speak the
+    reference's keys and flat shapes (hooks below), and the parameter sits in the same `fields` group.  The fp16 copy
+    the forward kernels read is a cache refreshed when `tables` changes (or written by the fused optimiser)."""
 
     def __init__(self, config: HashEnsembleConfig, seed: Optional[int] = None):
         super().__init__()
@@ -93,29 +113,79 @@ class HashEnsemble(nn.Module):
         self.use_soft_transition = config.use_soft_transition
         n_total_features = config.n_hash_encodings * hc.n_features_per_level
         self.levels = hc.level_table()
+        self.n_grids = ceil(n_total_features / 8)
         g = torch.Generator()
         if seed is not None:
             g.manual_seed(seed)
-        grids = []
-        for _ in range(ceil(n_total_features / 8)):
-            # tcnn grid init U(-1e-4, 1e-4)
-            grids.append(_FlatParams((torch.rand(self.levels["total_entries"] * 8, generator=g) * 2 - 1) * 1e-4))
-        self.hash_encodings = nn.ModuleList(grids)
+        # tcnn grid init U(-1e-4, 1e-4), drawn grid by grid like the reference builds its ModuleList
+        grids = [(torch.rand(self.levels["total_entries"] * 8, generator=g) * 2 - 1) * 1e-4 for _ in range(self.n_grids)]
+        self.tables = nn.Parameter(packing.tables_from_tcnn(grids))
+        del grids
         self.n_output_dims = hc.n_levels * hc.n_features_per_level
         self._native = None
         self._native_version = None
+        self._shadow = None
+        # fused optimiser protocol (nersemble_b200/optim.py): with defer_table_grad the training backward parks the
+        # table gradient here in rank-1 form instead of writing a dense `.grad`
+        self.defer_table_grad = False
+        self.pending_table_grad = None
+        self.tables._nsb_hash_ensemble = weakref.ref(self)
+        self._register_state_dict_hook(self._to_reference_keys)
+        self._register_load_state_dict_pre_hook(self._from_reference_keys)
 
-    # -- native table cache
-    def _versions(self):
-        return tuple((p.params._version, p.params.data_ptr()) for p in self.hash_encodings)
+    # -- reference-compatible views / checkpoints
+    @property
+    def hash_encodings(self) -> List[_GridView]:
+        return [_GridView(self, c) for c in range(self.n_grids)]
 
+    @torch.no_grad()
+    def load_tcnn_grids(self, grids) -> None:
+        """grids: 8 flat tensors in tcnn layout (what `hash_encodings.{c}.params` holds upstream)."""
+        self.tables.copy_(packing.tables_from_tcnn([g.to(self.tables.device) for g in grids]))
+
+    def tcnn_grids(self, tensor: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        return packing.tables_to_tcnn((self.tables if tensor is None else tensor).detach())
+
+    @staticmethod
+    def _to_reference_keys(module, state_dict, prefix, local_metadata):
+        t = state_dict.pop(prefix + "tables")
+        for c, g in enumerate(packing.tables_to_tcnn(t)):
+            state_dict[f"{prefix}hash_encodings.{c}.params"] = g
+        return state_dict
+
+    def _from_reference_keys(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        keys = [f"{prefix}hash_encodings.{c}.params" for c in range(self.n_grids)]
+        if all(k in state_dict for k in keys):
+            state_dict[prefix + "tables"] = packing.tables_from_tcnn([state_dict.pop(k) for k in keys])
+
+    # -- native fp16 table cache
     def native_tables(self) -> torch.Tensor:
-        v = self._versions()
+        v = (self.tables._version, self.tables.data_ptr())
         if self._native is None or v != self._native_version:
             with torch.no_grad():
-                self._native = packing.tables_from_tcnn([m.params.detach() for m in self.hash_encodings]).half().contiguous()
+                self._native = self.tables.detach().half()
             self._native_version = v
         return self._native
+
+    def shadow_buffer(self) -> torch.Tensor:
+        if self._shadow is None or self._shadow.device != self.tables.device:
+            self._shadow = torch.empty(self.tables.shape, dtype=torch.float16, device=self.tables.device)
+        return self._shadow
+
+    def materialize_pending(self, scale: float = 1.0) -> None:
+        """Turn a parked rank-1 table gradient into a dense `.grad` (+=): gradient accumulation, dense all-reduce."""
+        pend = self.pending_table_grad
+        if pend is None:
+            return
+        g = ops.rank1_expand(pend, self.tables.shape[0], grad_scale=scale * float(pend.get("scale", 1.0)), out=self.tables.grad)
+        if self.tables.grad is None:
+            self.tables.grad = g
+        self.pending_table_grad = None
+
+    def set_native_tables(self, shadow: torch.Tensor) -> None:
+        """The fused optimiser writes the fp16 copy itself; mark it current for the present value of `tables`."""
+        self._native = shadow
+        self._native_version = (self.tables._version, self.tables.data_ptr())
 
     def forward(self, in_tensor: torch.Tensor, conditioning_code: torch.Tensor, windows_param: Optional[float] = None,
                 window_hash_encodings: Optional[float] = None) -> torch.Tensor:
@@ -124,7 +194,7 @@ class HashEnsemble(nn.Module):
         assert conditioning_code.shape[-1] == self.n_hash_encodings, \
             "If blend mixing type is chosen, conditioning code needs to have as many dimensions as there are " \
             "hashtables in the encoding"
-        _no_autograd(in_tensor, conditioning_code, *[m.params for m in self.hash_encodings])
+        _no_autograd(in_tensor, conditioning_code, self.tables)
         P = ops.NativeParams(self.native_tables(), None, None, None, None, None, torch.tensor([[0., 0, 0], [1, 1, 1]]),
                              self.levels, 1)
         return ops.hash_blend_forward(P, in_tensor, conditioning_code, window_hash=window_hash_encodings, out_half=True,
@@ -135,7 +205,7 @@ class HashEnsemble(nn.Module):
         return self.n_output_dims
 
     def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
-        return {"fields": list(self.hash_encodings.parameters())}
+        return {"fields": [self.tables]}
 
 
 @dataclass

@@ -86,7 +86,7 @@ class _RenderFunction(torch.autograd.Function):
     """Differentiable fused render (training).  Forward = nsb_field_forward (saving the blended features, the warped
     positions and the deformation activations) + nsb_composite_forward; backward = nsb_composite_backward ->
     nsb_field_backward -> nsb_deform_backward, with the fp32 gradients mapped back to the reference's parameter
-    layouts (8 tcnn grids, flat tcnn MLP params, nn.Linear weights/biases, the two time embeddings)."""
+    layouts (flat tcnn MLP params, nn.Linear weights/biases, the two time embeddings; the hash tables in native layout)."""
 
     @staticmethod
     def forward(ctx, model, origins, directions, ray_times, starts, ends, ray_indices, packed_info, wh, wd, *params):
@@ -94,14 +94,14 @@ class _RenderFunction(torch.autograd.Function):
         deform = model.config.use_deformation_field
         kw = dict(origins=origins, directions=directions, ray_times=ray_times, t_starts=starts, t_ends=ends,
                   ray_indices=ray_indices)
-        want = ("sigma", "rgb", "feat", "xs") + (("offsets", "deform_acts") if deform else ())
+        want = ("sigma", "rgb", "feat", "xs") + (("offsets", "deform_acts", "corner_vals") if deform else ())
         f = ops.field_forward(P, window_hash=wh, window_deform=wd, use_deformation=deform, want=want, **kw,
                               **model._blend_opts())
         c = ops.composite(packed_info, starts, ends, f["sigma"], f["rgb"], f["offsets"] if deform else None, training=True)
         ctx.model, ctx.P, ctx.kw, ctx.wh, ctx.wd, ctx.deform = model, P, kw, wh, wd, deform
         ctx.saved = {k: f[k] for k in ("feat", "xs", "sigma", "rgb")}
         if deform:
-            ctx.saved.update(deform_acts=f["deform_acts"], deform_enc=f["deform_enc"])
+            ctx.saved.update(deform_acts=f["deform_acts"], deform_enc=f["deform_enc"], corner_vals=f["corner_vals"])
         ctx.packed_info, ctx.workspace = packed_info, c["workspace"]
         outs = (c["rgb"], c["accumulation"], c["depth"], c["weights"])
         if deform:
@@ -119,9 +119,13 @@ class _RenderFunction(torch.autograd.Function):
                                                 None if g_acc is None else g_acc.reshape(-1),
                                                 None if g_depth is None else g_depth.reshape(-1),
                                                 None if g_weights is None else g_weights.reshape(-1))
+        he = model.field.hash_ensemble
+        defer = he.defer_table_grad and he.pending_table_grad is None     # a second backward before step() goes dense
         g = ops.field_backward(ctx.P, ctx.saved, d_sigma, d_rgb, window_hash=ctx.wh, loss_scale=ls, want_dx=ctx.deform,
-                               **kw, **model._blend_opts())
-        grads = list(packing.tables_to_tcnn(g["d_tables"])) + [g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
+                               defer_tables=defer, **kw, **model._blend_opts())
+        if "pending" in g:
+            he.pending_table_grad = g["pending"]
+        grads = [g.get("d_tables"), g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
         if ctx.deform:
             d = ops.deform_backward(ctx.P, ctx.saved, g["d_xs"], window_deform=ctx.wd, loss_scale=ls, **kw)
             grads.append(d["d_warp_codes"])
@@ -297,7 +301,7 @@ class NeRSembleNGPModel(nn.Module):
         packed_info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)           # nerfacc.pack_info (:325)
         if needs_grad:
             he = self.field.hash_ensemble
-            params = [m.params for m in he.hash_encodings] + [self.field.mlp_base.params, self.field.mlp_head.params,
+            params = [he.tables, self.field.mlp_base.params, self.field.mlp_head.params,
                                                                self.time_embedding.weight]
             if cfg.use_deformation_field:
                 if not cfg.use_separate_deformation_time_embedding:

@@ -52,3 +52,31 @@ def test_gloo_world2_gradient_allreduce():
 def test_gloo_world2_shard_and_gather():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, 101), nprocs=2, join=True)
+
+
+def _pending_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nersemble_b200.distributed import allreduce_gradients
+
+    class FakeEnsemble:      # the protocol allreduce_gradients relies on (plugin/components.py: HashEnsemble)
+        def __init__(self):
+            self.tables = torch.nn.Parameter(torch.zeros(5, 32, 2))
+            self.pending_table_grad = {"g_rank1": torch.full((3, 5, 2), float(rank + 1)), "cw_slots": torch.ones(3, 32),
+                                       "n_slots": 3, "slots_are_timesteps": True}
+    he = FakeEnsemble()
+    w = torch.nn.Parameter(torch.zeros(4))
+    w.grad = torch.full((4,), float(rank))
+    allreduce_gradients([he.tables, w], hash_ensembles=[he])
+    assert torch.equal(he.pending_table_grad["g_rank1"], torch.full((3, 5, 2), 3.0))
+    assert he.pending_table_grad["scale"] == 0.5 and he.tables.grad is None
+    assert torch.equal(w.grad, torch.full((4,), 0.5))
+    dist.destroy_process_group()
+
+
+def test_allreduce_reduces_the_deferred_rank1_table_gradient_in_place():
+    """world_size 2, gloo: the parked [slots][entries][2] workspace is summed across ranks, the 1/world factor is left
+    to the fused optimiser step, and no dense table gradient is created."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_pending_worker, args=(2, port), nprocs=2, join=True)

@@ -56,10 +56,15 @@ def test_composite_backward_vs_autograd():
     assert _relerr(d_sigma.cpu(), sigma.grad) < 2e-4
 
 
-@pytest.mark.parametrize("rank1", [True, False])
+@pytest.mark.parametrize("rank1", [True, False, "saved_corners", "deferred"])
 def test_field_backward_vs_autograd(rank1):
     """Gradients of the hash tables, time codes and both tiny MLPs (no deformation field); rank1 = the
-    per-timestep 2-vector scatter + dense expansion, else the direct 64-float-per-line scatter."""
+    per-timestep 2-vector scatter + dense expansion, else the direct 64-float-per-line scatter;
+    "saved_corners" = rank-1 scatter from the corner values the training forward saved (no table re-gather, merged
+    atomics); "deferred" = additionally the table gradient stays in rank-1 form and is expanded by nsb_rank1_expand."""
+    cv = rank1 in ("saved_corners", "deferred")
+    deferred = rank1 == "deferred"
+    rank1 = bool(rank1)
     from nersemble_b200 import ops
     P = pl.random_params(**TRAINED)
     NP = native_from_oracle(P, DEV)
@@ -80,9 +85,14 @@ def test_field_backward_vs_autograd(rank1):
     ((sigma[:, 0] * g_sigma).sum() + (rgb * g_rgb).sum()).backward()
 
     kw = dict(positions=pos.detach().to(DEV), sample_times=times.to(DEV), sample_directions=dirs.to(DEV))
-    saved = ops.field_forward(NP, window_hash=w_hash, use_deformation=False, want=("sigma", "rgb", "feat", "xs"), **kw)
+    saved = ops.field_forward(NP, window_hash=w_hash, use_deformation=False,
+                              want=("sigma", "rgb", "feat", "xs") + (("corner_vals",) if cv else ()), **kw)
     torch.testing.assert_close(saved["sigma"].cpu(), sigma[:, 0].detach(), rtol=5e-3, atol=1e-5)
-    grads = ops.field_backward(NP, saved, g_sigma.to(DEV), g_rgb.to(DEV), window_hash=w_hash, loss_scale=128.0, want_dx=True, rank1=rank1, **kw)
+    grads = ops.field_backward(NP, saved, g_sigma.to(DEV), g_rgb.to(DEV), window_hash=w_hash, loss_scale=128.0, want_dx=True,
+                               rank1=rank1, defer_tables=deferred, **kw)
+    if deferred:
+        assert "d_tables" not in grads
+        grads["d_tables"] = ops.rank1_expand(grads["pending"], P.tables.shape[0])
     # dL/d(world position) = dL/d(normalised) / aabb size   (tcnn kernel_grid_backward_input)
     dpos = grads["d_xs"].cpu() / (hi - lo)
     assert _relerr(dpos, pos.grad) < 3e-2

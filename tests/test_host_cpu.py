@@ -96,7 +96,7 @@ def test_blend_fold_matches_reference_semantics():
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "nsb.h")).read()
-    declared = set(re.findall(r"\b(nsb_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(nsb_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     if not os.path.exists(_lib.LIB_PATH):
         import __graft_entry__ as ge
@@ -130,3 +130,24 @@ def test_time_bias_packing_is_the_same_linear_map():
             full = h(x) @ h(W[:, :173]).t() + b
             split = h(enc) @ h(W[:, :45]).t() + cb[t, 0 if l == 0 else 1]
             torch.testing.assert_close(split, full, rtol=1e-5, atol=1e-6)
+
+
+def test_gather_plans_reproduce_the_packers():
+    """Training re-packs the MLP weights every step through cached gather plans (packing.gather_plan); they must give
+    exactly what the defining packers give."""
+    from nersemble_b200 import packing as pk
+    g = torch.Generator().manual_seed(0)
+    stem = [torch.randn(s, generator=g) for s in pk._STEM_SHAPES]
+    sb = [torch.randn(128, generator=g) for _ in range(6)]
+    r_w, v_w, r_b, v_b = torch.randn(3, 128, generator=g), torch.randn(3, 128, generator=g), torch.randn(3, generator=g), torch.randn(3, generator=g)
+    codes = torch.randn(4, 128, generator=g)
+    for _ in range(2):      # second pass uses the cached plans
+        a, b, c = pk.pack_deform_weights_fast(stem, r_w, v_w)
+        assert torch.equal(a, pk.pack_deform(stem, sb, r_w, r_b, v_w, v_b)[0])
+        assert torch.equal(b, pk.pack_deform_tb(stem, sb, r_w, r_b, v_w, v_b, codes)[0])
+        assert torch.equal(c, pk.pack_deform_bwd(stem, r_w, v_w))
+        bw = [torch.randn(64, 32, generator=g), torch.randn(16, 64, generator=g)]
+        hw = [torch.randn(64, 32, generator=g), torch.randn(64, 64, generator=g), torch.randn(16, 64, generator=g)]
+        f, fb = pk.pack_field_fast(bw, hw)
+        assert torch.equal(f, pk.pack_field(bw, hw)) and torch.equal(fb, pk.pack_field_bwd(bw, hw))
+    assert torch.equal(pk.deform_bias_vector(sb, r_b, v_b), pk.pack_deform(stem, sb, r_w, r_b, v_w, v_b)[1])

@@ -36,7 +36,29 @@ def test_state_dict_and_param_groups_match_reference():
     m = make_model()
     sd = {k: list(v.shape) for k, v in m.state_dict().items()}
     assert sd == ref["state_dict"], (set(sd) ^ set(ref["state_dict"]))
-    assert {k: len(v) for k, v in m.get_param_groups().items()} == ref["param_groups"]
+    # same groups; `fields` holds ONE native-layout table tensor instead of the reference's 8 tcnn grids
+    got = {k: len(v) for k, v in m.get_param_groups().items()}
+    want = dict(ref["param_groups"]); want["fields"] -= 7
+    assert got == want
+
+
+def test_state_dict_round_trip_through_reference_keys():
+    """Checkpoints keep the reference's keys and flat tcnn shapes; loading one restores the native table bit for bit."""
+    m = make_model()
+    he = m.field.hash_ensemble
+    with torch.no_grad():
+        he.tables.uniform_(-1, 1)
+    sd = m.state_dict()
+    assert "field.hash_ensemble.tables" not in sd
+    g3 = sd["field.hash_ensemble.hash_encodings.3.params"]
+    E = he.levels["total_entries"]
+    assert g3.shape == (E * 8,)
+    # grid c, entry e, slot p, feat f  <->  tables[e, 4c + p, f]   (hash_ensemble.py:100-116 rearrange)
+    assert torch.equal(g3.view(E, 4, 2), he.tables.detach()[:, 12:16, :])
+    m2 = make_model()
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.field.hash_ensemble.tables, he.tables)
+    assert torch.equal(he.hash_encodings[3].params, g3)
 
 
 def test_scheduler_semantics():

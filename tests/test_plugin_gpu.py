@@ -15,8 +15,7 @@ DEV = "cuda:0"
 def load_oracle_params_into(model, P):
     from nersemble_b200 import packing
     with torch.no_grad():
-        for c, g in enumerate(packing.tables_to_tcnn(P.tables)):
-            model.field.hash_ensemble.hash_encodings[c].params.copy_(g)
+        model.field.hash_ensemble.load_tcnn_grids(packing.tables_to_tcnn(P.tables))
         model.field.mlp_base.params.copy_(torch.cat([w.reshape(-1) for w in P.base_w]))
         model.field.mlp_head.params.copy_(torch.cat([w.reshape(-1) for w in P.head_w]))
         se3 = model.deformation_field.se3_field
@@ -148,8 +147,7 @@ def test_training_step_gradients_and_descent():
                    lambda_near_loss=0, lambda_empty_loss=0, lambda_depth_loss=0, lambda_dist_loss=1e-2, lambda_alpha_loss=1e-2)
     with torch.no_grad():
         from nersemble_b200 import packing
-        for c, gtab in enumerate(packing.tables_to_tcnn(P.tables)):
-            m.field.hash_ensemble.hash_encodings[c].params.copy_(gtab)
+        m.field.hash_ensemble.load_tcnn_grids(packing.tables_to_tcnn(P.tables))
         m.field.mlp_base.params.copy_(torch.cat([w.reshape(-1) for w in P.base_w]))
         m.field.mlp_head.params.copy_(torch.cat([w.reshape(-1) for w in P.head_w]))
         m.time_embedding.weight.copy_(P.time_emb)
@@ -192,7 +190,7 @@ def test_training_step_gradients_and_descent():
     assert rel(m.field.mlp_head.params.grad.cpu(), torch.cat([x.grad.reshape(-1) for x in P.head_w])) < 3e-2
     assert rel(m.field.mlp_base.params.grad.cpu(), torch.cat([x.grad.reshape(-1) for x in P.base_w])) < 3e-2
     assert rel(m.time_embedding.weight.grad.cpu(), P.time_emb.grad) < 3e-2
-    got_t = packing.tables_from_tcnn([mm.params.grad.cpu() for mm in m.field.hash_ensemble.hash_encodings])
+    got_t = m.field.hash_ensemble.tables.grad.cpu()
     cos = torch.nn.functional.cosine_similarity(got_t.reshape(1, -1), P.tables.grad.reshape(1, -1)).item()
     assert cos > 0.999, cos
     # ---- a few optimiser steps on the same batch reduce the loss
@@ -257,7 +255,7 @@ def test_full_recipe_training_step_gradients():
     assert rel(m.time_embedding_deformation.weight.grad.cpu(), P.time_emb_deform.grad) < 6e-2
     assert rel(m.time_embedding.weight.grad.cpu(), P.time_emb.grad) < 4e-2
     assert rel(m.field.mlp_head.params.grad.cpu(), torch.cat([x.grad.reshape(-1) for x in P.head_w])) < 4e-2
-    got_t = packing.tables_from_tcnn([mm.params.grad.cpu() for mm in m.field.hash_ensemble.hash_encodings])
+    got_t = m.field.hash_ensemble.tables.grad.cpu()
     assert torch.nn.functional.cosine_similarity(got_t.reshape(1, -1), P.tables.grad.reshape(1, -1)).item() > 0.999
     # ---- optimiser steps over the reference's three parameter groups (train_nersemble.py:243-256)
     groups = m.get_param_groups()

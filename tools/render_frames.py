@@ -25,8 +25,7 @@ torch.manual_seed(0)                                  # identical replicas on ev
 T = 24
 m = make_model(T=T, log2T=args.log2T, eval_num_rays_per_chunk=1 << 15).to(dev).eval()
 with torch.no_grad():
-    for g in m.field.hash_ensemble.hash_encodings:
-        g.params.uniform_(-0.5, 0.5)
+    m.field.hash_ensemble.tables.uniform_(-0.5, 0.5)
     m.time_embedding.weight.normal_(0, 0.18); m.time_embedding_deformation.weight.normal_(0, 0.09)
     ax = (torch.arange(128, device=dev).float() + 0.5) / 128
     X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")

@@ -12,7 +12,7 @@ from test_plugin_cpu import make_model
 from nersemble_b200.nerfstudio_shim import RayBundle
 from nersemble_b200.distributed import allreduce_gradients
 
-ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true"); args = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true"); ap.add_argument("--torch-adam", action="store_true", help="dense table gradient + torch.optim.Adam (the reference's optimiser path) instead of FusedFieldsAdam"); args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr_ = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr_); dev = torch.device("cuda", lr_)
 if world > 1:
@@ -20,8 +20,7 @@ if world > 1:
 torch.manual_seed(0)
 m = make_model(T=24, log2T=19, lambda_near_loss=0, lambda_empty_loss=0, lambda_depth_loss=0).to(dev).train()
 with torch.no_grad():   # trained-like scale so that densities are non-trivial
-    for g in m.field.hash_ensemble.hash_encodings:
-        g.params.uniform_(-0.5, 0.5)
+    m.field.hash_ensemble.tables.uniform_(-0.5, 0.5)
     m.time_embedding.weight.normal_(0, 0.18); m.time_embedding_deformation.weight.normal_(0, 0.09)
 m.occupancy_grid.binaries[:] = True           # dense march (config 5: --disable_occupancy_grid-like sample count)
 m.config.far_plane = 1e3
@@ -30,8 +29,16 @@ rb = RayBundle(origins=o, directions=d, pixel_area=torch.ones(4096, 1, device=de
                camera_indices=torch.zeros(4096, 1, dtype=torch.long, device=dev), times=t)
 batch = {"image": torch.rand(4096, 3, device=dev), "alpha_map": torch.randint(0, 256, (4096, 1), device=dev).float()}
 groups = m.get_param_groups()
-opt = torch.optim.Adam([{"params": groups["fields"], "lr": 5e-3}, {"params": groups["embeddings"], "lr": 5e-3},
-                        {"params": [p for p in groups["deformation_field"] if p.requires_grad], "lr": 1e-3}], eps=1e-15)
+from nersemble_b200.optim import FusedFieldsAdam
+class _Opts:    # one optimiser per group, like nerfstudio's Optimizers
+    def __init__(self):
+        F = torch.optim.Adam if args.torch_adam else FusedFieldsAdam
+        self.o = [F(groups["fields"], lr=5e-3, eps=1e-15), torch.optim.Adam(groups["embeddings"], lr=5e-3, eps=1e-15),
+                  torch.optim.Adam([p for p in groups["deformation_field"] if p.requires_grad], lr=1e-3, eps=1e-15)]
+    def zero_grad(self, set_to_none=True): [o.zero_grad(set_to_none) for o in self.o]
+    def step(self): [o.step() for o in self.o]
+opt = _Opts()
+HE = [m.field.hash_ensemble]
 m.sampler.eval()
 def ev(): e = torch.cuda.Event(enable_timing=True); e.record(); return e
 rows = []
@@ -40,7 +47,7 @@ for step in range(args.steps + 2):
     out = m.get_outputs(rb); e1 = ev()
     loss = sum(m.get_loss_dict(out, batch).values()); e2 = ev()
     loss.backward(); e3 = ev()
-    allreduce_gradients([p for gr in groups.values() for p in gr]); e4 = ev()
+    allreduce_gradients([p for gr in groups.values() for p in gr], hash_ensembles=HE); e4 = ev()
     opt.step(); e5 = ev()
     torch.cuda.synchronize()
     if step >= 2:
@@ -58,7 +65,7 @@ if args.profile and rank == 0:
 avg = [sum(r[i] for r in rows) / len(rows) for i in range(5)]
 n_samples = int(out["num_samples_per_ray"].sum().item())
 if rank == 0:
-    print(json.dumps({"n_gpus": world, "samples_per_gpu": n_samples, "loss": loss.item(),
+    print(json.dumps({"optimizer": "torch.optim.Adam" if args.torch_adam else "FusedFieldsAdam", "n_gpus": world, "samples_per_gpu": n_samples, "loss": loss.item(),
                       "ms": dict(forward=avg[0], losses=avg[1], backward=avg[2], allreduce=avg[3], adam=avg[4], total=sum(avg)),
                       "it_per_s": 1000.0 / sum(avg), "M_samples_per_s": n_samples * world / sum(avg) / 1e3}))
 if world > 1:
