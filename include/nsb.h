@@ -217,8 +217,11 @@ typedef struct nsb_deform_bwd_args {
     float *d_r_w, *d_r_b;         /* [3][128], [3] */
     float *d_v_w, *d_v_b;         /* [3][128], [3] */
     float *d_warp_codes;          /* [n_timesteps][128] or NULL */
+    void *dw_workspace;           /* nsb_deform_bwd_workspace_bytes() of scratch (need not be zeroed): per-CTA private
+                                     weight-gradient accumulators, summed into d_stem_w at the end of the call */
 } nsb_deform_bwd_args;
 size_t nsb_deform_packed_t_bytes(void);
+size_t nsb_deform_bwd_workspace_bytes(void);
 int nsb_deform_backward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                         const nsb_deform_bwd_args *args, void *stream);
 

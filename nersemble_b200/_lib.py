@@ -77,7 +77,7 @@ class DeformBwdArgs(C.Structure):
     _fields_ = [("deform_packed_t", C.c_void_p), ("deform_acts", C.c_void_p), ("deform_enc", C.c_void_p),
                 ("d_xs", C.c_void_p), ("loss_scale", C.c_float), ("d_stem_w", C.c_void_p * 6), ("d_stem_b", C.c_void_p),
                 ("d_r_w", C.c_void_p), ("d_r_b", C.c_void_p), ("d_v_w", C.c_void_p), ("d_v_b", C.c_void_p),
-                ("d_warp_codes", C.c_void_p)]
+                ("d_warp_codes", C.c_void_p), ("dw_workspace", C.c_void_p)]
 
 
 class CompositeBwdArgs(C.Structure):
@@ -107,6 +107,7 @@ SYMBOLS = {
     "nsb_field_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
                                      C.POINTER(FieldBwdArgs), C.c_void_p]),
     "nsb_deform_packed_t_bytes": (C.c_size_t, []),
+    "nsb_deform_bwd_workspace_bytes": (C.c_size_t, []),
     "nsb_deform_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
                                       C.POINTER(DeformBwdArgs), C.c_void_p]),
     "nsb_table_adam_step": (C.c_int, [C.POINTER(TableAdamArgs), C.c_void_p]),

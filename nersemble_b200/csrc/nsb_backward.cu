@@ -33,10 +33,24 @@ struct FieldBwdKArgs {
 constexpr int kBaseW = 64 * 32 + 16 * 64;             // 3072
 constexpr int kHeadW = 64 * 32 + 64 * 64 + 16 * 64;   // 7168
 
+// Weight gradients dW_l = delta_l^T . x_l are reduced over ALL 128 rows of the tile on the tensor cores: every warp
+// stages its delta / input fragments (A-fragment order) in shared memory, then each warp owns 5 of the 40 16x16 output
+// blocks, contracts over the 8 row blocks (movmatrix transposes, K = 128) and adds the result to its private slots of
+// the per-CTA accumulator, which is kept in FRAGMENT order (conflict-free float4 per lane, no atomics).
+// (First version: every warp formed the K = 16 product of its own rows and atomicAdd'ed it to a shared [out][in]
+//  array: fp32 shared atomics are CAS loops -- ATOMS.CAST.SPIN, 8-way bank conflicts, 80 % of the kernel's samples.)
+constexpr int kStD = 14, kStX = 16, kDwBlocks = 40;
+struct DwBlock { uint8_t d, x, ob, ib, it; uint16_t base; };   // staged delta / input index, block coords, IT, flat offset
+__constant__ DwBlock kDwBlk[kDwBlocks];
+
 struct alignas(16) SmemBwd {
     uint4 wf[kFieldPackedU4];   // forward fragments
     uint4 wb[kFieldPackedU4];   // transposed fragments (dX GEMMs)
-    float dw[kBaseW + kHeadW];  // per-CTA weight-gradient accumulator, tcnn flat layout [out][in(kernel col order)]
+    float4 acc[kDwBlocks][2][32];   // per-CTA weight-gradient accumulator, fragment order [block][n-half][lane]
+    union {
+        struct { uint4 D[8][kStD][32]; uint4 X[8][kStX][32]; } st;   // per-tile staging
+        float dw[kBaseW + kHeadW];                                      // flush: flat [out][in(kernel col order)]
+    } u;
 };
 
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
@@ -68,34 +82,14 @@ __device__ __forceinline__ void mask_pack(const float (&acc)[NT][4], uint32_t ma
     }
 }
 
-// dW[o][i] += sum_rows delta[row][o] * x[row][i]   (O = 16*OT outputs, I = 16*IT inputs, 16 rows of this warp)
+// park this warp's delta (OT k-tiles of 16 outputs) and layer-input (IT k-tiles) fragments for the tile-wide dW pass
 template <int OT, int IT>
-__device__ __forceinline__ void dw_accumulate(const uint32_t (&dA)[OT][4], const uint32_t (&xA)[IT][4], float *dw, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-    uint32_t xb[IT][4];
+__device__ __forceinline__ void stage_dw(SmemBwd &sm, int warp, int d0, int x0, const uint32_t (&dA)[OT][4],
+                                         const uint32_t (&xA)[IT][4], int lane) {
 #pragma unroll
-    for (int ib = 0; ib < IT; ++ib)
+    for (int ob = 0; ob < OT; ++ob) sm.u.st.D[warp][d0 + ob][lane] = make_uint4(dA[ob][0], dA[ob][1], dA[ob][2], dA[ob][3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xb[ib][k] = movmatrix_trans(xA[ib][k]);
-#pragma unroll
-    for (int ob = 0; ob < OT; ++ob) {
-        // A = delta^T block [o 16][rows 16]: blocks (o-lo,r-lo)=T(d0) (o-hi,r-lo)=T(d2) (o-lo,r-hi)=T(d1) (o-hi,r-hi)=T(d3)
-        const uint32_t a[4] = {movmatrix_trans(dA[ob][0]), movmatrix_trans(dA[ob][2]), movmatrix_trans(dA[ob][1]),
-                               movmatrix_trans(dA[ob][3])};
-#pragma unroll
-        for (int ib = 0; ib < IT; ++ib) {
-#pragma unroll
-            for (int hn = 0; hn < 2; ++hn) {   // n-tile i = ib*16 + hn*8 .. +7: B = (T(x[2hn]) rows 0-7, T(x[2hn+1]) rows 8-15)
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
-                mma16816(c, a, xb[ib][2 * hn], xb[ib][2 * hn + 1]);
-                const int o = ob * 16 + g, i = ib * 16 + hn * 8 + 2 * q;
-                atomicAdd(&dw[o * (16 * IT) + i], c[0]);
-                atomicAdd(&dw[o * (16 * IT) + i + 1], c[1]);
-                atomicAdd(&dw[(o + 8) * (16 * IT) + i], c[2]);
-                atomicAdd(&dw[(o + 8) * (16 * IT) + i + 1], c[3]);
-            }
-        }
-    }
+    for (int ib = 0; ib < IT; ++ib) sm.u.st.X[warp][x0 + ib][lane] = make_uint4(xA[ib][0], xA[ib][1], xA[ib][2], xA[ib][3]);
 }
 
 __global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_constant__ FieldBwdKArgs K) {
@@ -109,17 +103,15 @@ __global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_cons
         const uint4 *f = reinterpret_cast<const uint4 *>(K.P.field_packed);
         const uint4 *b = reinterpret_cast<const uint4 *>(K.B.field_packed_t);
         for (int i = tid; i < kFieldPackedU4; i += 256) { sm.wf[i] = __ldg(f + i); sm.wb[i] = __ldg(b + i); }
-        for (int i = tid; i < kBaseW + kHeadW; i += 256) sm.dw[i] = 0.f;
+        for (int i = tid; i < kDwBlocks * 2 * 32; i += 256) (&sm.acc[0][0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     const float ls = K.B.loss_scale, inv_ls = 1.0f / K.B.loss_scale;
     const __half *featp = reinterpret_cast<const __half *>(K.B.feat);
     // weight-gradient slices inside sm.dw (kernel column order, flat [out][in])
-    float *dw_b0 = sm.dw, *dw_b1 = sm.dw + 2048, *dw_h0 = sm.dw + kBaseW, *dw_h1 = dw_h0 + 2048, *dw_h2 = dw_h1 + 4096;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * NSB_TILE + warp * 16;
-        if (row0 >= n) continue;
+        const int64_t row0 = tile * NSB_TILE + warp * 16;   // (a warp whose rows are all >= n runs with zero deltas: barriers below)
         const int64_t ra = row0 + g, rb = row0 + g + 8;
         const bool va = ra < n, vb = rb < n;
         const int64_t sa = va ? ra : n - 1, sb = vb ? rb : n - 1;
@@ -192,14 +184,14 @@ __global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_cons
         }
         uint32_t dA1[1][4];
         mask_pack<2>(dout, 0xffu, dA1);
-        dw_accumulate<1, 4>(dA1, c2in, dw_h2, lane);
+        stage_dw<1, 4>(sm, warp, 0, 0, dA1, c2in, lane);
         smem_gemm<1, 4>(acc8, dA1, sm.wb + 1152, lane);          // d c2in  [16 x 64]
         uint32_t dA4[4][4];
         mask_pack<8>(acc8, m_c1, dA4);
-        dw_accumulate<4, 4>(dA4, c1in, dw_h1, lane);
+        stage_dw<4, 4>(sm, warp, 1, 4, dA4, c1in, lane);
         smem_gemm<4, 4>(acc8, dA4, sm.wb + 640, lane);           // d c1in  [16 x 64]
         mask_pack<8>(acc8, m_c0, dA4);
-        dw_accumulate<4, 2>(dA4, ha, dw_h0, lane);
+        stage_dw<4, 2>(sm, warp, 5, 8, dA4, ha, lane);
         float dh[4][4];
         smem_gemm<4, 2>(dh, dA4, sm.wb + 384, lane);             // d head input [16 x 32]; cols 1..15 = geo features
         // delta of the density-MLP output: col 0 = d sigma * exp(clamp(h0,-15,15)) * selector (trunc_exp backward)
@@ -213,10 +205,10 @@ __global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_cons
             dhb[0][2] = ls * dsb * expf(fminf(fmaxf(b1acc[0][2], -15.f), 15.f)) * selb;
         }
         mask_pack<2>(dhb, 0xffu, dA1);
-        dw_accumulate<1, 4>(dA1, h1, dw_b1, lane);
+        stage_dw<1, 4>(sm, warp, 9, 10, dA1, h1, lane);
         smem_gemm<1, 4>(acc8, dA1, sm.wb + 256, lane);           // d h1 [16 x 64]
         mask_pack<8>(acc8, m_b0, dA4);
-        dw_accumulate<4, 2>(dA4, fa, dw_b0, lane);
+        stage_dw<4, 2>(sm, warp, 10, 14, dA4, fa, lane);
         float dfe[4][4];
         smem_gemm<4, 2>(dfe, dA4, sm.wb, lane);                  // d feat [16 x 32]
         if (K.B.d_feat) {
@@ -226,12 +218,43 @@ __global__ void __launch_bounds__(256, 1) field_mlp_bwd_kernel(const __grid_cons
                 if (vb) *reinterpret_cast<float2 *>(K.B.d_feat + rb * 32 + nt * 8 + 2 * q) = make_float2(dfe[nt][2] * inv_ls, dfe[nt][3] * inv_ls);
             }
         }
+        // ---------------- weight gradients: tile-wide contraction, 5 output blocks per warp ----------------
+        __syncthreads();
+#pragma unroll 1
+        for (int bi = 0; bi < kDwBlocks / 8; ++bi) {
+            const int blk = warp * (kDwBlocks / 8) + bi;
+            const int di = kDwBlk[blk].d, xi = kDwBlk[blk].x;
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int r = 0; r < 8; ++r) {
+                const uint4 d = sm.u.st.D[r][di][lane];
+                const uint4 x = sm.u.st.X[r][xi][lane];
+                // A = delta^T block [o 16][rows 16]: (o-lo,r-lo)=T(d0) (o-hi,r-lo)=T(d2) (o-lo,r-hi)=T(d1) (o-hi,r-hi)=T(d3)
+                const uint32_t a[4] = {movmatrix_trans(d.x), movmatrix_trans(d.z), movmatrix_trans(d.y), movmatrix_trans(d.w)};
+                mma16816(c0, a, movmatrix_trans(x.x), movmatrix_trans(x.y));   // input columns ib*16 + 0..7
+                mma16816(c1, a, movmatrix_trans(x.z), movmatrix_trans(x.w));   // input columns ib*16 + 8..15
+            }
+            float4 v0 = sm.acc[blk][0][lane], v1 = sm.acc[blk][1][lane];
+            v0.x += c0[0]; v0.y += c0[1]; v0.z += c0[2]; v0.w += c0[3];
+            v1.x += c1[0]; v1.y += c1[1]; v1.z += c1[2]; v1.w += c1[3];
+            sm.acc[blk][0][lane] = v0; sm.acc[blk][1][lane] = v1;
+        }
+        __syncthreads();   // staging is rewritten by the next tile
+    }
+    // fragment order -> flat [out][in(kernel col order)] (aliases the staging area)
+    for (int i = tid; i < kDwBlocks * 2 * 32; i += 256) {
+        const int l = i & 31, hn = (i >> 5) & 1, blk = i >> 6;
+        const DwBlock b = kDwBlk[blk];
+        const float4 v = sm.acc[blk][hn][l];
+        const int o = b.ob * 16 + (l >> 2), c = b.ib * 16 + hn * 8 + 2 * (l & 3), ld = 16 * b.it;
+        float *dst = sm.u.dw + b.base;
+        dst[o * ld + c] = v.x; dst[o * ld + c + 1] = v.y; dst[(o + 8) * ld + c] = v.z; dst[(o + 8) * ld + c + 1] = v.w;
     }
     __syncthreads();
     // flush: kernel column order -> tcnn flat layout.  Only head layer 0 has permuted input columns:
     // kernel col k' -> reference col: 0 -> 18, 1..15 -> k'+2, 16..18 -> k'-16, 19..31 -> k'
     for (int i = tid; i < kBaseW + kHeadW; i += 256) {
-        const float v = sm.dw[i] * inv_ls;
+        const float v = sm.u.dw[i] * inv_ls;
         if (v == 0.f) continue;
         if (i < kBaseW) {
             if (K.B.d_base_w) atomicAdd(K.B.d_base_w + i, v);
@@ -599,6 +622,29 @@ extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_fiel
     FieldBwdKArgs K;
     K.P = *params; K.O = *opts; K.S = *samples; K.B = *args;
     static bool configured = false;
+    {   // 16x16 output blocks of the five weight matrices, in flat-accumulator order (see SmemBwd)
+        static bool table_done_dev[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        bool &table_done = table_done_dev[dev & 63];
+        if (!table_done) {
+            DwBlock t[kDwBlocks];
+            int n = 0;
+            struct { int d0, x0, OT, IT, base; } L[5] = {
+                {0, 0, 1, 4, kBaseW + 2048 + 4096},   // head layer 2 (16 x 64)
+                {1, 4, 4, 4, kBaseW + 2048},          // head layer 1 (64 x 64)
+                {5, 8, 4, 2, kBaseW},                 // head layer 0 (64 x 32)
+                {9, 10, 1, 4, 2048},                  // base layer 1 (16 x 64)
+                {10, 14, 4, 2, 0}};                   // base layer 0 (64 x 32)
+            for (auto &l : L)
+                for (int ob = 0; ob < l.OT; ++ob)
+                    for (int ib = 0; ib < l.IT; ++ib)
+                        t[n++] = DwBlock{(uint8_t)(l.d0 + ob), (uint8_t)(l.x0 + ib), (uint8_t)ob, (uint8_t)ib, (uint8_t)l.IT, (uint16_t)l.base};
+            cudaError_t e = cudaMemcpyToSymbol(kDwBlk, t, sizeof(t));
+            if (e != cudaSuccess || n != kDwBlocks) { set_error("field_mlp_bwd: block table upload failed: %s", cudaGetErrorString(e)); return 1; }
+            table_done = true;
+        }
+    }
     const size_t smem = sizeof(SmemBwd);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(field_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

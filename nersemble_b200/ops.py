@@ -26,6 +26,19 @@ def _need_cuda(*tensors):
             raise RuntimeError("nersemble_b200 ops need CUDA tensors (there is no CPU fallback)")
 
 
+_WORKSPACES: dict = {}
+
+
+def _workspace(name: str, nbytes: int, dev) -> torch.Tensor:
+    """Reusable scratch buffers (contents undefined between calls; ops on one stream are ordered)."""
+    key = (name, str(dev))
+    t = _WORKSPACES.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = t
+    return t
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -366,6 +379,8 @@ def deform_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_xs: torch
         a.d_stem_w[l] = _ptr(out["d_stem_w"][l])
     a.d_stem_b, a.d_r_w, a.d_r_b = _ptr(out["d_stem_b"]), _ptr(out["d_r_w"]), _ptr(out["d_r_b"])
     a.d_v_w, a.d_v_b, a.d_warp_codes = _ptr(out["d_v_w"]), _ptr(out["d_v_b"]), _ptr(out["d_warp_codes"])
+    ws = _workspace("deform_bwd", int(lib.nsb_deform_bwd_workspace_bytes()), dev)
+    a.dw_workspace = _ptr(ws)
     if n == 0:
         return out
     opts = make_opts(None, window_deform, True, False)
