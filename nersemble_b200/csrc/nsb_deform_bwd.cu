@@ -41,13 +41,29 @@ struct alignas(128) SmemDB {
     float bias_heads[8];
     int ts[NSB_TILE];
     uint4 D[8][8][32];            // delta fragments of every warp (A-fragment order, 8 k-tiles of 16 outputs)
-    uint4 X[8][19][32];           // layer-input fragments of every warp: [hidden 8 | enc 3 | code 8]
+    uint4 X[8][19][32];           // layer-input fragments of every warp, TRANSPOSED (movmatrix): [hidden 8 | enc 3 | code 8]
+    float bias_acc[6][128];       // per-CTA bias-gradient accumulator (x loss scale), flushed once at the end
 };
 
 __device__ __forceinline__ uint32_t movt(uint32_t a) {
     uint32_t d;
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
     return d;
+}
+
+__device__ __forceinline__ uint4 movt4(const uint4 v) { return make_uint4(movt(v.x), movt(v.y), movt(v.z), movt(v.w)); }
+
+// bit e of the result: element e (low/high half of x, y, z, w) of the fragment is > 0   (ReLU derivative of a saved activation)
+__device__ __forceinline__ uint32_t pos_bits(const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // activations are post-ReLU fp16 (>= 0, never -0 from fmaxf(x, 0)): "> 0" is "bits != 0"
+        m |= ((w[k] & 0xffffu) != 0u ? 1u : 0u) << (2 * k);
+        m |= ((w[k] >> 16) != 0u ? 1u : 0u) << (2 * k + 1);
+    }
+    return m;
 }
 
 struct TRing {
@@ -171,9 +187,14 @@ constexpr int kSiteL5 = 0, kSiteL4A = 4096, kSiteL4B = 8192, kSiteL3 = 13824, kS
               kSiteL0 = 26112, kScrF4 = 31744;
 
 // dW block: output rows 16*ob.., input k-tiles IB0..IB0+NIB-1 of X, reduced over the 8 row blocks of the tile.
-template <int IB0, int NIB>
-__device__ __forceinline__ void dw_slice(const SmemDB &sm, int ob, float4 *site, bool first, int lane) {
+// sm.X holds the input fragments already TRANSPOSED (each warp transposes its own block once when staging; before,
+// all 8 warps repeated the movmatrix of every block: 262 M MOVM per step, more than the HMMAs).
+// BIAS: the bias gradient (column sums of delta) rides along as one more HMMA per row block against an all-ones B
+// fragment; lane (g, q == 0) owns outputs 16*ob + g and + 8 of bias_acc (no shuffles, no atomics).
+template <int IB0, int NIB, bool BIAS>
+__device__ __forceinline__ void dw_slice(SmemDB &sm, int ob, float4 *site, bool first, float *bias_acc, int lane) {
     float acc[NIB][2][4];
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < NIB; ++i)
 #pragma unroll
@@ -184,13 +205,17 @@ __device__ __forceinline__ void dw_slice(const SmemDB &sm, int ob, float4 *site,
     for (int rb = 0; rb < 8; ++rb) {
         const uint4 d = sm.D[rb][ob][lane];
         const uint32_t a[4] = {movt(d.x), movt(d.z), movt(d.y), movt(d.w)};   // delta^T block (see nsb_backward.cu)
+        if (BIAS) mma16816(bsum, a, 0x3c003c00u, 0x3c003c00u);                // x ones: every column = sum over the 16 rows
 #pragma unroll
         for (int i = 0; i < NIB; ++i) {
             const uint4 x = sm.X[rb][IB0 + i][lane];
-            const uint32_t b0 = movt(x.x), b1 = movt(x.y), b2 = movt(x.z), b3 = movt(x.w);
-            mma16816(acc[i][0], a, b0, b1);
-            mma16816(acc[i][1], a, b2, b3);
+            mma16816(acc[i][0], a, x.x, x.y);
+            mma16816(acc[i][1], a, x.z, x.w);
         }
+    }
+    if (BIAS && (lane & 3) == 0) {
+        bias_acc[ob * 16 + (lane >> 2)] += bsum[0];
+        bias_acc[ob * 16 + (lane >> 2) + 8] += bsum[2];
     }
     float4 *dst = site + (size_t)ob * NIB * 64 + lane;
     if (first) {
@@ -267,6 +292,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         const uint4 *hw = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(K.P.deform_packed_tb) + 92 * 2048);
         for (int i = tid; i < 256; i += 256) sm.heads_w[i] = __ldg(hw + i);
         if (tid < 8) sm.bias_heads[tid] = K.P.deform_bias[6 * 128 + tid];
+        for (int i = tid; i < 6 * 128; i += 256) (&sm.bias_acc[0][0])[i] = 0.f;
         if (tid == 0) {
             for (int s = 0; s < kDStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 8); }
             mbar_fence_init();
@@ -385,8 +411,13 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         uint32_t dAh[4] = {pack_h2(dh[0][0], dh[0][1]), pack_h2(dh[0][2], dh[0][3]), 0u, 0u};
         // ---- dW heads: stage delta (k-tile 0) and a5, every warp takes one 16-column block of the 128 inputs ----
         sm.D[warp][0][lane] = make_uint4(dAh[0], dAh[1], dAh[2], dAh[3]);
+        uint32_t relu_lo = 0, relu_hi = 0;     // ReLU-derivative bits of the staged activation: k-tiles 0-3 / 4-7, 8 bits each
 #pragma unroll
-        for (int kt = 0; kt < 8; ++kt) sm.X[warp][kt][lane] = __ldg(act_w + 5 * 256 + kt * 32 + lane);
+        for (int kt = 0; kt < 8; ++kt) {
+            const uint4 v = __ldg(act_w + 5 * 256 + kt * 32 + lane);
+            if (kt < 4) relu_lo |= pos_bits(v) << (8 * kt); else relu_hi |= pos_bits(v) << (8 * (kt - 4));
+            sm.X[warp][kt][lane] = movt4(v);
+        }
         __syncthreads();
         {
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -395,8 +426,8 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                 const uint4 d = sm.D[rb][0][lane];
                 const uint32_t a[4] = {movt(d.x), movt(d.z), movt(d.y), movt(d.w)};
                 const uint4 x = sm.X[rb][warp][lane];
-                mma16816(acc[0], a, movt(x.x), movt(x.y));
-                mma16816(acc[1], a, movt(x.z), movt(x.w));
+                mma16816(acc[0], a, x.x, x.y);
+                mma16816(acc[1], a, x.z, x.w);
             }
             // rows o = g (0..7) of the 16-row head block: 0..2 = mlp_v rows, 3..5 = mlp_r rows (rows 6..15 are padding)
             if (g < 6) {
@@ -421,11 +452,10 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
                     const int kt = half * 4 + nt / 2, rr = (nt & 1) * 2;
-                    const uint4 av = sm.X[warp][kt][lane];
-                    const uint32_t m0 = rr == 0 ? av.x : av.z, m1 = rr == 0 ? av.y : av.w;   // a5 (row g) / (row g+8)
-                    const float2 f0 = unpack_h2(m0), f1 = unpack_h2(m1);
-                    dcur[kt][rr] = pack_h2(f0.x > 0.f ? acc[nt][0] : 0.f, f0.y > 0.f ? acc[nt][1] : 0.f);
-                    dcur[kt][rr + 1] = pack_h2(f1.x > 0.f ? acc[nt][2] : 0.f, f1.y > 0.f ? acc[nt][3] : 0.f);
+                    // fragment register rr (row g) / rr+1 (row g+8) of k-tile kt: bits 2*rr.. of its byte
+                    const uint32_t mb = ((half == 0 ? relu_lo : relu_hi) >> (8 * (nt / 2) + 2 * rr)) & 0xfu;
+                    dcur[kt][rr] = pack_h2(mb & 1u ? acc[nt][0] : 0.f, mb & 2u ? acc[nt][1] : 0.f);
+                    dcur[kt][rr + 1] = pack_h2(mb & 4u ? acc[nt][2] : 0.f, mb & 8u ? acc[nt][3] : 0.f);
                 }
             }
         }
@@ -439,13 +469,18 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
             for (int kt = 0; kt < 8; ++kt) sm.D[warp][kt][lane] = make_uint4(dcur[kt][0], dcur[kt][1], dcur[kt][2], dcur[kt][3]);
             const bool has_hidden = l >= 1, has_in = (l == 4 || l == 0);
             if (has_hidden) {
+                relu_lo = 0; relu_hi = 0;
 #pragma unroll
-                for (int kt = 0; kt < 8; ++kt) sm.X[warp][kt][lane] = __ldg(act_w + (l - 1) * 256 + kt * 32 + lane);
+                for (int kt = 0; kt < 8; ++kt) {
+                    const uint4 v = __ldg(act_w + (l - 1) * 256 + kt * 32 + lane);
+                    if (kt < 4) relu_lo |= pos_bits(v) << (8 * kt); else relu_hi |= pos_bits(v) << (8 * (kt - 4));
+                    sm.X[warp][kt][lane] = movt4(v);
+                }
             }
             if (has_in) {
                 const int eb = l == 4 ? 8 : 0;   // k-tile offset of [enc | code] inside X
 #pragma unroll
-                for (int kt = 0; kt < 3; ++kt) sm.X[warp][eb + kt][lane] = __ldg(enc_w + kt * 32 + lane);
+                for (int kt = 0; kt < 3; ++kt) sm.X[warp][eb + kt][lane] = movt4(__ldg(enc_w + kt * 32 + lane));
                 const __half *cd0 = reinterpret_cast<const __half *>(K.P.warp_codes) + (size_t)tsr[0] * NSB_WARP_CODE_DIM;
                 const __half *cd1 = reinterpret_cast<const __half *>(K.P.warp_codes) + (size_t)tsr[1] * NSB_WARP_CODE_DIM;
 #pragma unroll
@@ -455,37 +490,19 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                     cv.y = __ldg(reinterpret_cast<const uint32_t *>(cd1 + kc * 16 + 2 * q));
                     cv.z = __ldg(reinterpret_cast<const uint32_t *>(cd0 + kc * 16 + 2 * q + 8));
                     cv.w = __ldg(reinterpret_cast<const uint32_t *>(cd1 + kc * 16 + 2 * q + 8));
-                    sm.X[warp][eb + 3 + kc][lane] = cv;
-                }
-            }
-            // bias gradient: column sums of delta_l over the warp's rows
-#pragma unroll
-            for (int kt = 0; kt < 8; ++kt) {
-                const float2 a0 = unpack_h2(dcur[kt][0]), a1 = unpack_h2(dcur[kt][1]), a2 = unpack_h2(dcur[kt][2]), a3 = unpack_h2(dcur[kt][3]);
-                float s0 = a0.x + a1.x, s1 = a0.y + a1.y, s2 = a2.x + a3.x, s3 = a2.y + a3.y;
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-                }
-                if (g == 0) {
-                    float *bp = K.B.d_stem_b + l * 128 + kt * 16 + 2 * q;
-                    if (s0 != 0.f) atomicAdd(bp, s0 * inv_ls);
-                    if (s1 != 0.f) atomicAdd(bp + 1, s1 * inv_ls);
-                    if (s2 != 0.f) atomicAdd(bp + 8, s2 * inv_ls);
-                    if (s3 != 0.f) atomicAdd(bp + 9, s3 * inv_ls);
+                    sm.X[warp][eb + 3 + kc][lane] = movt4(cv);
                 }
             }
             __syncthreads();
             // weight gradient: warp w computes output rows 16w..16w+15 of dW_l
             if (l == 4) {
-                dw_slice<0, 8>(sm, warp, scr + kSiteL4A, it == 0, lane);
-                dw_slice<8, 11>(sm, warp, scr + kSiteL4B, it == 0, lane);
+                dw_slice<0, 8, true>(sm, warp, scr + kSiteL4A, it == 0, sm.bias_acc[4], lane);
+                dw_slice<8, 11, false>(sm, warp, scr + kSiteL4B, it == 0, nullptr, lane);
             } else if (l == 0) {
-                dw_slice<0, 11>(sm, warp, scr + kSiteL0, it == 0, lane);
+                dw_slice<0, 11, true>(sm, warp, scr + kSiteL0, it == 0, sm.bias_acc[0], lane);
             } else {
                 const int site = l == 5 ? kSiteL5 : (l == 3 ? kSiteL3 : (l == 2 ? kSiteL2 : kSiteL1));
-                dw_slice<0, 8>(sm, warp, scr + site, it == 0, lane);
+                dw_slice<0, 8, true>(sm, warp, scr + site, it == 0, sm.bias_acc[l], lane);
             }
             // delta of the previous layer (own rows) and warp-code gradients, transposed weights from the ring
             // (A fragments come from the staged copy: a runtime k index into the register array would go to local memory)
@@ -504,11 +521,10 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         const int kt = half * 4 + nt / 2, rr = (nt & 1) * 2;
-                        const uint4 av = sm.X[warp][kt][lane];   // a_{l-1} of the own rows: ReLU mask
-                        const uint32_t m0 = rr == 0 ? av.x : av.z, m1 = rr == 0 ? av.y : av.w;
-                        const float2 f0 = unpack_h2(m0), f1 = unpack_h2(m1);
-                        dnext[kt][rr] = pack_h2(f0.x > 0.f ? acc[nt][0] : 0.f, f0.y > 0.f ? acc[nt][1] : 0.f);
-                        dnext[kt][rr + 1] = pack_h2(f1.x > 0.f ? acc[nt][2] : 0.f, f1.y > 0.f ? acc[nt][3] : 0.f);
+                        // ReLU mask of a_{l-1} (own rows) from the bits taken when it was staged
+                        const uint32_t mb = ((half == 0 ? relu_lo : relu_hi) >> (8 * (nt / 2) + 2 * rr)) & 0xfu;
+                        dnext[kt][rr] = pack_h2(mb & 1u ? acc[nt][0] : 0.f, mb & 2u ? acc[nt][1] : 0.f);
+                        dnext[kt][rr + 1] = pack_h2(mb & 4u ? acc[nt][2] : 0.f, mb & 8u ? acc[nt][3] : 0.f);
                     }
                 }
             }
@@ -552,6 +568,11 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                     for (int k = 0; k < 4; ++k) dcur[kt][k] = dnext[kt][k];
             }
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < 6 * 128; i += 256) {
+        const float v = (&sm.bias_acc[0][0])[i];
+        if (v != 0.f) atomicAdd(K.B.d_stem_b + i, v * inv_ls);
     }
 }
 
