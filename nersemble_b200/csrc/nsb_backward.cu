@@ -529,6 +529,16 @@ __global__ void __launch_bounds__(kExpWarps * 32) hash_expand_kernel(const __gri
     const int64_t n_blocks = (E + kExpLines - 1) / kExpLines;
     for (int64_t blk = (int64_t)blockIdx.x * kExpWarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kExpWarps) {
         const int64_t e0 = blk * kExpLines;
+        {   // pull the NEXT block's workspace rows (n_slots x 256 B) and table lines (32 x 128 B) into L2
+            const int64_t nb = blk + (int64_t)gridDim.x * kExpWarps;
+            if (nb < n_blocks) {
+                const int64_t ne = nb * kExpLines;
+                for (int i = lane; i < 2 * n_slots; i += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(K.B.g_rank1 + ((size_t)(i >> 1) * E + ne) * 2 + (i & 1) * 32));
+                if (K.B.d_blend_codes && ne + lane < E)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + (size_t)(ne + lane) * NSB_MEMBERS));
+            }
+        }
         unsigned any_slot = 0;
         bool mine = false;      // line e0 + lane touched in some slot
         for (int s0 = 0; s0 < n_slots; s0 += 8) {      // 8 slot rows in flight (a ballot per load serialises them)

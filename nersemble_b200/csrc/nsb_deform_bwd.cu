@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         float hacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int kt = 0; kt < 8; ++kt) {
-            const uint4 av = __ldg(act_w + 5 * 256 + kt * 32 + lane);
+            const uint4 av = __ldcs(act_w + 5 * 256 + kt * 32 + lane);
             const uint32_t a[4] = {av.x, av.y, av.z, av.w};
             const uint4 b = sm.heads_w[kt * 32 + lane];
             mma16816(hacc[0], a, b.x, b.y);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         uint32_t relu_lo = 0, relu_hi = 0;     // ReLU-derivative bits of the staged activation: k-tiles 0-3 / 4-7, 8 bits each
 #pragma unroll
         for (int kt = 0; kt < 8; ++kt) {
-            const uint4 v = __ldg(act_w + 5 * 256 + kt * 32 + lane);
+            const uint4 v = __ldcs(act_w + 5 * 256 + kt * 32 + lane);
             if (kt < 4) relu_lo |= pos_bits(v) << (8 * kt); else relu_hi |= pos_bits(v) << (8 * (kt - 4));
             sm.X[warp][kt][lane] = movt4(v);
         }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                 relu_lo = 0; relu_hi = 0;
 #pragma unroll
                 for (int kt = 0; kt < 8; ++kt) {
-                    const uint4 v = __ldg(act_w + (l - 1) * 256 + kt * 32 + lane);
+                    const uint4 v = __ldcs(act_w + (l - 1) * 256 + kt * 32 + lane);
                     if (kt < 4) relu_lo |= pos_bits(v) << (8 * kt); else relu_hi |= pos_bits(v) << (8 * (kt - 4));
                     sm.X[warp][kt][lane] = movt4(v);
                 }
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
             if (has_in) {
                 const int eb = l == 4 ? 8 : 0;   // k-tile offset of [enc | code] inside X
 #pragma unroll
-                for (int kt = 0; kt < 3; ++kt) sm.X[warp][eb + kt][lane] = movt4(__ldg(enc_w + kt * 32 + lane));
+                for (int kt = 0; kt < 3; ++kt) sm.X[warp][eb + kt][lane] = movt4(__ldcs(enc_w + kt * 32 + lane));
                 const __half *cd0 = reinterpret_cast<const __half *>(K.P.warp_codes) + (size_t)tsr[0] * NSB_WARP_CODE_DIM;
                 const __half *cd1 = reinterpret_cast<const __half *>(K.P.warp_codes) + (size_t)tsr[1] * NSB_WARP_CODE_DIM;
 #pragma unroll

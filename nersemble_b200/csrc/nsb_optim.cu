@@ -36,6 +36,18 @@ __global__ void __launch_bounds__(kOptWarps * 32) table_step_kernel(const __grid
     const float bc2_sqrt = sqrtf(a.bias_correction2);
     for (int64_t blk = (int64_t)blockIdx.x * kOptWarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kOptWarps) {
         const int64_t e0 = blk * kOptLines;
+        if (ADAM) {   // pull the NEXT block's p / m / v lines (3 x 8 KB) into L2 while this one is processed
+            const int64_t nb = blk + (int64_t)gridDim.x * kOptWarps;
+            if (nb < n_blocks) {
+                const size_t o = (size_t)nb * kOptLines * NSB_MEMBERS * 2 + (size_t)lane * 64;   // lane -> 256 B line-pair
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tables + o + h * 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.exp_avg + o + h * 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.exp_avg_sq + o + h * 32));
+                }
+            }
+        }
         unsigned any_slot = 0;   // bit sl: some line of this block has a non-zero vector in slot sl (warp-uniform)
         for (int s0 = 0; s0 < n_slots; s0 += 8) {      // 8 slot rows in flight (a ballot per load serialises them)
             float2 v[8];

@@ -157,6 +157,7 @@ class NeRSembleNGPModel(nn.Module):
         self.device_indicator_param = nn.Parameter(torch.empty(0))
         self._native = None
         self._native_version = None
+        self.sync_free_losses = True     # get_loss_dict without host syncs on CUDA (see _loss_dict_sync_free)
 
     @property
     def device(self):
@@ -354,6 +355,8 @@ class NeRSembleNGPModel(nn.Module):
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
         """models/nersemble_instant_ngp.py:366-407 -> models/base.py:90-249 (plain torch on per-ray/per-sample outputs)."""
         cfg = self.config
+        if self.sync_free_losses and outputs["rgb"].is_cuda:
+            return self._loss_dict_sync_free(outputs, batch)
         ld: Dict[str, Tensor] = {}
         acc, depth = outputs["accumulation"], outputs["depth"]
         rs: RaySamples = outputs["ray_samples"][0]
@@ -406,6 +409,67 @@ class NeRSembleNGPModel(nn.Module):
                 wm_pre = _segment_exclusive_sum(w * m, rid, n_rays)
                 dist = ((1.0 / 3.0) * (interval * w * w).sum() + 2.0 * (w * (m * w_pre - wm_pre)).sum()) / n_rays
                 ld["dist_loss"] = cfg.lambda_dist_loss * dist
+        return ld
+
+    def _loss_dict_sync_free(self, outputs, batch) -> Dict[str, Tensor]:
+        """Same six losses (models/base.py:90-249) without device->host synchronisation: the reference selects
+        elements with boolean indexing and `if mask.any()` (11 `nonzero` syncs per step in the r1e profile, each draining
+        the launch queue).  Here every masked mean is sum(mask * x) / count on the device.  Differences a caller can
+        see: a term whose mask is empty is PRESENT with value 0 (the reference omits the key); values agree to
+        summation order."""
+        cfg = self.config
+        ld: Dict[str, Tensor] = {}
+        acc, depth = outputs["accumulation"], outputs["depth"]
+        rs: RaySamples = outputs["ray_samples"][0]
+        ri = outputs["ray_indices"][0]
+        w = outputs["weights"][0].squeeze(1)
+        rgb = outputs["rgb"]
+        dev = rgb.device
+        image = batch["image"].to(dev)
+        n_rays = acc.shape[0]
+
+        def masked_mean(x: Tensor, mask: Tensor, per_elem: int = 1) -> Tensor:
+            cnt = mask.sum()
+            # an empty mask gives 0 (x * mask sums to 0); the rgb loss keeps the reference's 0/0 = nan for an empty mask
+            return (x * mask).sum() / (cnt.clamp(min=1) * per_elem)
+
+        alpha_per_ray = batch["alpha_map"].squeeze(1).to(dev) / 255. if "alpha_map" in batch else None
+        if cfg.use_masked_rgb_loss and alpha_per_ray is not None:
+            mask = (alpha_per_ray > cfg.alpha_mask_threshold).to(rgb.dtype)
+            ld["rgb_loss"] = (((image - rgb) ** 2) * mask[:, None]).sum() / (mask.sum() * 3)
+        else:
+            ld["rgb_loss"] = torch.nn.functional.mse_loss(image, rgb)
+        if cfg.lambda_alpha_loss is not None and cfg.lambda_alpha_loss > 0:
+            bg = (alpha_per_ray < 1).to(rgb.dtype)
+            ld["alpha_loss"] = masked_mean((acc.squeeze(1) - alpha_per_ray).abs(), bg) * cfg.lambda_alpha_loss
+        starts = rs.frustums.starts.squeeze(1)
+        ends = rs.frustums.ends.squeeze(1)
+        mid = (starts + ends) * 0.5
+        if (cfg.lambda_empty_loss > 0 or cfg.lambda_near_loss > 0) and self.training:
+            eps = self.sched_eps_depth.value
+            tgt = batch["depth_maps"].to(dev)[ri]
+            if cfg.lambda_empty_loss > 0:
+                vn = ((tgt > 0) & (mid < tgt - eps)).to(w.dtype)
+                ld["empty_loss"] = cfg.lambda_empty_loss * masked_mean(w ** 2, vn)
+            if cfg.lambda_near_loss > 0:
+                near = ((tgt > 0) & (tgt - eps <= mid) & (mid <= tgt + eps)).to(w.dtype)
+                expected = torch.distributions.Normal(0, (eps / 3) ** 2).cdf(mid - tgt)
+                accumulated = _segment_exclusive_sum(w, ri, n_rays) + w
+                ld["near_loss"] = cfg.lambda_near_loss * masked_mean((accumulated - expected) ** 2, near)
+        if cfg.lambda_depth_loss > 0 and self.training:
+            tgt_ray = batch["depth_maps"].to(dev)
+            dm = (tgt_ray > 0).to(rgb.dtype)
+            ld["depth_loss"] = masked_mean((tgt_ray - depth.squeeze()) ** 2, dm) * cfg.lambda_depth_loss
+        if cfg.lambda_dist_loss > 0:
+            sel = (ri < cfg.dist_loss_max_rays).to(w.dtype)
+            ws = w * sel                                           # rays beyond dist_loss_max_rays contribute nothing
+            interval = ends - starts
+            w_pre = _segment_exclusive_sum(ws, ri, n_rays)
+            wm_pre = _segment_exclusive_sum(ws * mid, ri, n_rays)
+            # torch_efficient_distloss divides by ray_id.max() + 1 of the selected samples (ray_indices are sorted)
+            n_sel = (ri * (ri < cfg.dist_loss_max_rays)).max() + 1
+            dist = ((1.0 / 3.0) * (interval * ws * ws).sum() + 2.0 * (ws * (mid * w_pre - wm_pre)).sum()) / n_sel
+            ld["dist_loss"] = cfg.lambda_dist_loss * dist
         return ld
 
     def get_metrics_dict(self, outputs, batch) -> Dict[str, Tensor]:

@@ -115,3 +115,12 @@ def test_loss_dict_matches_reference_glue_golden():
     assert set(ld) == set(want)
     for k in want:
         torch.testing.assert_close(ld[k].float(), want[k].float(), rtol=1e-4, atol=1e-9)
+    # the sync-free formulation used on CUDA (masked sums instead of boolean indexing / .any()) gives the same values
+    sf = m._loss_dict_sync_free(outputs, batch)
+    assert set(sf) == set(want)
+    for k in want:
+        torch.testing.assert_close(sf[k].float(), want[k].float(), rtol=1e-4, atol=1e-9)
+    # ... and a term with an empty mask is present with value 0 instead of missing
+    batch0 = dict(batch); batch0["depth_maps"] = torch.zeros_like(batch["depth_maps"])
+    assert "depth_loss" not in m.get_loss_dict(outputs, batch0)
+    assert float(m._loss_dict_sync_free(outputs, batch0)["depth_loss"]) == 0.0
