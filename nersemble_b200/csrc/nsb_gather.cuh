@@ -2,6 +2,13 @@
 #pragma once
 #include "nsb_common.cuh"
 
+#ifndef NSB_PREFETCH_QUADS
+// Measured r1e (tools/quick_time.py, full / no-deform): 2.38 / 2.10 ms with the quad-ahead L2 prefetch vs 2.27 / 1.92 ms
+// without, zero spills in both builds.  More requests in flight do not help: the kernel sits at the memory system's
+// REQUEST throughput for this access pattern (38 G L2 requests/s + 26 G DRAM lines/s; tools/randgather.cu tops out at
+// 45 G random lines/s), and every prefetched line is requested twice.
+#define NSB_PREFETCH_QUADS 0
+#endif
 #ifndef NSB_STREAM_HASHED
 #define NSB_STREAM_HASHED 0   // measured r1e: 2.78 vs 2.27 ms with L1::no_allocate on the hashed levels (they DO hit in L1: 4 lanes share a sector pair, neighbouring samples share corners)
 #endif
@@ -265,8 +272,10 @@ __device__ __forceinline__ void gather_issue_q(const nsb_field_params &P, const 
                                                GatherTile &G) {
     const uint32_t e0 = __shfl_sync(0xffffffffu, Q.entry, (2 * J) * 8 + g);
     const uint32_t e1 = __shfl_sync(0xffffffffu, Q.entry, (2 * J + 1) * 8 + g);
+#if !NSB_PREFETCH_QUADS
     G.w[0] = __shfl_sync(0xffffffffu, Q.w, (2 * J) * 8 + g);
     G.w[1] = __shfl_sync(0xffffffffu, Q.w, (2 * J + 1) * 8 + g);
+#endif
 #if NSB_STREAM_HASHED
     if (P.levels.hashed[4 * U + 2 * J]) ldg256_stream(tab + (size_t)e0 * 128, G.v[0]);   // uniform (constant bank)
     else ldg256(tab + (size_t)e0 * 128, G.v[0]);
@@ -317,6 +326,13 @@ __device__ __forceinline__ float gather_consume(const GatherTile &G, const Blend
     return butterfly(u0, u1, 3, lane);
 }
 
+// L2 prefetch of a quad's 32 lines (hashed levels only: the dense levels mostly hit L1/L2 anyway).  Costs no registers
+// beyond the address; issued one quad ahead so that the LDG.256 that land in registers find their line in L2.
+__device__ __forceinline__ void quad_prefetch(const nsb_field_params &P, const uint8_t *tab_base, const QuadIdx &Q, int U, int lane) {
+    if (P.levels.hashed[4 * U + (lane >> 3)])
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tab_base + (size_t)Q.entry * 128));
+}
+
 template <bool CV, class BT>
 __device__ __forceinline__ void gather_sample_quad(const nsb_field_params &P, const uint8_t *tab, float x, float y,
                                                    float z, const float4 *next_xs, float4 &next_out, const BT &B,
@@ -325,6 +341,45 @@ __device__ __forceinline__ void gather_sample_quad(const nsb_field_params &P, co
     const bool owner = (lane & 3) == 0;
     GatherTile Gb;
     float e, o, yv;
+#if NSB_PREFETCH_QUADS
+    // Index computation runs ONE QUAD AHEAD of the loads: quad u+1 is computed (and its lines prefetched into L2) one to
+    // two consume steps before its first load.  Qa / Qb alternate; the tiles do not carry their trilinear weights any
+    // more (the consume step shuffles them out of the quad that produced the tile), so the second QuadIdx is register-neutral.
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(P.tables);
+    QuadIdx &Qa = Q;
+    QuadIdx Qb;
+#define NSB_W(QQ, J) Ga_w0 = __shfl_sync(0xffffffffu, (QQ).w, (2 * (J)) * 8 + g); Ga_w1 = __shfl_sync(0xffffffffu, (QQ).w, (2 * (J) + 1) * 8 + g)
+    float Ga_w0, Ga_w1;
+    Qb = quad_compute<1>(P, x, y, z, lane); quad_prefetch(P, tb, Qb, 1, lane);
+    gather_issue_q<0, 1>(P, tab, Qa, g, Gb); NSB_W(Qa, 0); Ga.w[0] = Ga_w0; Ga.w[1] = Ga_w1;
+    e = gather_consume(Ga, B, lane, CV ? cv_row + 0 : nullptr);
+    gather_issue_q<1, 0>(P, tab, Qb, g, Ga); NSB_W(Qa, 1); Gb.w[0] = Ga_w0; Gb.w[1] = Ga_w1;
+    o = gather_consume(Gb, B, lane, CV ? cv_row + 16 : nullptr); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[g] = __float2half_rn(yv);
+    Qa = quad_compute<2>(P, x, y, z, lane); quad_prefetch(P, tb, Qa, 2, lane);
+    gather_issue_q<1, 1>(P, tab, Qb, g, Gb); NSB_W(Qb, 0); Ga.w[0] = Ga_w0; Ga.w[1] = Ga_w1;
+    e = gather_consume(Ga, B, lane, CV ? cv_row + 32 : nullptr);
+    gather_issue_q<2, 0>(P, tab, Qa, g, Ga); NSB_W(Qb, 1); Gb.w[0] = Ga_w0; Gb.w[1] = Ga_w1;
+    o = gather_consume(Gb, B, lane, CV ? cv_row + 48 : nullptr); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[8 + g] = __float2half_rn(yv);
+    Qb = quad_compute<3>(P, x, y, z, lane); quad_prefetch(P, tb, Qb, 3, lane);
+    gather_issue_q<2, 1>(P, tab, Qa, g, Gb); NSB_W(Qa, 0); Ga.w[0] = Ga_w0; Ga.w[1] = Ga_w1;
+    e = gather_consume(Ga, B, lane, CV ? cv_row + 64 : nullptr);
+    gather_issue_q<3, 0>(P, tab, Qb, g, Ga); NSB_W(Qa, 1); Gb.w[0] = Ga_w0; Gb.w[1] = Ga_w1;
+    o = gather_consume(Gb, B, lane, CV ? cv_row + 80 : nullptr); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[16 + g] = __float2half_rn(yv);
+    if (next_xs) {
+        next_out = *next_xs;
+        Qa = quad_compute<0>(P, next_out.x, next_out.y, next_out.z, lane); quad_prefetch(P, tb, Qa, 0, lane);
+    }
+    gather_issue_q<3, 1>(P, tab, Qb, g, Gb); NSB_W(Qb, 0); Ga.w[0] = Ga_w0; Ga.w[1] = Ga_w1;
+    e = gather_consume(Ga, B, lane, CV ? cv_row + 96 : nullptr);
+    if (next_xs) gather_issue_q<0, 0>(P, tab, Qa, g, Ga);
+    NSB_W(Qb, 1); Gb.w[0] = Ga_w0; Gb.w[1] = Ga_w1;
+    o = gather_consume(Gb, B, lane, CV ? cv_row + 112 : nullptr); yv = butterfly(e, o, 4, lane);
+    if (owner) feat_row[24 + g] = __float2half_rn(yv);
+#undef NSB_W
+#else
     gather_issue_q<0, 1>(P, tab, Q, g, Gb); e = gather_consume(Ga, B, lane, CV ? cv_row + 0 : nullptr);
     Q = quad_compute<1>(P, x, y, z, lane);
     gather_issue_q<1, 0>(P, tab, Q, g, Ga); o = gather_consume(Gb, B, lane, CV ? cv_row + 16 : nullptr); yv = butterfly(e, o, 4, lane);
@@ -345,6 +400,7 @@ __device__ __forceinline__ void gather_sample_quad(const nsb_field_params &P, co
     }
     o = gather_consume(Gb, B, lane, CV ? cv_row + 112 : nullptr); yv = butterfly(e, o, 4, lane);
     if (owner) feat_row[24 + g] = __float2half_rn(yv);
+#endif
 }
 
 }  // namespace nsb
