@@ -1,5 +1,6 @@
 """CPU tests of the host logic: packing layouts, level table, window folding, C-ABI exports."""
 import ctypes
+import sys
 import os
 import re
 
@@ -151,3 +152,19 @@ def test_gather_plans_reproduce_the_packers():
         f, fb = pk.pack_field_fast(bw, hw)
         assert torch.equal(f, pk.pack_field(bw, hw)) and torch.equal(fb, pk.pack_field_bwd(bw, hw))
     assert torch.equal(pk.deform_bias_vector(sb, r_b, v_b), pk.pack_deform(stem, sb, r_w, r_b, v_w, v_b)[1])
+
+
+def test_forward_kernel_gather_role_has_no_spill_storm():
+    """Regression guard for a performance cliff, not for correctness: local-memory traffic inside the 64-register gather
+    role of field_kernel_ws is catastrophic (48 spill instructions per sample: 2.6 -> 4.0 ms on B200, profiles/README.md)
+    and ptxas allocates that role erratically.  The committed source builds with <= 9 STL/LDL there; fail loudly when a
+    change (or a different toolkit) pushes a variant over 16."""
+    import shutil, subprocess
+    obj = os.path.join(ROOT, "nersemble_b200", "csrc", "nsb_field.o")
+    if not os.path.exists(obj) or shutil.which("cuobjdump") is None:
+        pytest.skip("needs the in-tree object file and cuobjdump")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "spill_report.py"), obj], capture_output=True, text=True).stdout
+    rows = [l.split() for l in out.splitlines() if "gather" in l]
+    assert len(rows) >= 8
+    for r in rows:
+        assert int(r[r.index("gather") + 1]) <= 16, out
