@@ -23,6 +23,10 @@
  *   nsb_march_*            nerfacc OccGridEstimator.sampling -> traverse_grids
  *                          (nerfstudio/model_components/nersemble_volumetric_sampler.py:95-108)
  *   nsb_visibility_*       nerfacc render_visibility_from_density (the training pre-pass of sampling())
+ *   nsb_composite_backward / nsb_field_backward / nsb_deform_backward
+ *                          torch autograd through all of the above (training)
+ *   nsb_table_adam_step    torch.optim.Adam on the 8 tcnn grid tensors (scripts/train/train_nersemble.py:243-247) and
+ *                          tcnn's per-call fp32 -> fp16 cast of the table parameters
  */
 #ifndef NSB_H
 #define NSB_H
@@ -253,6 +257,32 @@ int nsb_table_adam_step(const nsb_table_adam_args *args, void *stream);
  * a deferred gradient has to become a dense .grad after all: gradient accumulation, dense all-reduce). */
 int nsb_rank1_expand(const float *g_rank1, const float *cw_slots, int32_t n_slots, int64_t total_entries,
                      float grad_scale, float *d_tables, void *stream);
+
+/* The six training losses (reference: models/base.py:90-249 via models/nersemble_instant_ngp.py:366-407, and
+ * torch_efficient_distloss.flatten_eff_distloss) and their gradients w.r.t. the render outputs, fused: two launches
+ * forward, one backward, no host synchronisation (formulas in csrc/nsb_losses.cu).  A lambda of 0 (or alpha /
+ * depth_target == NULL) switches the corresponding term off; its value is then 0. */
+typedef struct nsb_loss_args {
+    int64_t n_rays, n_samples;
+    const int64_t *packed_info;   /* [n_rays][2] */
+    const float *t_starts, *t_ends, *weights;   /* [n_samples] */
+    const float *rgb, *acc, *depth;             /* [n_rays][3], [n_rays], [n_rays] */
+    const float *image;           /* [n_rays][3] ground truth */
+    const float *alpha;           /* [n_rays] in [0,1] (alpha_map / 255) or NULL */
+    const float *depth_target;    /* [n_rays] (0 = no depth) or NULL: empty / near / depth losses */
+    int32_t use_masked_rgb;
+    float alpha_mask_threshold;
+    float lambda_alpha, lambda_empty, lambda_near, lambda_depth, lambda_dist;
+    float eps_depth;
+    int64_t dist_max_rays;
+    double *accum;                /* [16] workspace (forward zeroes it) */
+    float *values;                /* [6] out: rgb, alpha, empty, near, depth, dist loss values */
+    float *coef;                  /* [8] out (forward) / in (backward): per-element gradient factors */
+    const float *upstream;        /* backward: [6] dL/d(values) */
+    float *d_rgb, *d_acc, *d_depth, *d_weights;   /* backward out: [n_rays][3], [n_rays], [n_rays], [n_samples] */
+} nsb_loss_args;
+int nsb_losses_forward(const nsb_loss_args *args, void *stream);
+int nsb_losses_backward(const nsb_loss_args *args, void *stream);
 
 /* Fixed-stride marcher (BASELINE configs 1/2): n_per_ray intervals of `step` from max(t_enter, near). */
 int nsb_march_fixed(const float *origins, const float *directions, int64_t n_rays, const float *aabb6,

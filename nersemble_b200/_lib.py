@@ -65,6 +65,17 @@ class TableAdamArgs(C.Structure):
                 ("bias_correction2", C.c_float)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int64), ("packed_info", C.c_void_p), ("t_starts", C.c_void_p),
+                ("t_ends", C.c_void_p), ("weights", C.c_void_p), ("rgb", C.c_void_p), ("acc", C.c_void_p),
+                ("depth", C.c_void_p), ("image", C.c_void_p), ("alpha", C.c_void_p), ("depth_target", C.c_void_p),
+                ("use_masked_rgb", C.c_int32), ("alpha_mask_threshold", C.c_float), ("lambda_alpha", C.c_float),
+                ("lambda_empty", C.c_float), ("lambda_near", C.c_float), ("lambda_depth", C.c_float),
+                ("lambda_dist", C.c_float), ("eps_depth", C.c_float), ("dist_max_rays", C.c_int64),
+                ("accum", C.c_void_p), ("values", C.c_void_p), ("coef", C.c_void_p), ("upstream", C.c_void_p),
+                ("d_rgb", C.c_void_p), ("d_acc", C.c_void_p), ("d_depth", C.c_void_p), ("d_weights", C.c_void_p)]
+
+
 class CompositeArgs(C.Structure):
     _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int64), ("packed_info", C.c_void_p),
                 ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p),
@@ -110,6 +121,8 @@ SYMBOLS = {
     "nsb_deform_bwd_workspace_bytes": (C.c_size_t, []),
     "nsb_deform_backward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(Samples),
                                       C.POINTER(DeformBwdArgs), C.c_void_p]),
+    "nsb_losses_forward": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
+    "nsb_losses_backward": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "nsb_table_adam_step": (C.c_int, [C.POINTER(TableAdamArgs), C.c_void_p]),
     "nsb_rank1_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "nsb_hash_blend_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.c_void_p, C.c_void_p,

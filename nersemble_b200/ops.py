@@ -6,6 +6,7 @@ the hand-written sm_100a kernels.  There is no CPU fallback: non-CUDA tensors ra
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
@@ -103,7 +104,10 @@ class NativeParams:
         return P
 
     def c_params(self) -> _lib.FieldParams:
-        p = _lib.FieldParams()
+        p = getattr(self, "_cp", None)      # the level table / aabb part never changes: fill it once (host time matters:
+        fresh = p is None                   # a training step is ~6 ms of host work against ~20 ms of GPU work)
+        if fresh:
+            p = self._cp = _lib.FieldParams()
         p.tables = _ptr(self.tables)
         p.deform_packed = _ptr(self.deform_packed)
         p.deform_bias = _ptr(self.deform_bias)
@@ -113,21 +117,30 @@ class NativeParams:
         p.warp_codes = _ptr(self.warp_codes)
         p.blend_codes = _ptr(self.blend_codes)
         p.n_timesteps = self.n_timesteps
-        for i, v in enumerate(self.aabb_list):
-            p.aabb[i] = v
-        lv = self.levels
-        p.levels.n_levels = lv["n_levels"]
-        for l in range(lv["n_levels"]):
-            p.levels.scale[l] = lv["scale"][l]
-            p.levels.res[l] = lv["res"][l]
-            p.levels.entries[l] = lv["entries"][l]
-            p.levels.offset[l] = lv["offset"][l]
-            p.levels.hashed[l] = lv["hashed"][l]
+        if fresh:
+            for i, v in enumerate(self.aabb_list):
+                p.aabb[i] = v
+            lv = self.levels
+            p.levels.n_levels = lv["n_levels"]
+            for l in range(lv["n_levels"]):
+                p.levels.scale[l] = lv["scale"][l]
+                p.levels.res[l] = lv["res"][l]
+                p.levels.entries[l] = lv["entries"][l]
+                p.levels.offset[l] = lv["offset"][l]
+                p.levels.hashed[l] = lv["hashed"][l]
         return p
 
 
 def make_opts(window_hash: Optional[float], window_deform: Optional[float], use_deformation: bool,
               compute_rgb: bool, disable_initial: bool = True, soft_transition: bool = True) -> _lib.FieldOpts:
+    """nsb_field_opts for the given schedule values (memoised: the windows change once per training step at most, and
+    the struct is only read)."""
+    return _make_opts(None if window_hash is None else float(window_hash), None if window_deform is None else float(window_deform),
+                      bool(use_deformation), bool(compute_rgb), bool(disable_initial), bool(soft_transition))
+
+
+@functools.lru_cache(maxsize=64)
+def _make_opts(window_hash, window_deform, use_deformation, compute_rgb, disable_initial, soft_transition) -> _lib.FieldOpts:
     o = _lib.FieldOpts()
     sc, bi = packing.blend_fold(window_hash, 32, disable_initial, soft_transition)
     for h in range(32):
@@ -352,6 +365,62 @@ def rank1_expand(pending: dict, total_entries: int, grad_scale: float = 1.0, out
     _lib.check(lib.nsb_rank1_expand(_ptr(g1), _ptr(pending["cw_slots"]), int(pending["n_slots"]), int(total_entries),
                                     float(grad_scale), _ptr(out), _stream()), "nsb_rank1_expand")
     return out
+
+
+LOSS_NAMES = ("rgb_loss", "alpha_loss", "empty_loss", "near_loss", "depth_loss", "dist_loss")
+
+
+def _loss_args(packed_info, t_starts, t_ends, weights, rgb, acc, depth, image, alpha, depth_target, cfg: dict, keep: list):
+    a = _lib.LossArgs()
+    pi = packed_info.to(torch.int64).contiguous()
+    ts, te, w = _f32c(t_starts).reshape(-1), _f32c(t_ends).reshape(-1), _f32c(weights).reshape(-1)
+    rgb_, acc_, dep_ = _f32c(rgb).reshape(-1, 3), _f32c(acc).reshape(-1), _f32c(depth).reshape(-1)
+    img = _f32c(image).reshape(-1, 3)
+    al = None if alpha is None else _f32c(alpha).reshape(-1)
+    dt = None if depth_target is None else _f32c(depth_target).reshape(-1)
+    _need_cuda(pi, ts, te, w, rgb_, acc_, dep_, img, al, dt)
+    keep += [pi, ts, te, w, rgb_, acc_, dep_, img, al, dt]
+    a.n_rays, a.n_samples = int(pi.shape[0]), int(w.shape[0])
+    a.packed_info, a.t_starts, a.t_ends, a.weights = _ptr(pi), _ptr(ts), _ptr(te), _ptr(w)
+    a.rgb, a.acc, a.depth, a.image, a.alpha, a.depth_target = _ptr(rgb_), _ptr(acc_), _ptr(dep_), _ptr(img), _ptr(al), _ptr(dt)
+    a.use_masked_rgb = int(bool(cfg.get("use_masked_rgb", True)))
+    a.alpha_mask_threshold = float(cfg.get("alpha_mask_threshold", 0.0))
+    for k in ("lambda_alpha", "lambda_empty", "lambda_near", "lambda_depth", "lambda_dist"):
+        setattr(a, k, float(cfg.get(k) or 0.0))
+    a.eps_depth = float(cfg.get("eps_depth", 0.0))
+    a.dist_max_rays = int(cfg.get("dist_max_rays", 1 << 62))
+    return a
+
+
+def losses_forward(packed_info, t_starts, t_ends, weights, rgb, acc, depth, image, alpha, depth_target, cfg: dict):
+    """The six losses of models/base.py in two launches (nsb_losses_forward).  Returns (values [6] in LOSS_NAMES order,
+    state for losses_backward).  cfg: use_masked_rgb, alpha_mask_threshold, lambda_{alpha,empty,near,depth,dist},
+    eps_depth, dist_max_rays; a lambda of 0 / a missing alpha or depth_target switches a term off (value 0)."""
+    lib = _lib.load()
+    keep: list = []
+    a = _loss_args(packed_info, t_starts, t_ends, weights, rgb, acc, depth, image, alpha, depth_target, cfg, keep)
+    dev = keep[0].device
+    accum = torch.empty(16, dtype=torch.float64, device=dev)
+    values = torch.empty(6, dtype=_F32, device=dev)
+    coef = torch.empty(8, dtype=_F32, device=dev)
+    a.accum, a.values, a.coef = _ptr(accum), _ptr(values), _ptr(coef)
+    _lib.check(lib.nsb_losses_forward(C.byref(a), _stream()), "nsb_losses_forward")
+    return values, {"args": a, "keep": keep + [accum, values, coef]}
+
+
+def losses_backward(state: dict, upstream: torch.Tensor):
+    """Gradients of sum_k upstream[k] * values[k] w.r.t. (rgb [R,3], acc [R], depth [R], weights [S])."""
+    lib = _lib.load()
+    a, keep = state["args"], state["keep"]
+    dev = keep[0].device
+    up = _f32c(upstream).reshape(6)
+    d_rgb = torch.empty((a.n_rays, 3), dtype=_F32, device=dev)
+    d_acc = torch.empty((a.n_rays,), dtype=_F32, device=dev)
+    d_depth = torch.empty((a.n_rays,), dtype=_F32, device=dev)
+    d_w = torch.zeros((a.n_samples,), dtype=_F32, device=dev)
+    a.upstream, a.d_rgb, a.d_acc, a.d_depth, a.d_weights = _ptr(up), _ptr(d_rgb), _ptr(d_acc), _ptr(d_depth), _ptr(d_w)
+    _lib.check(lib.nsb_losses_backward(C.byref(a), _stream()), "nsb_losses_backward")
+    return d_rgb, d_acc, d_depth, d_w
 
 
 def deform_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_xs: torch.Tensor, *, window_deform=None,

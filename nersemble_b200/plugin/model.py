@@ -135,6 +135,23 @@ class _RenderFunction(torch.autograd.Function):
         return (None,) * 10 + tuple(grads)
 
 
+class _FusedLosses(torch.autograd.Function):
+    """nsb_losses_forward / nsb_losses_backward behind autograd: values [6] in ops.LOSS_NAMES order."""
+
+    @staticmethod
+    def forward(ctx, rgb, acc, depth, weights, packed_info, starts, ends, image, alpha, depth_target, cfg):
+        values, state = ops.losses_forward(packed_info, starts, ends, weights, rgb, acc, depth, image, alpha, depth_target, cfg)
+        ctx.state = state
+        ctx.shapes = (rgb.shape, acc.shape, depth.shape, weights.shape)
+        return values
+
+    @staticmethod
+    def backward(ctx, g_values):
+        d_rgb, d_acc, d_depth, d_w = ops.losses_backward(ctx.state, g_values)
+        s = ctx.shapes
+        return (d_rgb.reshape(s[0]), d_acc.reshape(s[1]), d_depth.reshape(s[2]), d_w.reshape(s[3])) + (None,) * 7
+
+
 def _segment_exclusive_sum(x: Tensor, ray_indices: Tensor, n_rays: int) -> Tensor:
     cnt = torch.zeros(n_rays, dtype=torch.long, device=x.device).index_add_(0, ray_indices, torch.ones_like(ray_indices))
     starts = cnt.cumsum(0) - cnt
@@ -158,6 +175,7 @@ class NeRSembleNGPModel(nn.Module):
         self._native = None
         self._native_version = None
         self.sync_free_losses = True     # get_loss_dict without host syncs on CUDA (see _loss_dict_sync_free)
+        self.fused_losses = True         # ... and, when the outputs come from get_outputs, in fused kernels (_loss_dict_fused)
 
     @property
     def device(self):
@@ -355,6 +373,8 @@ class NeRSembleNGPModel(nn.Module):
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
         """models/nersemble_instant_ngp.py:366-407 -> models/base.py:90-249 (plain torch on per-ray/per-sample outputs)."""
         cfg = self.config
+        if self.fused_losses and outputs["rgb"].is_cuda and "num_samples_per_ray" in outputs:
+            return self._loss_dict_fused(outputs, batch)
         if self.sync_free_losses and outputs["rgb"].is_cuda:
             return self._loss_dict_sync_free(outputs, batch)
         ld: Dict[str, Tensor] = {}
@@ -410,6 +430,34 @@ class NeRSembleNGPModel(nn.Module):
                 dist = ((1.0 / 3.0) * (interval * w * w).sum() + 2.0 * (w * (m * w_pre - wm_pre)).sum()) / n_rays
                 ld["dist_loss"] = cfg.lambda_dist_loss * dist
         return ld
+
+    def _loss_dict_fused(self, outputs, batch) -> Dict[str, Tensor]:
+        """All six losses and their gradients in three kernel launches (csrc/nsb_losses.cu).  Same values as
+        _loss_dict_sync_free (terms with an empty mask are present with value 0; fp32 scans instead of float64)."""
+        cfg = self.config
+        rgb = outputs["rgb"]
+        dev = rgb.device
+        rs: RaySamples = outputs["ray_samples"][0]
+        cnt = outputs["num_samples_per_ray"].to(torch.int64)
+        packed_info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)
+        alpha = batch["alpha_map"].squeeze(1).to(dev) / 255. if "alpha_map" in batch else None
+        train_terms = self.training and "depth_maps" in batch
+        use = {"rgb_loss": True,
+               "alpha_loss": bool(cfg.lambda_alpha_loss) and cfg.lambda_alpha_loss > 0 and alpha is not None,
+               "empty_loss": train_terms and cfg.lambda_empty_loss > 0, "near_loss": train_terms and cfg.lambda_near_loss > 0,
+               "depth_loss": train_terms and cfg.lambda_depth_loss > 0, "dist_loss": cfg.lambda_dist_loss > 0}
+        lcfg = dict(use_masked_rgb=cfg.use_masked_rgb_loss, alpha_mask_threshold=cfg.alpha_mask_threshold,
+                    lambda_alpha=cfg.lambda_alpha_loss if use["alpha_loss"] else 0.0,
+                    lambda_empty=cfg.lambda_empty_loss if use["empty_loss"] else 0.0,
+                    lambda_near=cfg.lambda_near_loss if use["near_loss"] else 0.0,
+                    lambda_depth=cfg.lambda_depth_loss if use["depth_loss"] else 0.0,
+                    lambda_dist=cfg.lambda_dist_loss if use["dist_loss"] else 0.0,
+                    eps_depth=self.sched_eps_depth.value if self.sched_eps_depth is not None else 0.0,
+                    dist_max_rays=cfg.dist_loss_max_rays)
+        depth_target = batch["depth_maps"].to(dev) if (use["empty_loss"] or use["near_loss"] or use["depth_loss"]) else None
+        vals = _FusedLosses.apply(rgb, outputs["accumulation"], outputs["depth"], outputs["weights"][0], packed_info,
+                                  rs.frustums.starts, rs.frustums.ends, batch["image"].to(dev), alpha, depth_target, lcfg)
+        return {name: vals[i] for i, name in enumerate(ops.LOSS_NAMES) if use[name]}
 
     def _loss_dict_sync_free(self, outputs, batch) -> Dict[str, Tensor]:
         """Same six losses (models/base.py:90-249) without device->host synchronisation: the reference selects

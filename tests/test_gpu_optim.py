@@ -108,3 +108,50 @@ def test_fused_fields_adam_tracks_torch_adam_on_the_model():
     assert cos > 0.995, cos
     assert (t_f != 0).float().mean().item() > 0.01            # and they are real updates
     assert (b_f - b_t).abs().max().item() < 5e-3 * 0.05
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_fused_losses_match_the_torch_formulation_values_and_gradients(training):
+    """nsb_losses_forward/backward vs the plugin's torch formulation of models/base.py:90-249 (itself pinned to the
+    reference glue's golden in tests/test_plugin_cpu.py): six loss values and the gradients w.r.t. rgb / accumulation /
+    depth / per-sample weights, ragged rays including empty ones, upstream gradients != 1."""
+    from test_plugin_cpu import make_model
+    from nersemble_b200.nerfstudio_shim import Frustums, RaySamples
+    g = torch.Generator().manual_seed(11)
+    R = 300
+    cnt = torch.randint(0, 70, (R,), generator=g); cnt[5] = 0; cnt[R - 1] = 0; cnt[17] = 64
+    S = int(cnt.sum())
+    ri = torch.repeat_interleave(torch.arange(R), cnt)
+    ts = torch.cat([torch.sort(torch.rand(int(c), generator=g) * 6 + 5)[0] for c in cnt]) if S else torch.zeros(0)
+    te = ts + 0.011
+    m = make_model(T=4, log2T=12, dist_loss_max_rays=250).to(DEV)
+    m.train(training)
+    m.sched_eps_depth.value = 0.35
+    w = (torch.rand(S, generator=g) * 0.05).to(DEV).requires_grad_(True)
+    rgb = torch.rand(R, 3, generator=g).to(DEV).requires_grad_(True)
+    acc = torch.rand(R, 1, generator=g).to(DEV).requires_grad_(True)
+    depth = (torch.rand(R, 1, generator=g) * 6 + 5).to(DEV).requires_grad_(True)
+    rs = RaySamples(Frustums(torch.zeros(S, 3, device=DEV), torch.zeros(S, 3, device=DEV), ts[:, None].to(DEV), te[:, None].to(DEV), torch.zeros(S, 1, device=DEV)))
+    outputs = {"rgb": rgb, "accumulation": acc, "depth": depth, "ray_samples": (rs,), "ray_indices": (ri.to(DEV),),
+               "weights": (w[:, None],), "num_samples_per_ray": cnt.to(DEV)}
+    batch = {"image": torch.rand(R, 3, generator=g), "alpha_map": torch.randint(0, 256, (R, 1), generator=g).float(),
+             "depth_maps": (torch.rand(R, generator=g) * 6 + 5) * (torch.rand(R, generator=g) > 0.3)}
+    batch["alpha_map"][:20] = 255.0; batch["alpha_map"][20:30] = 0.0
+    up = {k: 0.5 + i * 0.37 for i, k in enumerate(("rgb_loss", "alpha_loss", "empty_loss", "near_loss", "depth_loss", "dist_loss"))}
+
+    def run(fused):
+        m.fused_losses = fused
+        for t in (w, rgb, acc, depth):
+            t.grad = None
+        ld = m.get_loss_dict(outputs, batch)
+        sum(up[k] * v for k, v in ld.items()).backward()
+        return {k: v.item() for k, v in ld.items()}, [torch.zeros_like(t) if t.grad is None else t.grad.clone() for t in (w, rgb, acc, depth)]
+
+    v_f, g_f = run(True)
+    v_t, g_t = run(False)
+    assert set(v_f) == set(v_t) and (len(v_f) == 6 if training else set(v_f) == {"rgb_loss", "alpha_loss", "dist_loss"})
+    for k in v_t:
+        assert abs(v_f[k] - v_t[k]) <= 2e-4 * abs(v_t[k]) + 1e-9, (k, v_f[k], v_t[k])
+    for a, b, name in zip(g_f, g_t, ("weights", "rgb", "acc", "depth")):
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= 2e-4 * scale, (name, (a - b).abs().max().item(), scale)
