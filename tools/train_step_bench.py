@@ -12,7 +12,7 @@ from test_plugin_cpu import make_model
 from nersemble_b200.nerfstudio_shim import RayBundle
 from nersemble_b200.distributed import allreduce_gradients
 
-ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true"); ap.add_argument("--all-losses", action="store_true", help="config 3: all six losses with the script's default lambdas (synthetic depth maps)"); ap.add_argument("--torch-adam", action="store_true", help="dense table gradient + torch.optim.Adam (the reference's optimiser path) instead of FusedFieldsAdam"); args = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true"); ap.add_argument("--cprofile", action="store_true", help="host-side cProfile of 5 more steps"); ap.add_argument("--all-losses", action="store_true", help="config 3: all six losses with the script's default lambdas (synthetic depth maps)"); ap.add_argument("--torch-adam", action="store_true", help="dense table gradient + torch.optim.Adam (the reference's optimiser path) instead of FusedFieldsAdam"); args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr_ = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr_); dev = torch.device("cuda", lr_)
 if world > 1:
@@ -69,6 +69,17 @@ if args.profile and rank == 0:
         opt.step()
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+if args.cprofile and rank == 0:
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable()
+    for _ in range(5):
+        opt.zero_grad(set_to_none=True)
+        out = m.get_outputs(rb)
+        loss = sum(m.get_loss_dict(out, batch).values())
+        loss.backward()
+        opt.step()
+    torch.cuda.synchronize(); pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
 avg = [sum(r[i] for r in rows) / len(rows) for i in range(5)]
 n_samples = int(out["num_samples_per_ray"].sum().item())
 if rank == 0:
