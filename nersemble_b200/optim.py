@@ -27,6 +27,10 @@ class FusedFieldsAdam(torch.optim.Adam):
         if kw.get("amsgrad") or kw.get("maximize"):
             raise NotImplementedError("FusedFieldsAdam: amsgrad / maximize")
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+        # torch.cuda.amp.GradScaler unscales `.grad` tensors only; the parked table gradient is not one.  A trainer that
+        # scales the loss sets this to 1 / scaler.get_scale() before step() (Adam is scale-invariant up to eps, so
+        # forgetting it changes the update only where |g| ~ eps = 1e-15).
+        self.pending_grad_scale = 1.0
         self._ensembles = []
         for group in self.param_groups:
             for p in group["params"]:
@@ -65,7 +69,7 @@ class FusedFieldsAdam(torch.optim.Adam):
             ops.table_adam_step(p.data, st["exp_avg"], st["exp_avg_sq"], shadow, step=int(st["step"].item()),
                                 lr=float(group["lr"]), betas=group["betas"], eps=group["eps"],
                                 weight_decay=group["weight_decay"], grad=dense, pending=pending,
-                                grad_scale=1.0 if pending is None else float(pending.get("scale", 1.0)))
+                                grad_scale=(1.0 if pending is None else float(pending.get("scale", 1.0)) * float(self.pending_grad_scale)))
             torch.autograd.graph.increment_version(p)
             he.set_native_tables(shadow)
             he.pending_table_grad = None
