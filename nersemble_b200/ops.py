@@ -86,12 +86,17 @@ class NativeParams:
         dev = torch.device(device)
         tab = None if tables is None else tables.detach().to(dev).half().contiguous()
         fp = fpt = None
-        if base_w is not None:
-            fp, fpt = packing.pack_field_fast([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
         dp = db = wc = None
         if deform is not None:
             sw, sb = [w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]]
+        if base_w is not None and deform is not None:      # the training path: one gather for all five buffers
+            dp, dtb, dpt, fp, fpt = packing.pack_all_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev),
+                                                          [w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
+        elif base_w is not None:
+            fp, fpt = packing.pack_field_fast([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
+        elif deform is not None:
             dp, dtb, dpt = packing.pack_deform_weights_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
+        if deform is not None:
             db = packing.deform_bias_vector(sb, deform["r_b"].to(dev), deform["v_b"].to(dev))
             wc = time_emb_deform.detach().to(dev).half().contiguous()
             dcb = packing.deform_code_bias(sw, sb, wc)

@@ -76,8 +76,7 @@ class NeRSembleNeRFactoField(nn.Module):
         return packing.split_tcnn_mlp_params(self.mlp_head.params, HEAD_SHAPES)
 
     def _native_params(self) -> ops.NativeParams:
-        v = (self.mlp_base.params._version, self.mlp_head.params._version, self.hash_ensemble._versions(),
-             self.mlp_base.params.data_ptr())
+        v = (self.mlp_base.params._version, self.mlp_head.params._version, self.mlp_base.params.data_ptr())
         if self._native is None or v != self._native_version:
             with torch.no_grad():
                 self._native = ops.NativeParams.build(tables=None, time_emb=None, aabb=self.aabb, levels=self.hash_ensemble.levels,

@@ -151,6 +151,9 @@ def test_gather_plans_reproduce_the_packers():
         hw = [torch.randn(64, 32, generator=g), torch.randn(64, 64, generator=g), torch.randn(16, 64, generator=g)]
         f, fb = pk.pack_field_fast(bw, hw)
         assert torch.equal(f, pk.pack_field(bw, hw)) and torch.equal(fb, pk.pack_field_bwd(bw, hw))
+        al = pk.pack_all_fast(stem, r_w, v_w, bw, hw)      # one gather for all five
+        for got, want in zip(al, (a, b, c, f, fb)):
+            assert torch.equal(got, want)
     assert torch.equal(pk.deform_bias_vector(sb, r_b, v_b), pk.pack_deform(stem, sb, r_w, r_b, v_w, v_b)[1])
 
 

@@ -98,6 +98,14 @@ def test_field_density_fn_and_components():
         want_o = pl.compute_offsets(P, pos, wc, 5.5)
         got_o = m.deformation_field.compute_offsets(pos.to(DEV), wc.to(DEV), 5.5).cpu()
     torch.testing.assert_close(got_o, want_o, rtol=5e-3, atol=5e-6)
+    # Field component API (fields/nersemble_nerfacto_field.py:228-248): density_fn with explicit time codes = the
+    # oracle's field_density on the same positions
+    tsteps = torch.randint(0, 4, (300,), generator=gen)
+    with torch.no_grad():
+        want_s, _ = pl.field_density(P, pos, P.time_emb[tsteps], 20.25)
+        got_s = m.field.density_fn(pos.to(DEV), times=None, window_hash_encodings=20.25,
+                                   time_codes=P.time_emb[tsteps].to(DEV)).cpu()
+    torch.testing.assert_close(got_s.reshape(-1), want_s.reshape(-1), rtol=5e-3, atol=1e-5)
     Precision.mode = "reference"
 
 
