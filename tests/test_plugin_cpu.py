@@ -124,3 +124,30 @@ def test_loss_dict_matches_reference_glue_golden():
     batch0 = dict(batch); batch0["depth_maps"] = torch.zeros_like(batch["depth_maps"])
     assert "depth_loss" not in m.get_loss_dict(outputs, batch0)
     assert float(m._loss_dict_sync_free(outputs, batch0)["depth_loss"]) == 0.0
+
+
+def test_fused_fields_adam_host_logic_and_no_cpu_fallback():
+    """FusedFieldsAdam finds the table parameter by itself, switches the ensemble to deferred table gradients, leaves
+    every other parameter to torch.optim.Adam, clears a parked gradient on zero_grad -- and refuses to update a table
+    that is not on a CUDA device instead of falling back to a CPU implementation."""
+    from nersemble_b200.optim import FusedFieldsAdam, FusedFieldsAdamOptimizerConfig
+    m = make_model()
+    he = m.field.hash_ensemble
+    groups = m.get_param_groups()
+    with pytest.raises(ValueError):
+        FusedFieldsAdam(groups["embeddings"], lr=1e-3)            # no table among these parameters
+    assert not he.defer_table_grad
+    opt = FusedFieldsAdamOptimizerConfig(lr=5e-3, eps=1e-15).setup(groups["fields"])
+    assert isinstance(opt, torch.optim.Adam) and he.defer_table_grad
+    opt.step()                                                    # nothing to do: no gradients anywhere
+    assert len(opt.state[he.tables]) == 0
+    he.pending_table_grad = {"g_rank1": None}
+    opt.zero_grad()
+    assert he.pending_table_grad is None
+    base = m.field.mlp_base.params
+    before = base.detach().clone()
+    base.grad = torch.ones_like(base)
+    he.tables.grad = torch.zeros_like(he.tables)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+    assert not torch.equal(base.detach(), before)                 # the torch part of the step did run
