@@ -191,7 +191,9 @@ constexpr int kSiteL5 = 0, kSiteL4A = 4096, kSiteL4B = 8192, kSiteL3 = 13824, kS
 // all 8 warps repeated the movmatrix of every block: 262 M MOVM per step, more than the HMMAs).
 // BIAS: the bias gradient (column sums of delta) rides along as one more HMMA per row block against an all-ones B
 // fragment; lane (g, q == 0) owns outputs 16*ob + g and + 8 of bias_acc (no shuffles, no atomics).
-template <int IB0, int NIB, bool BIAS>
+// NTOT / I0: the site holds NTOT input k-tiles per output block; this call covers tiles I0..I0+NIB-1 of them (wide
+// layers are done in two calls: 11 k-tiles of accumulators would be 88 registers of the 128 a 512-thread CTA allows).
+template <int IB0, int NIB, bool BIAS, int NTOT = NIB, int I0 = 0>
 __device__ __forceinline__ void dw_slice(SmemDB &sm, int ob, float4 *site, bool first, float *bias_acc, int lane) {
     float acc[NIB][2][4];
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -217,29 +219,22 @@ __device__ __forceinline__ void dw_slice(SmemDB &sm, int ob, float4 *site, bool 
         bias_acc[ob * 16 + (lane >> 2)] += bsum[0];
         bias_acc[ob * 16 + (lane >> 2) + 8] += bsum[2];
     }
-    float4 *dst = site + (size_t)ob * NIB * 64 + lane;
+    float4 *dst = site + (size_t)ob * NTOT * 64 + I0 * 64 + lane;
     if (first) {
 #pragma unroll
         for (int i = 0; i < NIB; ++i)
 #pragma unroll
             for (int h = 0; h < 2; ++h) dst[(i * 2 + h) * 32] = make_float4(acc[i][h][0], acc[i][h][1], acc[i][h][2], acc[i][h][3]);
     } else {
+        // fire-and-forget vector reductions: nobody else touches these lines, and unlike load-add-store the warp does
+        // not wait a DRAM/L2 round trip per slice (the accumulators do not stay L2-resident next to 2.8 GB of streamed
+        // activations)
 #pragma unroll
-        for (int i0 = 0; i0 < NIB; i0 += 4) {       // 8 float4 in flight
-            float4 cur[4][2];
+        for (int i = 0; i < NIB; ++i)
 #pragma unroll
-            for (int i = i0; i < i0 + 4 && i < NIB; ++i)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) cur[i - i0][h] = dst[(i * 2 + h) * 32];
-#pragma unroll
-            for (int i = i0; i < i0 + 4 && i < NIB; ++i)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float4 c = cur[i - i0][h];
-                    c.x += acc[i][h][0]; c.y += acc[i][h][1]; c.z += acc[i][h][2]; c.w += acc[i][h][3];
-                    dst[(i * 2 + h) * 32] = c;
-                }
-        }
+            for (int h = 0; h < 2; ++h)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (i * 2 + h) * 32), "f"(acc[i][h][0]),
+                             "f"(acc[i][h][1]), "f"(acc[i][h][2]), "f"(acc[i][h][3]) : "memory");
     }
 }
 
@@ -280,19 +275,27 @@ __global__ void __launch_bounds__(256) deform_dw_reduce_kernel(const __grid_cons
     if (c1 >= 0) { dw[(size_t)o * ld + c1] += s.y * R.inv_ls; dw[(size_t)(o + 8) * ld + c1] += s.w * R.inv_ls; }
 }
 
-__global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constant__ DeformBwdKArgs K) {
+// 16 warps, two roles that only meet at the per-layer barriers:
+//   CHAIN warps 0-7  : rows 16w..16w+15 -- SE(3) backward, delta chain through the transposed weights (ring), staging
+//   DW    warps 8-15 : output block ob = w - 8 of every weight gradient (tile-wide contraction), bias sums
+// (One role per warp doubled the resident warps: the r1e capture of the 8-warp version showed 22 % issue-active at
+//  12.5 % occupancy, the dX chain and the dW contraction of a layer are independent once D / X are staged.)
+constexpr int kDbThreads = 512;
+__global__ void __launch_bounds__(kDbThreads, 1) deform_bwd_kernel(const __grid_constant__ DeformBwdKArgs K) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemDB &sm = *reinterpret_cast<SmemDB *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool chain = tid < 256;
+    const int warp = (tid >> 5) & 7;          // CHAIN: row block; DW: output block
     const int g = lane >> 2, q = lane & 3;
     const int64_t n = K.S.n_samples;
     const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
     const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     {   // forward heads fragments live at the end of deform_packed_tb (slabs 92,93 of 94)
         const uint4 *hw = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(K.P.deform_packed_tb) + 92 * 2048);
-        for (int i = tid; i < 256; i += 256) sm.heads_w[i] = __ldg(hw + i);
+        for (int i = tid; i < 256; i += kDbThreads) sm.heads_w[i] = __ldg(hw + i);
         if (tid < 8) sm.bias_heads[tid] = K.P.deform_bias[6 * 128 + tid];
-        for (int i = tid; i < 6 * 128; i += 256) (&sm.bias_acc[0][0])[i] = 0.f;
+        for (int i = tid; i < 6 * 128; i += kDbThreads) (&sm.bias_acc[0][0])[i] = 0.f;
         if (tid == 0) {
             for (int s = 0; s < kDStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 8); }
             mbar_fence_init();
@@ -301,12 +304,14 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
     __syncthreads();
     const float ls = K.B.loss_scale, inv_ls = 1.0f / K.B.loss_scale;
     TRing rf;
-    rf.producer = warp == 0 && lane == 0;
+    rf.producer = tid == 0;
     rf.total = (uint32_t)(my_tiles * kTChunks);
     rf.src = reinterpret_cast<const uint8_t *>(K.B.deform_packed_t);
     rf.gbase = 0;
-    for (uint32_t c = 0; c < kDStages - 1; ++c) rf.issue(sm, c);
-    __syncwarp();
+    if (chain) {
+        for (uint32_t c = 0; c < kDStages - 1; ++c) rf.issue(sm, c);
+        __syncwarp();
+    }
     const uint4 *acts = reinterpret_cast<const uint4 *>(K.B.deform_acts);
     const uint4 *encs = reinterpret_cast<const uint4 *>(K.B.deform_enc);
     const float amin[3] = {K.P.aabb[0], K.P.aabb[1], K.P.aabb[2]};
@@ -318,9 +323,14 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         rf.gbase = (uint32_t)(it * kTChunks);
         const uint4 *act_w = acts + ((size_t)tile * 8 + warp) * 6 * 256;     // [layer][kt][lane]
         const uint4 *enc_w = encs + ((size_t)tile * 8 + warp) * 3 * 32;
+        int tsr[2] = {0, 0};
+        bool ts_uniform = true;
+        uint32_t dAh[4] = {0u, 0u, 0u, 0u};
+        uint32_t relu_lo = 0, relu_hi = 0;     // ReLU-derivative bits of the staged activation: k-tiles 0-3 / 4-7, 8 bits each
+        uint32_t dcur[8][4];
+        if (chain) {
         // ---- per-row inputs: normalised position and timestep of rows g / g+8 ----
         float pn[2][3];
-        int tsr[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int64_t s = row0 + g + 8 * h;
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         }
         if (q == 0) { sm.ts[warp * 16 + g] = tsr[0]; sm.ts[warp * 16 + g + 8] = tsr[1]; }
         const int ts_lane0 = __shfl_sync(0xffffffffu, tsr[0], 0);   // (no shuffle inside a short-circuit expression)
-        const bool ts_uniform = __all_sync(0xffffffffu, (tsr[0] == ts_lane0) & (tsr[1] == ts_lane0));
+        ts_uniform = __all_sync(0xffffffffu, (tsr[0] == ts_lane0) & (tsr[1] == ts_lane0));
         // ---- heads forward (v, r) from a5, SE(3) backward ----
         float hacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
@@ -408,18 +418,18 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                 if (s1 != 0.f) atomicAdd(b1p, s1 * inv_ls);
             }
         }
-        uint32_t dAh[4] = {pack_h2(dh[0][0], dh[0][1]), pack_h2(dh[0][2], dh[0][3]), 0u, 0u};
-        // ---- dW heads: stage delta (k-tile 0) and a5, every warp takes one 16-column block of the 128 inputs ----
+        dAh[0] = pack_h2(dh[0][0], dh[0][1]); dAh[1] = pack_h2(dh[0][2], dh[0][3]);
+        // ---- dW heads: stage delta (k-tile 0) and a5; DW warp ob takes one 16-column block of the 128 inputs ----
         sm.D[warp][0][lane] = make_uint4(dAh[0], dAh[1], dAh[2], dAh[3]);
-        uint32_t relu_lo = 0, relu_hi = 0;     // ReLU-derivative bits of the staged activation: k-tiles 0-3 / 4-7, 8 bits each
 #pragma unroll
         for (int kt = 0; kt < 8; ++kt) {
             const uint4 v = __ldcs(act_w + 5 * 256 + kt * 32 + lane);
             if (kt < 4) relu_lo |= pos_bits(v) << (8 * kt); else relu_hi |= pos_bits(v) << (8 * (kt - 4));
             sm.X[warp][kt][lane] = movt4(v);
         }
+        }   // chain
         __syncthreads();
-        {
+        if (!chain) {
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 1
             for (int rb = 0; rb < 8; ++rb) {
@@ -441,8 +451,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
             }
         }
         // ---- delta_5 = (delta_heads . W_heads) * (a5 > 0) ----
-        uint32_t dcur[8][4];
-        {
+        if (chain) {
             auto ah = [&](int, uint32_t(&a)[4]) { a[0] = dAh[0]; a[1] = dAh[1]; a[2] = dAh[2]; a[3] = dAh[3]; };
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -464,10 +473,11 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         // ---- the six stem layers, last to first ----
 #pragma unroll 1
         for (int l = 5; l >= 0; --l) {
+            const bool has_hidden = l >= 1, has_in = (l == 4 || l == 0);
+            if (chain) {
             // stage this layer's delta and input fragments
 #pragma unroll
             for (int kt = 0; kt < 8; ++kt) sm.D[warp][kt][lane] = make_uint4(dcur[kt][0], dcur[kt][1], dcur[kt][2], dcur[kt][3]);
-            const bool has_hidden = l >= 1, has_in = (l == 4 || l == 0);
             if (has_hidden) {
                 relu_lo = 0; relu_hi = 0;
 #pragma unroll
@@ -493,17 +503,22 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                     sm.X[warp][eb + 3 + kc][lane] = movt4(cv);
                 }
             }
+            }   // chain: staging
             __syncthreads();
-            // weight gradient: warp w computes output rows 16w..16w+15 of dW_l
+            // weight gradient: DW warp ob computes output rows 16ob..16ob+15 of dW_l
+            if (!chain) {
             if (l == 4) {
                 dw_slice<0, 8, true>(sm, warp, scr + kSiteL4A, it == 0, sm.bias_acc[4], lane);
-                dw_slice<8, 11, false>(sm, warp, scr + kSiteL4B, it == 0, nullptr, lane);
+                dw_slice<8, 6, false, 11, 0>(sm, warp, scr + kSiteL4B, it == 0, nullptr, lane);
+                dw_slice<14, 5, false, 11, 6>(sm, warp, scr + kSiteL4B, it == 0, nullptr, lane);
             } else if (l == 0) {
-                dw_slice<0, 11, true>(sm, warp, scr + kSiteL0, it == 0, sm.bias_acc[0], lane);
+                dw_slice<0, 6, true, 11, 0>(sm, warp, scr + kSiteL0, it == 0, sm.bias_acc[0], lane);
+                dw_slice<6, 5, false, 11, 6>(sm, warp, scr + kSiteL0, it == 0, nullptr, lane);
             } else {
                 const int site = l == 5 ? kSiteL5 : (l == 3 ? kSiteL3 : (l == 2 ? kSiteL2 : kSiteL1));
                 dw_slice<0, 8, true>(sm, warp, scr + site, it == 0, sm.bias_acc[l], lane);
             }
+            }   // DW warps
             // delta of the previous layer (own rows) and warp-code gradients, transposed weights from the ring
             // (A fragments come from the staged copy: a runtime k index into the register array would go to local memory)
             auto da = [&](int kt, uint32_t(&a)[4]) {
@@ -511,7 +526,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                 a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
             };
             uint32_t dnext[8][4];
-            if (l >= 1) {
+            if (chain && l >= 1) {
                 const int j0 = l == 5 ? jT_L5 : (l == 4 ? jT_L4H : (l == 3 ? jT_L3 : (l == 2 ? jT_L2 : jT_L1)));
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -528,7 +543,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                     }
                 }
             }
-            if (has_in) {
+            if (chain && has_in) {
                 const int j0 = l == 4 ? jT_L4C : jT_L0C;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -561,7 +576,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
                 }
             }
             __syncthreads();   // D / X are rewritten by the next layer
-            if (l >= 1) {
+            if (chain && l >= 1) {
 #pragma unroll
                 for (int kt = 0; kt < 8; ++kt)
 #pragma unroll
@@ -570,7 +585,7 @@ __global__ void __launch_bounds__(256, 1) deform_bwd_kernel(const __grid_constan
         }
     }
     __syncthreads();
-    for (int i = tid; i < 6 * 128; i += 256) {
+    for (int i = tid; i < 6 * 128; i += kDbThreads) {
         const float v = (&sm.bias_acc[0][0])[i];
         if (v != 0.f) atomicAdd(K.B.d_stem_b + i, v * inv_ls);
     }
@@ -623,7 +638,7 @@ extern "C" int nsb_deform_backward(const nsb_field_params *params, const nsb_fie
     }
     const int64_t n_tiles = (samples->n_samples + NSB_TILE - 1) / NSB_TILE;
     const int n_ctas = (int)std::min<int64_t>(n_tiles, g_db_sms);
-    deform_bwd_kernel<<<n_ctas, 256, smem, (cudaStream_t)stream>>>(K);
+    deform_bwd_kernel<<<n_ctas, kDbThreads, smem, (cudaStream_t)stream>>>(K);
     int rc = check_launch("deform_bwd_kernel");
     if (rc) return rc;
     DwReduceArgs R;
