@@ -16,6 +16,7 @@ from nersemble_b200.nerfstudio_shim import RayBundle
 ap = argparse.ArgumentParser()
 ap.add_argument("--height", type=int, default=272); ap.add_argument("--width", type=int, default=480)
 ap.add_argument("--frames", type=int, default=4); ap.add_argument("--log2T", type=int, default=19)
+ap.add_argument("--chunk", type=int, default=1 << 19, help="eval_num_rays_per_chunk (reference scripts pass n_rays_eval; the loop is host-bound, 180 GB of HBM allow large chunks)")
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lrank = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lrank); dev = torch.device("cuda", lrank)
@@ -23,7 +24,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)                                  # identical replicas on every rank
 T = 24
-m = make_model(T=T, log2T=args.log2T, eval_num_rays_per_chunk=1 << 15).to(dev).eval()
+m = make_model(T=T, log2T=args.log2T, eval_num_rays_per_chunk=args.chunk).to(dev).eval()
 with torch.no_grad():
     m.field.hash_ensemble.tables.uniform_(-0.5, 0.5)
     m.time_embedding.weight.normal_(0, 0.18); m.time_embedding_deformation.weight.normal_(0, 0.09)
@@ -46,13 +47,13 @@ def camera_rays(frame):
 
 def render(o, d, t):
     n = o.shape[0]
-    outs, samples = [], 0
+    outs, samples = [], torch.zeros((), dtype=torch.long, device=dev)      # counted on the device: no extra host sync per chunk
     for i in range(0, n, m.config.eval_num_rays_per_chunk):
         sl = slice(i, i + m.config.eval_num_rays_per_chunk)
         rb = RayBundle(origins=o[sl], directions=d[sl], pixel_area=torch.ones_like(t[sl]),
                        camera_indices=torch.zeros_like(t[sl], dtype=torch.long), times=t[sl])
         out = m.get_outputs(rb)
-        outs.append(out["rgb"]); samples += int(out["num_samples_per_ray"].sum())
+        outs.append(out["rgb"]); samples += out["num_samples_per_ray"].sum()
     return torch.cat(outs), samples
 
 
@@ -60,7 +61,8 @@ max_diff, total_samples = 0.0, 0
 torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 with torch.no_grad():
-    render(*[x[:4096] for x in camera_rays(0)])        # warm-up
+    lo0, hi0 = shard_bounds(H * W, rank, world)
+    render(*[x[lo0:hi0] for x in camera_rays(0)])      # warm-up: one frame at the real chunk sizes (allocator, lazy module loads)
     if world > 1: dist.barrier()
     torch.cuda.synchronize(); e0.record()
     frames = []
@@ -68,13 +70,14 @@ with torch.no_grad():
         o, d, t = camera_rays(f % T)
         lo, hi = shard_bounds(H * W, rank, world)
         rgb_local, ns = render(o[lo:hi], d[lo:hi], t[lo:hi])
-        total_samples += ns
+        ns_dev = ns if f == 0 else ns_dev + ns
         frames.append(gather_rays(rgb_local, H * W))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if rank == 0:   # unsharded reference of the last frame: chunk boundaries differ, pixels must not
         full, _ = render(o, d, t)
         max_diff = (full - frames[-1]).abs().max().item()
+total_samples = int(ns_dev)
 tot = torch.tensor([float(total_samples), ms], device=dev, dtype=torch.float64)
 if world > 1:
     dist.all_reduce(tot[:1]); dist.all_reduce(tot[1:], op=dist.ReduceOp.MAX)
