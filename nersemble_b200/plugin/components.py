@@ -18,8 +18,8 @@ from .. import ops, packing
 def _no_autograd(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            "nersemble_b200 round 1 provides the forward path only; wrap the call in torch.no_grad() "
-            "(the backward kernels are not built yet).")
+            "the stand-alone component modules are forward-only: gradients flow through the fused model path "
+            "(NeRSembleNGPModel.get_outputs in training mode); wrap this call in torch.no_grad().")
 
 
 class GenericScheduler(nn.Module):
