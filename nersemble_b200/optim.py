@@ -51,6 +51,10 @@ class FusedFieldsAdam(torch.optim.Adam):
     def step(self, closure=None):
         work = []
         for he, p, group in self._ensembles:
+            if p.grad is not None and he.pending_table_grad is not None:
+                # a dense .grad AND a parked rank-1 gradient (second backward before step()): they may carry different
+                # scale factors (all-reduce averaging), so fold the parked one into the dense tensor first
+                he.materialize_pending(scale=float(self.pending_grad_scale))
             work.append((he, p, group, p.grad, he.pending_table_grad))
             p.grad = None                   # torch's Adam skips parameters without .grad
         loss = super().step(closure)
