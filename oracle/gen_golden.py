@@ -210,11 +210,71 @@ def loss_case(name):
     save(name, tensors, dict(name=name, eps_depth=0.35, render_case=name + "_render"))
 
 
+def grad_case(name):
+    """Parameter GRADIENTS of one full training step computed by torch autograd through the unmodified reference glue
+    (NeRSembleNGPModel.get_outputs -> get_loss_dict -> backward) on the CPU stand-ins: pins the backward kernels and
+    the oracle's own autograd.  Samples are deterministic (sampler.eval(): no jitter, no pre-pass); all six losses."""
+    from oracle.tp.tcnn_cpu import Precision
+    from oracle import pipeline as pl
+    from nerfstudio.cameras.rays import RayBundle
+    Precision.mode = "none"; Precision.autocast = False
+    knobs = dict(seed=19980801, n_timesteps=4, log2_hashmap_size=14, table_scale=0.5, time_std_scale=100.0, deform_last_scale=0.02)
+    P = pl.random_params(**knobs)
+    model = build_reference_model(P, 4, 14)
+    w_hash, w_deform, R = 32.0, 5.5, 48
+    model.sched_window_hash_encodings.value = w_hash
+    model.sched_window_deform.value = w_deform
+    o, d, times, cams = ring_rays(R, 21)
+    rb = RayBundle(origins=o, directions=d, pixel_area=torch.ones(R, 1), camera_indices=cams, times=times)
+    occ = blob_grid(3)
+    model.occupancy_grid.binaries[0] = occ
+    model.occupancy_grid.occs.copy_(occ.flatten().float() * 0.05)
+    model.train(True)
+    model.sampler.eval()
+    g = torch.Generator().manual_seed(11)
+    batch = {"image": torch.rand((R, 3), generator=g), "alpha_map": torch.randint(0, 256, (R, 1), generator=g).float(),
+             "depth_maps": torch.where(torch.rand((R,), generator=g) < 0.8, 7.5 + 2.0 * torch.rand((R,), generator=g), torch.zeros(R))}
+    batch["alpha_map"][:5] = 255.0
+    model.sched_eps_depth.value = 0.35
+    out = model.get_outputs(rb)
+    ld = model.get_loss_dict(out, batch)
+    sum(ld.values()).backward()
+    from oracle.pipeline import tables_from_tcnn
+    gt = tables_from_tcnn([m.params.grad for m in model.field.hash_ensemble.hash_encodings])     # [entries, 32, 2]
+    # the dense table gradient is 63 MB (8 M non-zeros): the fixture keeps a seeded random sample of 400 k elements
+    # (zeros included), the global sums, and the squared norm per level
+    flat = gt.reshape(-1)
+    pick = torch.randint(0, flat.numel(), (400_000,), generator=torch.Generator().manual_seed(5))
+    from oracle.tp.tcnn_cpu import hashgrid_levels
+    lv = hashgrid_levels(16, 14, 16, 1.4472692012786865)
+    offs = [int(v) for v in lv.offset]          # [L + 1], entry units
+    per_level = torch.stack([(gt[offs[l]:offs[l + 1]].double() ** 2).sum() for l in range(16)])
+    se3 = model.deformation_field.se3_field
+    tensors = {"origins": o, "directions": d, "times": times, "camera_indices": cams,
+               "ray_indices": out["ray_indices"][0], "tables_grad_sample": flat[pick],
+               "tables_grad_sums": torch.stack([flat.double().sum(), (flat.double() ** 2).sum(), flat.double().abs().sum()]),
+               "tables_grad_sq_per_level": per_level, "tables_grad_nonzeros": torch.tensor(int((flat != 0).sum())),
+               "mlp_base_grad": model.field.mlp_base.params.grad, "mlp_head_grad": model.field.mlp_head.params.grad,
+               "time_emb_grad": model.time_embedding.weight.grad, "time_emb_deform_grad": model.time_embedding_deformation.weight.grad,
+               "r_w_grad": se3.mlp_r.layers[0].weight.grad, "r_b_grad": se3.mlp_r.layers[0].bias.grad,
+               "v_w_grad": se3.mlp_v.layers[0].weight.grad, "v_b_grad": se3.mlp_v.layers[0].bias.grad}
+    for i, layer in enumerate(se3.mlp_stem.layers):
+        tensors[f"stem_w{i}_grad"] = layer.weight.grad
+        tensors[f"stem_b{i}_grad"] = layer.bias.grad
+    tensors.update({("loss_" + k): v.detach() for k, v in ld.items()})
+    tensors.update({("batch_" + k): v for k, v in batch.items()})
+    save(name, tensors, dict(name=name, knobs=knobs, R=R, w_hash=w_hash, w_deform=w_deform, grid_seed=3, rays_seed=21,
+                             eps_depth=0.35, table_entries=int(gt.shape[0])))
+
+
 def main():
     sys.path.insert(0, REF_SRC)
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle.tp import install_stubs
     install_stubs()
+    if len(sys.argv) > 1 and sys.argv[1] == "grads":     # only the gradient golden (the others are unchanged)
+        grad_case("grads_train")
+        return
     init = dict(table_scale=1e-4, time_std_scale=1.0, deform_last_scale=1e-5)
     trained = dict(table_scale=0.5, time_std_scale=100.0, deform_last_scale=1e-3)
     # BASELINE config 1: 32 rays x 64 samples, 1 timestep, no occ-grid, full-size tables
@@ -236,6 +296,7 @@ def main():
     density_case("density_fn_none", "none")
     density_case("density_fn_kernel", "kernel")
     loss_case("losses_train")
+    grad_case("grads_train")
 
 
 if __name__ == "__main__":
