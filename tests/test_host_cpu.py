@@ -171,3 +171,36 @@ def test_forward_kernel_gather_role_has_no_spill_storm():
     assert len(rows) >= 8
     for r in rows:
         assert int(r[r.index("gather") + 1]) <= 16, out
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """ABI drift guard: size and every field offset of the ctypes mirrors in _lib.py against what a C compiler makes of
+    include/nsb.h (the header is plain C; gcc is in the image)."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    pairs = {"nsb_levels": _lib.Levels, "nsb_field_params": _lib.FieldParams, "nsb_field_opts": _lib.FieldOpts,
+             "nsb_samples": _lib.Samples, "nsb_field_out": _lib.FieldOut, "nsb_field_bwd_args": _lib.FieldBwdArgs,
+             "nsb_table_adam_args": _lib.TableAdamArgs, "nsb_loss_args": _lib.LossArgs,
+             "nsb_composite_args": _lib.CompositeArgs, "nsb_deform_bwd_args": _lib.DeformBwdArgs,
+             "nsb_composite_bwd_args": _lib.CompositeBwdArgs, "nsb_march_args": _lib.MarchArgs}
+    header = open(os.path.join(ROOT, "include", "nsb.h")).read()
+    assert set(re.findall(r"^typedef struct (nsb_\w+)", header, flags=re.M)) == set(pairs)     # every struct is mirrored
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nsb.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    want = {}
+    for cname, cls in pairs.items():
+        want[(cname, "size")] = ctypes.sizeof(cls)
+        for fname, _ in cls._fields_:
+            want[(cname, fname)] = getattr(cls, fname).offset
+    got = {(a, b): int(c) for a, b, c in (l.split() for l in out.splitlines())}
+    assert got == want, {k: (got.get(k), want.get(k)) for k in set(got) | set(want) if got.get(k) != want.get(k)}
