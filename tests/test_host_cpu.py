@@ -204,3 +204,26 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
             want[(cname, fname)] = getattr(cls, fname).offset
     got = {(a, b): int(c) for a, b, c in (l.split() for l in out.splitlines())}
     assert got == want, {k: (got.get(k), want.get(k)) for k in set(got) | set(want) if got.get(k) != want.get(k)}
+
+
+def test_rank1_slot_map_for_many_timesteps():
+    """The rank-1 table-gradient scatter keys its workspace by timestep SLOT: identity for <= 32 timesteps, the batch's
+    distinct timesteps (same rounding as the kernels: round(t * (T - 1))) for longer sequences, and no rank-1 path when a
+    batch holds more than 32 distinct timesteps or per-sample blend codes are given."""
+    from types import SimpleNamespace
+    from nersemble_b200 import ops
+    dev = torch.device("cpu")
+    slot, n = ops._rank1_slots(SimpleNamespace(n_timesteps=24), dev, {})
+    assert n == 24 and torch.equal(slot, torch.arange(24, dtype=torch.int32))
+    T = 200
+    steps = torch.tensor([3, 3, 77, 199, 0, 77])
+    times = steps.float() / (T - 1)
+    slot, n = ops._rank1_slots(SimpleNamespace(n_timesteps=T), dev, {"origins": torch.zeros(6, 3), "ray_times": times})
+    assert n == 4 and slot.shape == (T,)
+    assert sorted(slot[[0, 3, 77, 199]].tolist()) == [0, 1, 2, 3] and int((slot >= 0).sum()) == 4
+    many = torch.arange(40).float() / (T - 1)
+    assert ops._rank1_slots(SimpleNamespace(n_timesteps=T), dev, {"origins": torch.zeros(40, 3), "ray_times": many}) == (None, 0)
+    assert ops._rank1_slots(SimpleNamespace(n_timesteps=24), dev, {"sample_blend_codes": torch.zeros(5, 32)}) == (None, 0)
+    # explicit positions use per-sample times
+    slot, n = ops._rank1_slots(SimpleNamespace(n_timesteps=T), dev, {"positions": torch.zeros(3, 3), "sample_times": times[:3]})
+    assert n == 2
