@@ -11,7 +11,8 @@ from .components import (HashEnsemble, HashEnsembleConfig, SE3DeformationField, 
 from .field import NeRSembleNeRFactoField
 from .sampler import NeRSembleVolumetricSampler, OccGridEstimator
 from .model import NeRSembleNGPModel, NeRSembleNGPModelConfig, BaseModelConfig
+from .occupancy_filter import filter_occupancy_grid
 
 __all__ = ["HashEnsemble", "HashEnsembleConfig", "SE3DeformationField", "SE3DeformationFieldConfig",
            "TCNNHashEncodingConfig", "GenericScheduler", "NeRSembleNeRFactoField", "NeRSembleVolumetricSampler",
-           "OccGridEstimator", "NeRSembleNGPModel", "NeRSembleNGPModelConfig", "BaseModelConfig"]
+           "OccGridEstimator", "NeRSembleNGPModel", "NeRSembleNGPModelConfig", "BaseModelConfig", "filter_occupancy_grid"]

@@ -1,6 +1,7 @@
 """Plugin surface on CPU: state_dict / param-group compatibility with the real reference model, config
 surface, scheduler semantics, loss restatement vs the reference-glue golden, no-CPU-fallback behaviour."""
 import json
+import numpy as np
 import os
 
 import pytest
@@ -151,3 +152,43 @@ def test_fused_fields_adam_host_logic_and_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="CUDA"):
         opt.step()
     assert not torch.equal(base.detach(), before)                 # the torch part of the step did run
+
+
+def test_filter_occupancy_grid_keeps_the_largest_component():
+    """util/connected_components.py:102-139 semantics: blur, threshold, 6-connected labelling, largest component (dilated),
+    AND into binaries[0] -- against a brute-force flood fill on a small case."""
+    from nersemble_b200.plugin.occupancy_filter import extract_top_k_connected_component, filter_occupancy_grid
+    m = make_model()
+    og = m.occupancy_grid
+    res = og.binaries.shape[1]
+    dens = torch.full((res, res, res), -6.0)
+    dens[10:40, 10:40, 10:40] = 6.0              # big blob
+    dens[80:86, 80:86, 80:86] = 6.0              # floater
+    dens[40:80, 24, 24] = 6.0                    # a one-voxel-thin bridge towards the floater: removed by the blur
+    og.occs.copy_(dens.reshape(-1))
+    og.binaries[:] = True
+    filter_occupancy_grid(og, threshold=0.6, sigma_thinning=1, sigma_erosion=2)
+    b = og.binaries[0]
+    assert b[20, 20, 20] and not b[83, 83, 83] and not b[60, 24, 24]
+    assert b[8, 20, 20]                           # dilated beyond the blob's faces ...
+    assert not b[100, 100, 100]                   # ... but still local
+    # component ordering: K = 2 returns [second largest, largest (dilated)]
+    two = extract_top_k_connected_component(dens.numpy(), threshold=0.6, sigma_thinning=0.5, sigma_erosion=1, K=2)
+    assert two[0][83, 83, 83] == 1 and two[0][20, 20, 20] == 0 and two[1][20, 20, 20] == 1
+    # brute-force check of the labelling step on a tiny random grid (no blur): sizes of 6-connected components
+    rng = np.random.default_rng(0)
+    small = rng.random((9, 9, 9)) > 0.6
+    from scipy import ndimage
+    lab, n = ndimage.label(small, structure=ndimage.generate_binary_structure(3, 1))
+    seen = np.zeros_like(small); sizes = []
+    for start in zip(*np.nonzero(small)):
+        if seen[start]: continue
+        stack, cnt = [start], 0; seen[start] = True
+        while stack:
+            x, y, z = stack.pop(); cnt += 1
+            for dx, dy, dz in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+                p = (x + dx, y + dy, z + dz)
+                if all(0 <= p[i] < 9 for i in range(3)) and small[p] and not seen[p]:
+                    seen[p] = True; stack.append(p)
+        sizes.append(cnt)
+    assert sorted(sizes) == sorted(np.bincount(lab.ravel())[1:].tolist())
