@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NSB_VERSION 100
+#define NSB_VERSION 200
 #define NSB_MAX_LEVELS 16
 #define NSB_MEMBERS 32        /* ensemble members (hash_ensemble_config.n_hash_encodings) */
 #define NSB_FEATS 2           /* features per member per level */
@@ -60,12 +60,12 @@ typedef struct nsb_levels {
 /* Parameters of the field, in the native layouts (all DEVICE pointers). */
 typedef struct nsb_field_params {
     const void *tables;        /* __half [total_entries][32 members][2 feats]: 128 B per entry */
-    const void *deform_packed; /* fp16 deformation weights in MMA-B fragment order (python: pack_deform) */
     const float *deform_bias;  /* float [6*128 + 8]: stem biases, then v_bias(3), r_bias(3), 0, 0 */
-    const void *deform_packed_tb;   /* same weights WITHOUT the warp-code columns of layers 0 and 4 (python: pack_deform_tb) */
-    const float *deform_code_bias;  /* float [n_timesteps][2][128]: W_code(layer 0|4) . warp_code[t] + bias, fp32.  With
-                                       both set, table-indexed warp codes cost no tensor work (-26 % MACs); per-sample
-                                       warp codes (nsb_samples.sample_warp_codes) use deform_packed. */
+    const void *deform_packed_tb;   /* fp16 deformation weights in MMA-B fragment order WITHOUT the warp-code columns of
+                                       layers 0 and 4 (python: pack_deform_tb; nsb_deform_packed_bytes() bytes) */
+    const float *deform_code_bias;  /* float [n_timesteps][2][128]: W_code(layer 0|4) . warp_code[t] + bias, fp32: the
+                                       warp code only depends on the timestep, so its columns cost no tensor work
+                                       (-26 % MACs).  Per-sample warp codes (component API): nsb_samples.sample_code_bias. */
     const void *field_packed;  /* fp16 mlp_base + mlp_head weights in MMA-B fragment order */
     const void *warp_codes;    /* __half [n_timesteps][128]  (time_embedding_deformation) */
     const float *blend_codes;  /* float  [n_timesteps][32]   (time_embedding) */
@@ -103,7 +103,8 @@ typedef struct nsb_samples {
     const float *sample_directions; /* [n_samples][3] or NULL (density_fn uses ones: nersemble_nerfacto_field.py:240) */
     /* optional per-sample conditioning overriding the time-embedding tables (component APIs) */
     const float *sample_blend_codes; /* float  [n_samples][32] or NULL */
-    const void *sample_warp_codes;   /* __half [n_samples][128] or NULL */
+    const float *sample_code_bias;   /* float [n_samples][2][128] or NULL: W_code(layer 0|4) . warp_code[sample] + bias
+                                        (python: packing.deform_code_bias on the per-sample codes); <= 2^24 samples */
 } nsb_samples;
 
 typedef struct nsb_field_out {
@@ -310,6 +311,17 @@ int nsb_march_occupancy(const nsb_march_args *args, void *stream);
 int nsb_visibility_mask(const int64_t *packed_info, int64_t n_rays, const float *t_starts, const float *t_ends,
                         const float *sigma, float early_stop_eps, float alpha_thre, uint8_t *mask,
                         int32_t *kept_counts, void *stream);
+
+/* Occupancy-grid EMA update (nerfacc 0.5.2 estimators/occ_grid.py OccGridEstimator._update, called by
+ * models/nersemble_instant_ngp.py:184-196 every 16 steps):
+ *   occs[cell] = max(occs[cell] * ema_decay, occ_new[i])   for the evaluated cells cell_ids[i]
+ *   thre = min(mean(occs[occs >= 0]), occ_thre);  binaries = occs > thre
+ * cell_ids may repeat (uniform + occupied sampling): upstream's indexed assignment keeps the value of an unspecified
+ * one of the duplicates; here a repeated cell deterministically gets max(old * decay, max_i occ_new[i]) -- the result
+ * of the duplicate with the largest occ_new writing last.  scratch: float [n_cells] + double [2], caller-provided. */
+int nsb_occ_update(float *occs, uint8_t *binaries, int64_t n_cells, const int64_t *cell_ids, const float *occ_new,
+                   int64_t n, float ema_decay, float occ_thre, void *scratch, void *stream);
+size_t nsb_occ_update_scratch_bytes(int64_t n_cells);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ class Levels(C.Structure):
 
 
 class FieldParams(C.Structure):
-    _fields_ = [("tables", C.c_void_p), ("deform_packed", C.c_void_p), ("deform_bias", C.c_void_p),
+    _fields_ = [("tables", C.c_void_p), ("deform_bias", C.c_void_p),
                 ("deform_packed_tb", C.c_void_p), ("deform_code_bias", C.c_void_p),
                 ("field_packed", C.c_void_p), ("warp_codes", C.c_void_p), ("blend_codes", C.c_void_p),
                 ("n_timesteps", C.c_int32), ("aabb", C.c_float * 6), ("levels", Levels)]
@@ -41,7 +41,7 @@ class Samples(C.Structure):
                 ("origins", C.c_void_p), ("directions", C.c_void_p), ("ray_times", C.c_void_p),
                 ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("ray_indices", C.c_void_p),
                 ("positions", C.c_void_p), ("sample_times", C.c_void_p), ("sample_directions", C.c_void_p),
-                ("sample_blend_codes", C.c_void_p), ("sample_warp_codes", C.c_void_p)]
+                ("sample_blend_codes", C.c_void_p), ("sample_code_bias", C.c_void_p)]
 
 
 class FieldOut(C.Structure):
@@ -134,6 +134,9 @@ SYMBOLS = {
     "nsb_march_occupancy": (C.c_int, [C.POINTER(MarchArgs), C.c_void_p]),
     "nsb_visibility_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsb_occ_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                 C.c_float, C.c_void_p, C.c_void_p]),
+    "nsb_occ_update_scratch_bytes": (C.c_size_t, [C.c_int64]),
 }
 
 _lib = None
@@ -153,7 +156,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.nsb_version() != 100:
+    if lib.nsb_version() != 200:
         raise RuntimeError(f"libnsb version mismatch: {lib.nsb_version()}")
     _lib = lib
     return lib

@@ -623,7 +623,7 @@ extern "C" int nsb_deform_backward(const nsb_field_params *params, const nsb_fie
     }
     for (int l = 0; l < 6; ++l)
         if (!args->d_stem_w[l]) { set_error("nsb_deform_backward: d_stem_w[%d] missing", l); return 1; }
-    if (samples->sample_warp_codes) { set_error("nsb_deform_backward: per-sample warp codes are not supported"); return 1; }
+    if (samples->sample_code_bias) { set_error("nsb_deform_backward: per-sample warp codes are not supported"); return 1; }
     if (!args->dw_workspace) { set_error("nsb_deform_backward: dw_workspace missing (nsb_deform_bwd_workspace_bytes)"); return 1; }
     db_sms();
     DeformBwdKArgs K;

@@ -8,19 +8,9 @@
 //   field_components/hash_ensemble.py:93-158                HashEnsemble.forward (8 tcnn grids + einsum)
 //   fields/nersemble_nerfacto_field.py:250-301,303-383      get_density / get_outputs (tcnn MLPs)
 //
-// Work decomposition.  A CTA has 8 consumer warps + 1 producer warp (288 threads, 2 CTAs/SM).
-// A tile is 128 consecutive samples; consumer warp w owns rows 16w..16w+15 END TO END, so the
-// only cross-warp coupling is the deformation-weight ring:
-//   * the 252 KB of fp16 deformation weights do not fit in shared memory; the producer warp streams
-//     them from L2 in 8 KB chunks with cp.async.bulk (TMA 1-D, UBLKCP) through a 4-stage mbarrier
-//     ring; weights are pre-packed on the host in mma.sync B-fragment order so a warp reads a
-//     fragment pair with one conflict-free 512 B LDS.128.
-//   * activations never touch shared memory: the m16n8k16 accumulator layout of two adjacent
-//     n-tiles IS the A-fragment layout of the next layer's k-tile (bias+ReLU+pack in registers).
-//   * the gather maps a 128 B table line (32 members x 2 feats fp16) onto 8 lanes x 16 B: one
-//     warp-wide LDG.128 fetches 4 corner lines, 2 loads cover the 8 corners of a level; lanes
-//     hold (corner-group, member-group) partial sums that a 31-shuffle transposing butterfly
-//     reduces so that lane i ends with output feature i.
+// Work decomposition: see the comment block above field_kernel_ws (persistent, one CTA per SM, warp-specialised:
+// tensor warps run the deformation MLP and the density/colour MLPs on mma.sync with the deformation weights
+// streamed through a cp.async.bulk ring; gather warps do nothing but the 128-byte-line hash gather).
 #include <algorithm>
 #include <cstdlib>
 
@@ -31,33 +21,11 @@
 
 namespace nsb {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kSlabBytes = 2048;  // one k-tile (16) x 64 output columns, fragment order
 constexpr int kChunkSlabs = 4;
 constexpr int kChunkBytes = kSlabBytes * kChunkSlabs;
 constexpr int kStages = 4;
-// slab index (within a tile) of each layer-half; heads use 8 x 512 B = 2 slabs
-constexpr int kJ_L0 = 0;                 // 2 x 11
-constexpr int kJ_L1 = kJ_L0 + 22;        // 2 x 8
-constexpr int kJ_L2 = kJ_L1 + 16;
-constexpr int kJ_L3 = kJ_L2 + 16;
-constexpr int kJ_L4 = kJ_L3 + 16;        // 2 x 19
-constexpr int kJ_L5 = kJ_L4 + 38;        // 2 x 8
-constexpr int kJ_HEADS = kJ_L5 + 16;     // 124
-constexpr int kNumSlabs = kJ_HEADS + 2;  // 126
-constexpr int kNumChunks = (kNumSlabs + kChunkSlabs - 1) / kChunkSlabs;  // 32
-static_assert(kNumChunks % (2 * kStages) == 0, "stage parity must be tile-invariant");
-static_assert(kJ_HEADS % kChunkSlabs == 0, "heads must start a chunk");
-constexpr int kDeformPackedBytes = kNumSlabs * kSlabBytes;  // 258048
 constexpr int kBiasFloats = 6 * 128 + 8;
-#ifndef NSB_GATHER_LB
-#define NSB_GATHER_LB 4
-#endif
-#ifndef NSB_GATHER_MMA
-#define NSB_GATHER_MMA 1
-#endif
-constexpr int kGatherLB = NSB_GATHER_LB;  // levels per load batch: 2*LB LDG.128 in flight per lane
 
 struct FieldArgs {
     nsb_field_params P;
@@ -65,72 +33,7 @@ struct FieldArgs {
     nsb_samples S;
     nsb_field_out out;
     float aabb_size[3];
-    uint32_t stagger_ns;   // second-wave CTAs start this much later (de-phases the two CTAs of an SM)
 };
-
-struct alignas(16) WarpScratch {
-    float pos[16][4];       // world position xyz, w = timestep (int bits)
-    float xs[16][4];        // normalised warped position xyz, w = selector
-    float dir[16][4];       // ray direction xyz
-    uint4 enc[3][32];       // posenc A fragments (k-tile, lane)
-    union {
-        uint4 act[8][32];   // hidden activations as A fragments (k-tile, lane): lane-private "spill" area
-        __half feat[16 * kFeatStride];  // blended hash features (after the deformation stage)
-    };
-};
-
-struct alignas(128) Smem {
-    uint8_t ring[kStages][kChunkBytes];
-    uint4 field_w[kFieldPackedU4];
-    float bias[kBiasFloats];
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
-    WarpScratch ws[kConsumerWarps];
-};
-
-// -------------------------------------------------------------------------------------------
-// one N-half (64 output columns) of a deformation layer, weights from the ring
-// -------------------------------------------------------------------------------------------
-template <class AFn>
-__device__ __forceinline__ void ring_gemm(float (&acc)[8][4], const int j0, const int KT, AFn &&afn, Smem &sm, int lane) {
-    static_assert(kChunkSlabs == 4 && kStages == 4, "index arithmetic below assumes 4x4");
-#pragma unroll 2
-    for (int kt = 0; kt < KT; ++kt) {
-        const int j = j0 + kt;
-        const int chunk = j >> 2, stage = chunk & 3;
-        if ((j & 3) == 0) mbar_wait<20>(&sm.full[stage], (chunk >> 2) & 1);
-        uint32_t a[4];
-        afn(kt, a);
-        const uint4 *slab = reinterpret_cast<const uint4 *>(&sm.ring[stage][(j & 3) * kSlabBytes]);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            uint4 b = slab[p * 32 + lane];
-            mma16816(acc[2 * p], a, b.x, b.y);
-            mma16816(acc[2 * p + 1], a, b.z, b.w);
-        }
-        if ((j & 3) == 3) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[stage]);
-        }
-    }
-}
-
-// bias + ReLU + pack this half's 64 columns into the next layer's A fragments (k-tiles 4*HALF..4*HALF+3)
-template <int HALF>
-__device__ __forceinline__ void relu_pack(const float (&acc)[8][4], uint4 (&nxt)[4], const float *bias, int q) {
-#pragma unroll
-    for (int kt = 0; kt < 4; ++kt) {
-        uint32_t r[4];
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            const int nt = 2 * kt + o;
-            float2 bb = *reinterpret_cast<const float2 *>(&bias[HALF * 64 + nt * 8 + 2 * q]);
-            r[o * 2 + 0] = pack_h2(fmaxf(acc[nt][0] + bb.x, 0.f), fmaxf(acc[nt][1] + bb.y, 0.f));
-            r[o * 2 + 1] = pack_h2(fmaxf(acc[nt][2] + bb.x, 0.f), fmaxf(acc[nt][3] + bb.y, 0.f));
-        }
-        nxt[kt] = make_uint4(r[0], r[1], r[2], r[3]);
-    }
-}
 
 __device__ __forceinline__ void zero_acc(float (&acc)[8][4]) {
 #pragma unroll
@@ -159,404 +62,6 @@ __device__ __forceinline__ void se3_apply(const float p[3], const float r[3], co
     for (int k = 0; k < 3; ++k) {
         float o = (p[k] + f1 * rp[k] + f2 * rrp[k]) + (v[k] + f2 * rv[k] + f3 * rrv[k]);
         out[k] = isnan(o) ? p[k] : o;
-    }
-}
-
-// effective blend weights of this lane's 4 members for a sample (hash_ensemble.py:119-139 folded)
-__device__ __forceinline__ void load_cw(const FieldArgs &A, const float *code_row, int mg, float (&cw)[4]) {
-    float4 c = __ldg(reinterpret_cast<const float4 *>(code_row) + mg);
-    cw[0] = fmaf(c.x, A.O.cw_scale[4 * mg + 0], A.O.cw_bias[4 * mg + 0]);
-    cw[1] = fmaf(c.y, A.O.cw_scale[4 * mg + 1], A.O.cw_bias[4 * mg + 1]);
-    cw[2] = fmaf(c.z, A.O.cw_scale[4 * mg + 2], A.O.cw_bias[4 * mg + 2]);
-    cw[3] = fmaf(c.w, A.O.cw_scale[4 * mg + 3], A.O.cw_bias[4 * mg + 3]);
-}
-
-// -------------------------------------------------------------------------------------------
-// the fused kernel
-// -------------------------------------------------------------------------------------------
-template <bool DEFORM, bool FIELD, bool HEAD>
-__global__ void __launch_bounds__(kThreads, 2) field_kernel(const __grid_constant__ FieldArgs A) {
-    // NOTE: no integer round-trip on the pointer, or the compiler loses the shared address space and
-    // emits generic LD/ST instead of LDS/STS (seen in profiles/r1b).
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n = A.S.n_samples;
-    const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
-
-    // ---- one-time setup ----
-    if (FIELD) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(A.P.field_packed);
-        for (int i = tid; i < kFieldPackedU4; i += kThreads) sm.field_w[i] = __ldg(src + i);
-    }
-    if (DEFORM) {
-        for (int i = tid; i < kBiasFloats; i += kThreads) sm.bias[i] = __ldg(A.P.deform_bias + i);
-        if (tid == 0) {
-            for (int s = 0; s < kStages; ++s) {
-                mbar_init(&sm.full[s], 1);
-                mbar_init(&sm.empty[s], kConsumerWarps);
-            }
-            mbar_fence_init();
-        }
-    }
-    __syncthreads();
-    // The two co-resident CTAs of an SM run identical tile sequences and would stay in lock-step
-    // (both in the tensor-bound deformation phase, then both in the memory-bound gather).  Starting the
-    // second wave half a tile later keeps one CTA gathering while the other deforms.
-    if (DEFORM && A.stagger_ns && blockIdx.x >= (gridDim.x + 1) / 2) {
-        uint64_t t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do {
-            __nanosleep(1000);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (t1 - t0 < A.stagger_ns);
-    }
-
-    // ---- producer warp: stream the deformation weights through the ring, once per tile ----
-    if (warp == kConsumerWarps) {
-        if (DEFORM && lane == 0) {
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(A.P.deform_packed);
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < kNumChunks; ++c) {
-                    const int s = c % kStages;
-                    mbar_wait<64>(&sm.empty[s], ((c / kStages) & 1) ^ 1);
-                    const uint32_t bytes = (c == kNumChunks - 1) ? (kNumSlabs - c * kChunkSlabs) * kSlabBytes : kChunkBytes;
-                    mbar_expect_tx(&sm.full[s], bytes);
-                    bulk_g2s(sm.ring[s], src + (size_t)c * kChunkBytes, bytes, &sm.full[s]);
-                }
-            }
-        }
-        return;
-    }
-
-    WarpScratch &ws = sm.ws[warp];
-    const int g = lane >> 2, q = lane & 3;
-    const float amin0 = A.P.aabb[0], amin1 = A.P.aabb[1], amin2 = A.P.aabb[2];
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * NSB_TILE + warp * 16;
-        __syncwarp();  // previous tile's readers of ws are done
-        // ---- stage 0: per-row inputs (lanes 0..15 own one row each) ----
-        if (lane < 16) {
-            const int64_t s = row0 + lane;
-            float px = 0.f, py = 0.f, pz = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f, tt = 0.f;
-            if (s < n) {
-                if (A.S.origins != nullptr) {
-                    const int ri = A.S.ray_indices[s];
-                    const float t0 = A.S.t_starts[s], t1 = A.S.t_ends[s];
-                    const float mid = __fadd_rn(t0, t1);
-                    ddx = A.S.directions[3 * (int64_t)ri + 0];
-                    ddy = A.S.directions[3 * (int64_t)ri + 1];
-                    ddz = A.S.directions[3 * (int64_t)ri + 2];
-                    // Frustums.get_positions: o + d*(ts+te)/2 (no fma: bit-exact to the oracle)
-                    px = __fadd_rn(A.S.origins[3 * (int64_t)ri + 0], __fmul_rn(__fmul_rn(ddx, mid), 0.5f));
-                    py = __fadd_rn(A.S.origins[3 * (int64_t)ri + 1], __fmul_rn(__fmul_rn(ddy, mid), 0.5f));
-                    pz = __fadd_rn(A.S.origins[3 * (int64_t)ri + 2], __fmul_rn(__fmul_rn(ddz, mid), 0.5f));
-                    if (A.S.ray_times) tt = A.S.ray_times[ri];
-                } else {
-                    px = A.S.positions[3 * s + 0];
-                    py = A.S.positions[3 * s + 1];
-                    pz = A.S.positions[3 * s + 2];
-                    ddx = ddy = ddz = 1.0f;  // density_fn builds dummy frustums with direction ones
-                    if (A.S.sample_directions) {
-                        ddx = A.S.sample_directions[3 * s + 0]; ddy = A.S.sample_directions[3 * s + 1];
-                        ddz = A.S.sample_directions[3 * s + 2];
-                    }
-                    if (A.S.sample_times) tt = A.S.sample_times[s];
-                }
-            }
-            // timesteps = round(t*(T-1)) half-to-even (nersemble_instant_ngp.py:249,303)
-            int ts = __float2int_rn(__fmul_rn(tt, (float)(A.P.n_timesteps - 1)));
-            ts = min(max(ts, 0), A.P.n_timesteps - 1);
-            ws.pos[lane][0] = px; ws.pos[lane][1] = py; ws.pos[lane][2] = pz; ws.pos[lane][3] = __int_as_float(ts);
-            ws.dir[lane][0] = ddx; ws.dir[lane][1] = ddy; ws.dir[lane][2] = ddz; ws.dir[lane][3] = 0.f;
-        }
-        __syncwarp();
-
-        // ---- stage 1: deformation field ----
-        if (DEFORM) {
-            // normalised positions of the two rows this lane contributes fragments for
-            float pn[2][3];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r = g + 8 * h;
-                pn[h][0] = __fdiv_rn(__fsub_rn(ws.pos[r][0], amin0), A.aabb_size[0]);
-                pn[h][1] = __fdiv_rn(__fsub_rn(ws.pos[r][1], amin1), A.aabb_size[1]);
-                pn[h][2] = __fdiv_rn(__fsub_rn(ws.pos[r][2], amin2), A.aabb_size[2]);
-            }
-            // windowed posenc directly in A-fragment layout.  Column pairs (2i, 2i+1) =
-            // (sin, cos)(2*pi*x_d*2^j)*win_j for i = d*7+j < 21; pair 21 = (2pi x, 2pi y);
-            // pair 22 = (2pi z, 0); pair 23 = 0.  (windowed_nerf_encoding.py:48-73, permuted;
-            // the weight packer applies the same permutation.)
-#pragma unroll
-            for (int kt = 0; kt < 3; ++kt) {
-#pragma unroll
-                for (int hi = 0; hi < 2; ++hi) {
-                    const int i = kt * 8 + hi * 4 + q;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float e0 = 0.f, e1 = 0.f;
-                        if (i < 21) {
-                            const int d = i / 7, j = i - d * 7;
-                            const float arg = (6.283185307179586f * pn[h][d]) * (float)(1 << j);
-                            const float wj = A.O.pe_window[j];
-                            e0 = wj * sinf(arg);
-                            // the reference computes the cosine half as sin(arg + pi/2) in fp32 (:54)
-                            e1 = wj * sinf(arg + 1.5707963267948966f);
-                        } else if (i == 21) {
-                            e0 = 6.283185307179586f * pn[h][0];
-                            e1 = 6.283185307179586f * pn[h][1];
-                        } else if (i == 22) {
-                            e0 = 6.283185307179586f * pn[h][2];
-                        }
-                        reinterpret_cast<uint32_t *>(&ws.enc[kt][lane])[hi * 2 + h] = pack_h2(e0, e1);
-                    }
-                }
-            }
-            __syncwarp();
-            const int ts0 = __float_as_int(ws.pos[g][3]), ts1 = __float_as_int(ws.pos[g + 8][3]);
-            const __half *code0, *code1;
-            if (A.S.sample_warp_codes) {
-                const int64_t sa = min(row0 + g, n - 1), sb = min(row0 + g + 8, n - 1);
-                code0 = reinterpret_cast<const __half *>(A.S.sample_warp_codes) + sa * NSB_WARP_CODE_DIM;
-                code1 = reinterpret_cast<const __half *>(A.S.sample_warp_codes) + sb * NSB_WARP_CODE_DIM;
-            } else {
-                code0 = reinterpret_cast<const __half *>(A.P.warp_codes) + (size_t)ts0 * NSB_WARP_CODE_DIM;
-                code1 = reinterpret_cast<const __half *>(A.P.warp_codes) + (size_t)ts1 * NSB_WARP_CODE_DIM;
-            }
-            auto enc_a = [&](int kt, uint32_t(&a)[4]) {
-                const uint4 v = ws.enc[kt][lane];
-                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-            };
-            auto code_a = [&](int kc, uint32_t(&a)[4]) {
-                a[0] = __ldg(reinterpret_cast<const uint32_t *>(code0 + kc * 16 + 2 * q));
-                a[1] = __ldg(reinterpret_cast<const uint32_t *>(code1 + kc * 16 + 2 * q));
-                a[2] = __ldg(reinterpret_cast<const uint32_t *>(code0 + kc * 16 + 2 * q + 8));
-                a[3] = __ldg(reinterpret_cast<const uint32_t *>(code1 + kc * 16 + 2 * q + 8));
-            };
-            auto in_a = [&](int kt, uint32_t(&a)[4]) {
-                if (kt < 3) enc_a(kt, a); else code_a(kt - 3, a);
-            };
-            // hidden activations live in ws.act in A-fragment order; the C-fragment -> A-fragment
-            // mapping is lane-local, so this is a lane-private, conflict-free register spill area.
-            auto hid_a = [&](int kt, uint32_t(&a)[4]) {
-                const uint4 v = ws.act[kt][lane];
-                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-            };
-            auto skip_a = [&](int kt, uint32_t(&a)[4]) {
-                if (kt < 8) hid_a(kt, a); else in_a(kt - 8, a);
-            };
-            float acc[8][4];
-            uint4 lo[4], hi4[4];
-            auto commit = [&]() {
-#pragma unroll
-                for (int kt = 0; kt < 4; ++kt) { ws.act[kt][lane] = lo[kt]; ws.act[4 + kt][lane] = hi4[kt]; }
-            };
-            // layer 0: 176 -> 128
-            zero_acc(acc); ring_gemm(acc, kJ_L0, 11, in_a, sm, lane); relu_pack<0>(acc, lo, sm.bias + 0 * 128, q);
-            zero_acc(acc); ring_gemm(acc, kJ_L0 + 11, 11, in_a, sm, lane); relu_pack<1>(acc, hi4, sm.bias + 0 * 128, q);
-            commit();
-            // layers 1..3: 128 -> 128
-            zero_acc(acc); ring_gemm(acc, kJ_L1, 8, hid_a, sm, lane); relu_pack<0>(acc, lo, sm.bias + 1 * 128, q);
-            zero_acc(acc); ring_gemm(acc, kJ_L1 + 8, 8, hid_a, sm, lane); relu_pack<1>(acc, hi4, sm.bias + 1 * 128, q);
-            commit();
-            zero_acc(acc); ring_gemm(acc, kJ_L2, 8, hid_a, sm, lane); relu_pack<0>(acc, lo, sm.bias + 2 * 128, q);
-            zero_acc(acc); ring_gemm(acc, kJ_L2 + 8, 8, hid_a, sm, lane); relu_pack<1>(acc, hi4, sm.bias + 2 * 128, q);
-            commit();
-            zero_acc(acc); ring_gemm(acc, kJ_L3, 8, hid_a, sm, lane); relu_pack<0>(acc, lo, sm.bias + 3 * 128, q);
-            zero_acc(acc); ring_gemm(acc, kJ_L3 + 8, 8, hid_a, sm, lane); relu_pack<1>(acc, hi4, sm.bias + 3 * 128, q);
-            commit();
-            // layer 4 (skip): [hidden 128 | input 176] -> 128
-            zero_acc(acc); ring_gemm(acc, kJ_L4, 19, skip_a, sm, lane); relu_pack<0>(acc, lo, sm.bias + 4 * 128, q);
-            zero_acc(acc); ring_gemm(acc, kJ_L4 + 19, 19, skip_a, sm, lane); relu_pack<1>(acc, hi4, sm.bias + 4 * 128, q);
-            commit();
-            // layer 5: 128 -> 128 (+ ReLU out_activation, deformation_field.py:56)
-            zero_acc(acc); ring_gemm(acc, kJ_L5, 8, hid_a, sm, lane); relu_pack<0>(acc, lo, sm.bias + 5 * 128, q);
-            zero_acc(acc); ring_gemm(acc, kJ_L5 + 8, 8, hid_a, sm, lane); relu_pack<1>(acc, hi4, sm.bias + 5 * 128, q);
-            commit();
-            // heads: columns 0..2 = mlp_v, 3..5 = mlp_r (screw axis [v|r], deformation_field.py:90)
-            float hacc[2][4];
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) hacc[i][k] = 0.f;
-            {
-                constexpr int j = kJ_HEADS;
-                mbar_wait<20>(&sm.full[(j / kChunkSlabs) % kStages], (j / kChunkSlabs / kStages) & 1);
-                const uint4 *hw = reinterpret_cast<const uint4 *>(&sm.ring[(j / kChunkSlabs) % kStages][0]);
-#pragma unroll
-                for (int kt = 0; kt < 8; ++kt) {
-                    uint4 b = hw[kt * 32 + lane];
-                    uint32_t a[4];
-                    hid_a(kt, a);
-                    mma16816(hacc[0], a, b.x, b.y);
-                    mma16816(hacc[1], a, b.z, b.w);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[(j / kChunkSlabs) % kStages]);
-            }
-            // gather (v, r) of row g (c0,c1) / row g+8 (c2,c3) from the quad: cols 2q, 2q+1
-            const float hb0 = sm.bias[6 * 128 + 2 * q], hb1 = sm.bias[6 * 128 + 2 * q + 1];
-            const float c0 = hacc[0][0] + hb0, c1 = hacc[0][1] + hb1, c2 = hacc[0][2] + hb0, c3 = hacc[0][3] + hb1;
-            const int rsel = q & 1;  // lane q=0 -> row g, q=1 -> row g+8 (q=2,3 duplicate)
-            float vr[6];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int src = (lane & ~3) | k;
-                const float a0 = __shfl_sync(0xffffffffu, c0, src), a1 = __shfl_sync(0xffffffffu, c1, src);
-                const float b0 = __shfl_sync(0xffffffffu, c2, src), b1 = __shfl_sync(0xffffffffu, c3, src);
-                vr[2 * k] = rsel ? b0 : a0;
-                vr[2 * k + 1] = rsel ? b1 : a1;
-            }
-            const int r = g + 8 * rsel;
-            const float p[3] = {rsel ? pn[1][0] : pn[0][0], rsel ? pn[1][1] : pn[0][1], rsel ? pn[1][2] : pn[0][2]};
-            const float v[3] = {vr[0], vr[1], vr[2]}, rr[3] = {vr[3], vr[4], vr[5]};
-            float pw[3];
-            se3_apply(p, rr, v, pw);
-            if (q < 2) {
-                // offsets in NORMALISED units, added to WORLD positions (reference quirk:
-                // deformation_field.py:162 + Frustums.get_positions / nersemble_instant_ngp.py:258-259)
-                const float o0 = pw[0] - p[0], o1 = pw[1] - p[1], o2 = pw[2] - p[2];
-                const int64_t s = row0 + r;
-                if (A.out.offsets && s < n) {
-                    A.out.offsets[3 * s + 0] = o0; A.out.offsets[3 * s + 1] = o1; A.out.offsets[3 * s + 2] = o2;
-                }
-                ws.xs[r][0] = ws.pos[r][0] + o0; ws.xs[r][1] = ws.pos[r][1] + o1; ws.xs[r][2] = ws.pos[r][2] + o2;
-            }
-        } else {
-            if (lane < 16) {
-                ws.xs[lane][0] = ws.pos[lane][0]; ws.xs[lane][1] = ws.pos[lane][1]; ws.xs[lane][2] = ws.pos[lane][2];
-            }
-        }
-        __syncwarp();
-        if (!FIELD) continue;
-
-        // ---- stage 2: normalise, selector (nersemble_nerfacto_field.py:257,268-269) ----
-        if (lane < 16) {
-            float x = __fdiv_rn(__fsub_rn(ws.xs[lane][0], amin0), A.aabb_size[0]);
-            float y = __fdiv_rn(__fsub_rn(ws.xs[lane][1], amin1), A.aabb_size[1]);
-            float z = __fdiv_rn(__fsub_rn(ws.xs[lane][2], amin2), A.aabb_size[2]);
-            const bool sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
-            ws.xs[lane][0] = sel ? x : 0.f; ws.xs[lane][1] = sel ? y : 0.f; ws.xs[lane][2] = sel ? z : 0.f;
-            ws.xs[lane][3] = sel ? 1.f : 0.f;
-            if (A.out.xs && row0 + lane < n)
-                *reinterpret_cast<float4 *>(A.out.xs + 4 * (row0 + lane)) = make_float4(ws.xs[lane][0], ws.xs[lane][1], ws.xs[lane][2], ws.xs[lane][3]);
-        }
-        __syncwarp();
-
-        // ---- stage 3: hash-ensemble gather + blend, one sample at a time, whole warp ----
-        const int rows_valid = (int)min((int64_t)16, n - row0);
-#if NSB_GATHER_MMA
-        {
-            const uint8_t *tab = reinterpret_cast<const uint8_t *>(A.P.tables) + q * 32;
-            GatherTile Ga;
-            float4 xs = *reinterpret_cast<const float4 *>(ws.xs[0]);
-            if (rows_valid > 0) gather_issue<0>(A.P, tab, xs.x, xs.y, xs.z, g & 1, (g >> 1) & 1, g >> 2, Ga);
-            for (int r = 0; r < 16; ++r) {
-                float val = 0.f;
-                if (r < rows_valid) {
-                    const float *code_row = A.S.sample_blend_codes
-                                                ? A.S.sample_blend_codes + (row0 + r) * NSB_MEMBERS
-                                                : A.P.blend_codes + (size_t)__float_as_int(ws.pos[r][3]) * NSB_MEMBERS;
-                    const BlendB Bf = make_blend_b(A.O, code_row, lane);
-                    const bool has_next = r + 1 < rows_valid;
-                    const float4 nx = *reinterpret_cast<const float4 *>(ws.xs[has_next ? r + 1 : r]);
-                    val = gather_sample_pipelined(A.P, tab, xs.x, xs.y, xs.z, has_next, nx.x, nx.y, nx.z, Bf, Ga, lane);
-                    xs = nx;
-                    if (A.out.feat)
-                        reinterpret_cast<__half *>(A.out.feat)[(row0 + r) * 32 + lane] = __float2half_rn(val);
-                }
-                ws.feat[r * kFeatStride + lane] = __float2half_rn(val);
-            }
-        }
-#else
-        for (int r = 0; r < 16; ++r) {
-            float val = 0.f;
-            if (r < rows_valid) {
-                const float4 xs = *reinterpret_cast<const float4 *>(ws.xs[r]);
-                const float *code_row = A.S.sample_blend_codes
-                                            ? A.S.sample_blend_codes + (row0 + r) * NSB_MEMBERS
-                                            : A.P.blend_codes + (size_t)__float_as_int(ws.pos[r][3]) * NSB_MEMBERS;
-                float cw[4];
-                load_cw(A, code_row, lane & 7, cw);
-                val = gather_blend<kGatherLB>(A.P, xs.x, xs.y, xs.z, cw, lane);
-                if (A.out.feat)
-                    reinterpret_cast<__half *>(A.out.feat)[(row0 + r) * 32 + lane] = __float2half_rn(val);
-            }
-            ws.feat[r * kFeatStride + lane] = __float2half_rn(val);
-        }
-#endif
-        __syncwarp();
-
-        // ---- stage 4: density MLP 32 -> 64 -> 16 (tcnn FullyFusedMLP, no bias) ----
-        uint32_t fa[2][4];
-#pragma unroll
-        for (int kt = 0; kt < 2; ++kt) {
-            fa[kt][0] = *reinterpret_cast<const uint32_t *>(&ws.feat[g * kFeatStride + kt * 16 + 2 * q]);
-            fa[kt][1] = *reinterpret_cast<const uint32_t *>(&ws.feat[(g + 8) * kFeatStride + kt * 16 + 2 * q]);
-            fa[kt][2] = *reinterpret_cast<const uint32_t *>(&ws.feat[g * kFeatStride + kt * 16 + 2 * q + 8]);
-            fa[kt][3] = *reinterpret_cast<const uint32_t *>(&ws.feat[(g + 8) * kFeatStride + kt * 16 + 2 * q + 8]);
-        }
-        float b0acc[8][4];
-        smem_gemm<2, 4>(b0acc, fa, sm.field_w, lane);
-        uint32_t h1[4][4];
-        relu_pack_nobias<8>(b0acc, h1);
-        float b1acc[2][4];
-        smem_gemm<4, 1>(b1acc, h1, sm.field_w + 256, lane);
-        // column 0 = density pre-activation (lane q==0 holds cols 0,1)
-        const float sel0 = ws.xs[g][3], sel1 = ws.xs[g + 8][3];
-        if (q == 0 && A.out.sigma) {
-            // trunc_exp forward = exp (nerfstudio activations), times selector (:292-293)
-            if (row0 + g < n) A.out.sigma[row0 + g] = expf(b1acc[0][0]) * sel0;
-            if (row0 + g + 8 < n) A.out.sigma[row0 + g + 8] = expf(b1acc[0][2]) * sel1;
-        }
-        if (!HEAD) continue;
-
-        // ---- stage 5: colour MLP 32 -> 64 -> 64 -> 16, sigmoid.  Input columns are permuted
-        //      (weights packed accordingly): [1.0 | geo(15) | d'(3) | 1.0 x13]  ----
-        uint32_t ha[2][4];
-        {
-            float g00 = b1acc[0][0], g02 = b1acc[0][2];
-            if (q == 0) { g00 = 1.0f; g02 = 1.0f; }   // the density column becomes one of the 14 pad-ones
-            ha[0][0] = pack_h2(g00, b1acc[0][1]);
-            ha[0][1] = pack_h2(g02, b1acc[0][3]);
-            ha[0][2] = pack_h2(b1acc[1][0], b1acc[1][1]);
-            ha[0][3] = pack_h2(b1acc[1][2], b1acc[1][3]);
-            // k-tile 1: cols 16..18 = (d+1)/2 (shift_directions_for_tcnn), cols 19..31 = 1.0
-            float e[2][2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r = g + 8 * h;
-                const float d0 = (ws.dir[r][0] + 1.0f) / 2.0f, d1 = (ws.dir[r][1] + 1.0f) / 2.0f,
-                            d2 = (ws.dir[r][2] + 1.0f) / 2.0f;
-                e[h][0] = q == 0 ? d0 : (q == 1 ? d2 : 1.0f);
-                e[h][1] = q == 0 ? d1 : 1.0f;
-            }
-            ha[1][0] = pack_h2(e[0][0], e[0][1]);
-            ha[1][1] = pack_h2(e[1][0], e[1][1]);
-            ha[1][2] = pack_h2(1.0f, 1.0f);
-            ha[1][3] = pack_h2(1.0f, 1.0f);
-        }
-        float c0acc[8][4];
-        smem_gemm<2, 4>(c0acc, ha, sm.field_w + 384, lane);
-        uint32_t c1in[4][4];
-        relu_pack_nobias<8>(c0acc, c1in);
-        float c1acc[8][4];
-        smem_gemm<4, 4>(c1acc, c1in, sm.field_w + 640, lane);
-        uint32_t c2in[4][4];
-        relu_pack_nobias<8>(c1acc, c2in);
-        float c2acc[2][4];
-        smem_gemm<4, 1>(c2acc, c2in, sm.field_w + 1152, lane);
-        if (A.out.rgb) {
-            const int64_t sa = row0 + g, sb = row0 + g + 8;
-            if (q == 0) {
-                if (sa < n) { A.out.rgb[3 * sa + 0] = 1.f / (1.f + expf(-c2acc[0][0])); A.out.rgb[3 * sa + 1] = 1.f / (1.f + expf(-c2acc[0][1])); }
-                if (sb < n) { A.out.rgb[3 * sb + 0] = 1.f / (1.f + expf(-c2acc[0][2])); A.out.rgb[3 * sb + 1] = 1.f / (1.f + expf(-c2acc[0][3])); }
-            } else if (q == 1) {
-                if (sa < n) A.out.rgb[3 * sa + 2] = 1.f / (1.f + expf(-c2acc[0][0]));
-                if (sb < n) A.out.rgb[3 * sb + 2] = 1.f / (1.f + expf(-c2acc[0][2]));
-            }
-        }
     }
 }
 
@@ -938,6 +443,9 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             }
             int tsi = __float2int_rn(__fmul_rn(tt, (float)(A.P.n_timesteps - 1)));
             tsi = min(max(tsi, 0), A.P.n_timesteps - 1);
+            // component API (per-sample warp codes): the code-bias rows are indexed by SAMPLE instead of by timestep
+            // (n <= 2^24 and per-sample blend codes whenever the field is evaluated: checked on the host)
+            if (A.S.sample_code_bias) tsi = (int)min(s, n - 1);
             ts.pos[lane][0] = px; ts.pos[lane][1] = py; ts.pos[lane][2] = pz; ts.pos[lane][3] = __int_as_float(tsi);
             ts.dirsel[b][lane][0] = ddx; ts.dirsel[b][lane][1] = ddy; ts.dirsel[b][lane][2] = ddz;
         }
@@ -993,7 +501,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
             for (int m = 0; m < kMT; ++m)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) cb[m][h] = (uint32_t)__float_as_int(ts.pos[m * 16 + g + 8 * h][3]) * 256u;
-            const float *const gcb = A.P.deform_code_bias;
+            const float *const gcb = A.S.sample_code_bias ? A.S.sample_code_bias : A.P.deform_code_bias;
             auto in_a = [&](int m, int kt, uint32_t(&a)[4]) {
                 const uint4 v = ts.enc[m][kt][lane];
                 a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
@@ -1192,16 +700,6 @@ static int num_sms() {
     return g_num_sms;
 }
 
-static int kernel_version() {
-    static int v = 0;
-    if (v == 0) {
-        const char *e = getenv("NSB_KERNEL");   // 1: SPMD-warp kernel (2 CTAs/SM), 2: warp-specialised (default)
-        v = e ? atoi(e) : 2;
-        if (v != 1) v = 2;
-    }
-    return v;
-}
-
 template <bool D, bool F, bool H, bool SV>
 static int launch_field_ws_(const FieldArgs &A, cudaStream_t st) {
     const size_t smem = sizeof(SmemWS);
@@ -1226,35 +724,13 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
 }
 
 template <bool D, bool F, bool H>
-static int launch_field(const FieldArgs &A, cudaStream_t st) {
-    if (kernel_version() == 2 && (!D || (A.P.deform_packed_tb && A.P.deform_code_bias && !A.S.sample_warp_codes)))
-        return launch_field_ws<D, F, H>(A, st);
-    const size_t smem = sizeof(Smem);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(field_kernel<D, F, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(field_kernel): %s", cudaGetErrorString(e));
-            return 1;
-        }
-        configured = true;
-    }
-    const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        const char *e = getenv("NSB_CTAS_PER_SM");   // tuning/debug knob
-        ctas_per_sm = e ? std::max(1, atoi(e)) : 2;
-    }
-    const int grid = (int)std::min<int64_t>(n_tiles, ctas_per_sm * (int64_t)num_sms());
-    field_kernel<D, F, H><<<grid, kThreads, smem, st>>>(A);
-    return check_launch("field_kernel");
-}
+static int launch_field(const FieldArgs &A, cudaStream_t st) { return launch_field_ws<D, F, H>(A, st); }
 
 }  // namespace nsb
 
 using namespace nsb;
 
-extern "C" size_t nsb_deform_packed_bytes(void) { return kDeformPackedBytes; }
+extern "C" size_t nsb_deform_packed_bytes(void) { return (size_t)kTbNumSlabs * kSlabBytes; }
 extern "C" size_t nsb_field_packed_bytes(void) { return kFieldPackedU4 * sizeof(uint4); }
 
 extern "C" int nsb_field_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
@@ -1273,22 +749,18 @@ extern "C" int nsb_field_forward(const nsb_field_params *params, const nsb_field
     if (!need_field && !(deform && out->offsets)) { set_error("nsb_field_forward: no outputs requested"); return 1; }
     if (need_field && (!params->tables || !params->field_packed)) { set_error("nsb_field_forward: tables/field_packed missing"); return 1; }
     if (need_field && !params->blend_codes && !samples->sample_blend_codes) { set_error("nsb_field_forward: no blend codes"); return 1; }
-    if (deform && (!params->deform_packed || !params->deform_bias || (!params->warp_codes && !samples->sample_warp_codes))) {
-        set_error("nsb_field_forward: deformation parameters missing");
+    if (deform && (!params->deform_packed_tb || !params->deform_bias || (!params->deform_code_bias && !samples->sample_code_bias))) {
+        set_error("nsb_field_forward: deformation parameters missing (deform_packed_tb, deform_bias, code bias)");
+        return 1;
+    }
+    if (deform && samples->sample_code_bias && (samples->n_samples > (int64_t(1) << 24) || (need_field && !samples->sample_blend_codes))) {
+        set_error("nsb_field_forward: per-sample code bias needs <= 2^24 samples and per-sample blend codes");
         return 1;
     }
     if (params->n_timesteps < 1) { set_error("nsb_field_forward: n_timesteps < 1"); return 1; }
     FieldArgs A;
     A.P = *params; A.O = *opts; A.S = *samples; A.out = *out;
     for (int k = 0; k < 3; ++k) A.aabb_size[k] = params->aabb[3 + k] - params->aabb[k];
-    {
-        static int stagger = -1;
-        if (stagger < 0) {
-            const char *e = getenv("NSB_STAGGER_NS");
-            stagger = e ? atoi(e) : 0;
-        }
-        A.stagger_ns = (uint32_t)stagger;
-    }
     cudaStream_t st = (cudaStream_t)stream;
     if (deform) {
         if (!need_field) return launch_field<true, false, false>(A, st);

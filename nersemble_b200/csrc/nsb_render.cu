@@ -407,6 +407,47 @@ __global__ void depth_clip_kernel(float *depth, int64_t n_rays, const uint32_t *
     depth[r] = fminf(fmaxf(depth[r], lo), hi);
 }
 
+// ---------------------------------------------------------------------------------------------
+// occupancy-grid EMA update (nerfacc OccGridEstimator._update): see nsb.h.  occ values are >= 0 (densities), so the
+// int ordering of their bit patterns is the float ordering and atomicMax(int) resolves duplicate cells.
+// ---------------------------------------------------------------------------------------------
+__global__ void occ_decay_kernel(const float *__restrict__ occs, const int64_t *__restrict__ ids, int64_t n, float decay,
+                                 float *__restrict__ tmp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tmp[ids[i]] = occs[ids[i]] * decay;      // duplicates store the same value
+}
+__global__ void occ_max_kernel(const int64_t *__restrict__ ids, const float *__restrict__ occ_new, int64_t n,
+                               float *__restrict__ tmp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = occ_new[i];
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(tmp + ids[i]), __float_as_int(v));
+    else if (isnan(v)) tmp[ids[i]] = v;                  // torch.maximum propagates NaN
+}
+__global__ void occ_commit_kernel(float *__restrict__ occs, const int64_t *__restrict__ ids, int64_t n,
+                                  const float *__restrict__ tmp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) occs[ids[i]] = tmp[ids[i]];
+}
+__global__ void __launch_bounds__(256) occ_mean_kernel(const float *__restrict__ occs, int64_t n_cells, double *__restrict__ acc) {
+    double s = 0.0, c = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = occs[i];
+        if (v >= 0.f) { s += (double)v; c += 1.0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if ((threadIdx.x & 31) == 0 && c > 0.0) { atomicAdd(acc, s); atomicAdd(acc + 1, c); }
+}
+__global__ void occ_binarise_kernel(const float *__restrict__ occs, int64_t n_cells, const double *__restrict__ acc,
+                                    float occ_thre, uint8_t *__restrict__ binaries) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const float mean = (float)(acc[0] / acc[1]);        // 0/0 = NaN like torch.mean of an empty selection
+    const float thre = fminf(mean, occ_thre);            // torch.clamp(mean, max=occ_thre); NaN mean -> occ_thre
+    binaries[i] = occs[i] > (isnan(mean) ? occ_thre : thre) ? 1 : 0;
+}
+
 }  // namespace nsb
 
 using namespace nsb;
@@ -485,4 +526,28 @@ extern "C" int nsb_composite_forward(const nsb_composite_args *args, void *strea
     composite_kernel<<<blocks, 256, 0, st>>>(C);
     depth_clip_kernel<<<(int)((args->n_rays + 255) / 256), 256, 0, st>>>(args->out_depth, args->n_rays, args->workspace);
     return check_launch("composite_kernel");
+}
+
+extern "C" size_t nsb_occ_update_scratch_bytes(int64_t n_cells) { return (size_t)n_cells * sizeof(float) + 2 * sizeof(double) + 8; }
+
+extern "C" int nsb_occ_update(float *occs, uint8_t *binaries, int64_t n_cells, const int64_t *cell_ids, const float *occ_new,
+                              int64_t n, float ema_decay, float occ_thre, void *scratch, void *stream) {
+    if (!occs || !binaries || !scratch || n_cells <= 0 || (n > 0 && (!cell_ids || !occ_new))) {
+        set_error("nsb_occ_update: null argument");
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *acc = reinterpret_cast<double *>(scratch);                                   // 8-byte aligned head
+    float *tmp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(scratch) + 2 * sizeof(double));
+    const int T = 256;
+    if (n > 0) {
+        const int blocks = (int)((n + T - 1) / T);
+        occ_decay_kernel<<<blocks, T, 0, st>>>(occs, cell_ids, n, ema_decay, tmp);
+        occ_max_kernel<<<blocks, T, 0, st>>>(cell_ids, occ_new, n, tmp);
+        occ_commit_kernel<<<blocks, T, 0, st>>>(occs, cell_ids, n, tmp);
+    }
+    cudaMemsetAsync(acc, 0, 2 * sizeof(double), st);
+    occ_mean_kernel<<<296, 256, 0, st>>>(occs, n_cells, acc);
+    occ_binarise_kernel<<<(int)((n_cells + T - 1) / T), T, 0, st>>>(occs, n_cells, acc, occ_thre, binaries);
+    return check_launch("nsb_occ_update");
 }

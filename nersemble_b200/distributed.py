@@ -36,6 +36,24 @@ def gather_rays(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
 
 
+def allreduce_pending(he, average: bool = True) -> None:
+    """All-reduce of a HashEnsemble's parked rank-1 table gradient (fused optimiser), once: a reduced gradient is marked.
+    Same slot map and blend weights on every rank (n_timesteps <= 32: slot = timestep, cw_slots from the replicated
+    time embedding) -> the [slots][entries][2] workspace is summed in
+    place and the 1/world factor folded into the optimiser step; otherwise, or when a dense `.grad` exists as well
+    (gradient accumulation: the dense part must be averaged too), it becomes a dense `.grad` for the dense reduction."""
+    pend = he.pending_table_grad
+    if pend is None or pend.get("reduced") or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    if pend.get("slots_are_timesteps") and he.tables.grad is None:
+        dist.all_reduce(pend["g_rank1"], op=dist.ReduceOp.SUM)
+        pend["scale"] = float(pend.get("scale", 1.0)) / (world if average else 1)
+        pend["reduced"] = True
+    else:
+        he.materialize_pending()
+
+
 _BIG = 1 << 24   # elements: tensors this large are reduced in place, not copied into the flat bucket
 
 
@@ -52,14 +70,7 @@ def allreduce_gradients(params, average: bool = True, hash_ensembles=()) -> None
         return
     world = dist.get_world_size()
     for he in hash_ensembles:
-        pend = he.pending_table_grad
-        if pend is None:
-            continue
-        if pend.get("slots_are_timesteps"):
-            dist.all_reduce(pend["g_rank1"], op=dist.ReduceOp.SUM)
-            pend["scale"] = float(pend.get("scale", 1.0)) / (world if average else 1)
-        else:
-            he.materialize_pending()
+        allreduce_pending(he, average)
     params = [p for p in params if p.requires_grad]
     deferred = {id(he.tables) for he in hash_ensembles if he.pending_table_grad is not None}
     params = [p for p in params if id(p) not in deferred]

@@ -19,6 +19,7 @@ try:  # pragma: no cover - real nerfstudio is not installed in this image
     from nerfstudio.engine.callbacks import (TrainingCallback, TrainingCallbackAttributes,  # type: ignore
                                              TrainingCallbackLocation)
     from nerfstudio.field_components.field_heads import FieldHeadNames  # type: ignore
+    from nerfstudio.models.base_model import Model  # type: ignore
     HAVE_NERFSTUDIO = True
 except Exception:  # noqa: BLE001
     HAVE_NERFSTUDIO = False
@@ -101,6 +102,57 @@ except Exception:  # noqa: BLE001
         def run_callback_at_location(self, step, location):
             if location in self.where_to_run:
                 self.run_callback(step)
+
+
+    class Model(nn.Module):
+        """nerfstudio.models.base_model.Model (0.3.1): constructor protocol, device, forward, the chunked camera-ray
+        render, checkpoint loading and the step hook -- what the trainer / pipeline call on a model."""
+
+        def __init__(self, config, scene_box, num_train_data: int, **kwargs):
+            super().__init__()
+            self.config = config
+            self.scene_box = scene_box
+            self.render_aabb = None
+            self.num_train_data = num_train_data
+            self.kwargs = kwargs
+            self.collider = None
+            self.populate_modules()
+            self.callbacks = None
+            self.device_indicator_param = nn.Parameter(torch.empty(0))
+
+        @property
+        def device(self):
+            return self.device_indicator_param.device
+
+        def populate_modules(self):
+            pass
+
+        def get_training_callbacks(self, training_callback_attributes):
+            return []
+
+        def forward(self, ray_bundle):
+            if self.collider is not None:
+                ray_bundle = self.collider(ray_bundle)
+            return self.get_outputs(ray_bundle)
+
+        @torch.no_grad()
+        def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle):
+            n = self.config.eval_num_rays_per_chunk
+            h, w = camera_ray_bundle.origins.shape[:2]
+            lists: Dict[str, list] = {}
+            for i in range(0, h * w, n):
+                rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + n)
+                for name, out in self.forward(ray_bundle=rb).items():
+                    if torch.is_tensor(out):          # tuple-wrapped per-sample outputs are skipped (NeRSemble wraps them)
+                        lists.setdefault(name, []).append(out)
+            return {k: torch.cat(v).view(h, w, -1) for k, v in lists.items()}
+
+        def load_model(self, loaded_state: Dict[str, Any]) -> None:
+            state = {key.replace("module.", ""): value for key, value in loaded_state["model"].items()}
+            self.load_state_dict(state)
+
+        def update_to_step(self, step: int) -> None:
+            """Called when loading a checkpoint to fast-forward step-dependent state (schedulers)."""
 
 
 class SceneBox:

@@ -31,8 +31,9 @@ _WORKSPACES: dict = {}
 
 
 def _workspace(name: str, nbytes: int, dev) -> torch.Tensor:
-    """Reusable scratch buffers (contents undefined between calls; ops on one stream are ordered)."""
-    key = (name, str(dev))
+    """Reusable scratch buffers, one per (name, device, STREAM): contents are undefined between calls and ops on one
+    stream are ordered, so two streams (trainer + viewer thread, engine/nersemble_trainer.py:38-40) never share one."""
+    key = (name, str(dev), torch.cuda.current_stream(dev).cuda_stream)
     t = _WORKSPACES.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -54,7 +55,6 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 class NativeParams:
     """Device-resident parameters in the kernels' layouts (see packing.py)."""
     tables: Optional[torch.Tensor]          # half [entries, 32, 2]
-    deform_packed: Optional[torch.Tensor]   # half, fragment order
     deform_bias: Optional[torch.Tensor]     # float [776]
     field_packed: Optional[torch.Tensor]    # half, fragment order
     warp_codes: Optional[torch.Tensor]      # half [T, 128]
@@ -65,6 +65,7 @@ class NativeParams:
     field_packed_t: Optional[torch.Tensor] = None     # half, transposed field weights (backward)
     deform_packed_t: Optional[torch.Tensor] = None    # half, transposed deformation weights (backward)
     deform_packed_tb: Optional[torch.Tensor] = None   # half, fragment order, no warp-code columns
+    deform_code_w: Optional[list] = None              # (stem_w[0], stem_w[4], stem_b[0], stem_b[4]): per-sample code bias
     deform_code_bias: Optional[torch.Tensor] = None   # float [T, 2, 128]
 
     def __post_init__(self):
@@ -84,27 +85,32 @@ class NativeParams:
         """tables: [entries,32,2] (any float dtype); base_w/head_w: lists of [out,in] matrices;
         deform: dict(stem_w, stem_b, r_w, r_b, v_w, v_b) or None."""
         dev = torch.device(device)
+        if time_emb is not None and base_w is not None and time_emb.shape[-1] != 32:
+            raise ValueError(f"time_emb must be [T, 32] (one blend weight per ensemble member), got {tuple(time_emb.shape)}")
+        if deform is not None and (time_emb_deform is None or time_emb_deform.shape[-1] != 128):
+            raise ValueError("time_emb_deform must be [T, 128] (SE3DeformationFieldConfig.warp_code_dim = 128)")
         tab = None if tables is None else tables.detach().to(dev).half().contiguous()
         fp = fpt = None
-        dp = db = wc = None
+        db = wc = dtb = dpt = dcb = None
         if deform is not None:
             sw, sb = [w.to(dev) for w in deform["stem_w"]], [b.to(dev) for b in deform["stem_b"]]
         if base_w is not None and deform is not None:      # the training path: one gather for all five buffers
-            dp, dtb, dpt, fp, fpt = packing.pack_all_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev),
+            dtb, dpt, fp, fpt = packing.pack_all_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev),
                                                           [w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
         elif base_w is not None:
             fp, fpt = packing.pack_field_fast([w.detach().to(dev) for w in base_w], [w.detach().to(dev) for w in head_w])
         elif deform is not None:
-            dp, dtb, dpt = packing.pack_deform_weights_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
+            dtb, dpt = packing.pack_deform_weights_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
         if deform is not None:
             db = packing.deform_bias_vector(sb, deform["r_b"].to(dev), deform["v_b"].to(dev))
             wc = time_emb_deform.detach().to(dev).half().contiguous()
             dcb = packing.deform_code_bias(sw, sb, wc)
         te = None if time_emb is None else time_emb.detach().to(dev).float().contiguous()
         n_t = int(time_emb.shape[0]) if time_emb is not None else (int(time_emb_deform.shape[0]) if time_emb_deform is not None else 1)
-        P = NativeParams(tab, dp, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
+        P = NativeParams(tab, db, fp, wc, te, aabb.detach().float().cpu(), levels, n_t)
         if deform is not None:
             P.deform_packed_tb, P.deform_code_bias, P.deform_packed_t = dtb, dcb, dpt
+            P.deform_code_w = [sw[0].detach(), sw[4].detach(), sb[0].detach(), sb[4].detach()]
         P.field_packed_t = fpt
         return P
 
@@ -114,7 +120,6 @@ class NativeParams:
         if fresh:
             p = self._cp = _lib.FieldParams()
         p.tables = _ptr(self.tables)
-        p.deform_packed = _ptr(self.deform_packed)
         p.deform_bias = _ptr(self.deform_bias)
         p.deform_packed_tb = _ptr(self.deform_packed_tb)
         p.deform_code_bias = _ptr(self.deform_code_bias)
@@ -194,9 +199,14 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
         assert sample_blend_codes.shape == (n, 32)
         s.sample_blend_codes = _ptr(sample_blend_codes); keep.append(sample_blend_codes)
     if sample_warp_codes is not None:
-        sample_warp_codes = sample_warp_codes.detach().half().contiguous()
-        assert sample_warp_codes.shape == (n, 128)
-        s.sample_warp_codes = _ptr(sample_warp_codes); keep.append(sample_warp_codes)
+        # component API (SE3DeformationField.compute_offsets with explicit codes): the kernel takes the code columns of
+        # layers 0 / 4 as a per-sample bias, W_code . code + b (fp16-rounded operands, fp32 accumulate)
+        assert sample_warp_codes.shape == (n, 128) and P.deform_code_w is not None
+        if n > (1 << 24):
+            raise RuntimeError("per-sample warp codes: at most 2^24 samples per call")
+        w0, w4, b0, b4 = P.deform_code_w
+        scb = packing.deform_code_bias({0: w0, 4: w4}, {0: b0, 4: b4}, sample_warp_codes.to(dev))
+        s.sample_code_bias = _ptr(scb); keep.append(scb)
     s.n_samples = n
     out = {}
     o = _lib.FieldOut()
@@ -595,6 +605,23 @@ def visibility_mask(packed_info, t_starts, t_ends, sigma, early_stop_eps: float,
                                  float(alpha_thre), _ptr(mask), _ptr(kept), _stream())
     _lib.check(rc, "nsb_visibility_mask")
     return mask.bool(), kept
+
+
+def occ_update(occs: torch.Tensor, binaries: torch.Tensor, cell_ids: torch.Tensor, occ_new: torch.Tensor,
+               ema_decay: float, occ_thre: float) -> None:
+    """nerfacc OccGridEstimator._update's EMA-max + re-threshold, in place (nsb_occ_update): `occs` float [n_cells],
+    `binaries` bool (any shape with n_cells elements); duplicates in cell_ids resolve to the largest candidate."""
+    lib = _lib.load()
+    _need_cuda(occs, binaries, cell_ids, occ_new)
+    assert occs.dtype == _F32 and occs.is_contiguous() and binaries.dtype == torch.bool and binaries.is_contiguous()
+    assert binaries.numel() == occs.numel()
+    ids = cell_ids.detach().to(torch.int64).contiguous()
+    new = _f32c(occ_new).reshape(-1)
+    assert ids.shape == new.shape
+    n_cells = occs.numel()
+    ws = _workspace("occ_update", int(lib.nsb_occ_update_scratch_bytes(n_cells)), occs.device)
+    _lib.check(lib.nsb_occ_update(_ptr(occs), _ptr(binaries), n_cells, _ptr(ids), _ptr(new), int(ids.numel()),
+                                  float(ema_decay), float(occ_thre), _ptr(ws), _stream()), "nsb_occ_update")
 
 
 def render_packed(P: NativeParams, origins, directions, ray_times, t_starts, t_ends, ray_indices, packed_info, *,

@@ -23,14 +23,31 @@ from . import ops
 
 
 class FusedFieldsAdam(torch.optim.Adam):
+    """torch.optim.Adam whose update of the HashEnsemble table is one fused CUDA pass.
+
+    GradScaler (engine/nersemble_trainer.py:182-186 runs `grad_scaler.scale(loss).backward(); grad_scaler.step(opt)`):
+    the parked rank-1 table gradient is not a `.grad`, so `GradScaler.unscale_` neither unscales nor inf-checks it.
+    This class therefore declares `_step_supports_amp_scaling` -- GradScaler.step() then hands `grad_scale` /
+    `found_inf` (computed over the `.grad` tensors) to step() instead of deciding itself.  (1) The training backward
+    makes a non-finite table-side gradient visible to that check by poisoning the mlp_base gradient with NaN
+    (plugin/model.py::_RenderFunction.backward), so the scaler's own found_inf / back-off logic covers it; (2) step()
+    skips the WHOLE step when found_inf is set (no inf reaches the 1.6 GB table or its fp16 copy); (3) it unscales both
+    the dense `.grad`s and the parked gradient by 1/scale, so the Adam moments are accumulated at the true gradient scale whatever the scaler
+    does to its scale.  One host synchronisation (found_inf, scale), where torch's GradScaler.step() has its own.
+
+    DDP: the table's `.grad` is None, so DistributedDataParallel does not reduce it.  step() all-reduces a parked
+    gradient that `distributed.allreduce_gradients` has not already reduced whenever a process group with more than
+    one rank exists (every rank steps, so every rank issues the collective)."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, **kw):
         if kw.get("amsgrad") or kw.get("maximize"):
             raise NotImplementedError("FusedFieldsAdam: amsgrad / maximize")
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
-        # torch.cuda.amp.GradScaler unscales `.grad` tensors only; the parked table gradient is not one.  A trainer that
-        # scales the loss sets this to 1 / scaler.get_scale() before step() (Adam is scale-invariant up to eps, so
-        # forgetting it changes the update only where |g| ~ eps = 1e-15).
+        self._step_supports_amp_scaling = True     # see the class docstring
+        # extra factor on the parked gradient for trainers that scale the loss WITHOUT a GradScaler (1 / their scale)
         self.pending_grad_scale = 1.0
+        self.auto_allreduce = True
+        self.last_step_skipped = False
         self._ensembles = []
         for group in self.param_groups:
             for p in group["params"]:
@@ -47,17 +64,54 @@ class FusedFieldsAdam(torch.optim.Adam):
         for he, _, _ in self._ensembles:
             he.pending_table_grad = None
 
+    def _amp_state(self):
+        """(skip, inv_scale) from the attributes GradScaler.step() sets on optimisers that support amp scaling."""
+        gs, fi = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
+        if gs is None and fi is None:
+            return False, 1.0
+        dev = (gs if gs is not None else fi).device
+        # found_inf covers the parked table gradient too: the training backward poisons the mlp_base gradient (a real
+        # `.grad` of this optimiser) with NaN whenever the table-side gradient is non-finite (plugin/model.py)
+        bad = torch.zeros((), device=dev) if fi is None else fi.detach().float().reshape(-1).sum()
+        scale = torch.ones((), device=dev) if gs is None else gs.detach().float().reshape(())
+        bad_v, scale_v = torch.stack([bad, scale]).tolist()      # the one host synchronisation of an amp step
+        return bad_v > 0, (1.0 / scale_v if gs is not None else 1.0)
+
     @torch.no_grad()
     def step(self, closure=None):
+        import torch.distributed as dist
+        if self.auto_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .distributed import allreduce_pending
+            for he, _, _ in self._ensembles:
+                allreduce_pending(he, average=True)
+        skip, inv_scale = self._amp_state()
+        self.last_step_skipped = skip
+        if skip:
+            for he, _, _ in self._ensembles:
+                he.pending_table_grad = None
+            return None
+        if inv_scale != 1.0:
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        p.grad.mul_(inv_scale)
         work = []
         for he, p, group in self._ensembles:
             if p.grad is not None and he.pending_table_grad is not None:
                 # a dense .grad AND a parked rank-1 gradient (second backward before step()): they may carry different
                 # scale factors (all-reduce averaging), so fold the parked one into the dense tensor first
-                he.materialize_pending(scale=float(self.pending_grad_scale))
+                he.materialize_pending(scale=float(self.pending_grad_scale) * inv_scale)
             work.append((he, p, group, p.grad, he.pending_table_grad))
             p.grad = None                   # torch's Adam skips parameters without .grad
-        loss = super().step(closure)
+        # torch's non-fused Adam asserts that it was not handed amp state: hide it for the inner call
+        amp_attrs = {k: getattr(self, k) for k in ("grad_scale", "found_inf") if hasattr(self, k)}
+        for k in amp_attrs:
+            setattr(self, k, None)
+        try:
+            loss = super().step(closure)
+        finally:
+            for k, v in amp_attrs.items():
+                setattr(self, k, v)
         for he, p, group, dense, pending in work:
             if dense is None and pending is None:
                 continue
@@ -70,10 +124,10 @@ class FusedFieldsAdam(torch.optim.Adam):
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
             st["step"] += 1
             shadow = he.shadow_buffer()
+            gscale = 1.0 if pending is None else float(pending.get("scale", 1.0)) * float(self.pending_grad_scale) * inv_scale
             ops.table_adam_step(p.data, st["exp_avg"], st["exp_avg_sq"], shadow, step=int(st["step"].item()),
                                 lr=float(group["lr"]), betas=group["betas"], eps=group["eps"],
-                                weight_decay=group["weight_decay"], grad=dense, pending=pending,
-                                grad_scale=(1.0 if pending is None else float(pending.get("scale", 1.0)) * float(self.pending_grad_scale)))
+                                weight_decay=group["weight_decay"], grad=dense, pending=pending, grad_scale=gscale)
             torch.autograd.graph.increment_version(p)
             he.set_native_tables(shadow)
             he.pending_table_grad = None

@@ -211,16 +211,13 @@ _FIELD_SHAPES = [(64, 32), (16, 64), (64, 32), (64, 64), (16, 64)]
 
 
 def pack_deform_weights_fast(stem_w, r_w, v_w):
-    """(pack_deform weights, pack_deform_tb weights, pack_deform_bwd) through cached gather plans."""
+    """(pack_deform_tb weights, pack_deform_bwd) through cached gather plans."""
     dev = stem_w[0].device
     shapes = _STEM_SHAPES + [(3, 128), (3, 128)]
     src = list(stem_w) + [r_w, v_w]
-    z6 = [torch.zeros(128) for _ in range(6)]
-    z3 = torch.zeros(3)
-    p_fwd = gather_plan("deform", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()), shapes, dev)
     p_tb = gather_plan("deform_tb", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()[:48]), shapes, dev)
     p_bwd = gather_plan("deform_bwd", lambda *w: pack_deform_bwd(w[:6], w[6], w[7]), shapes, dev)
-    return apply_plan(p_fwd, src), apply_plan(p_tb, src), apply_plan(p_bwd, src)
+    return apply_plan(p_tb, src), apply_plan(p_bwd, src)
 
 
 def pack_field_fast(base_w, head_w):
@@ -233,15 +230,14 @@ def pack_field_fast(base_w, head_w):
 
 
 def pack_all_fast(stem_w, r_w, v_w, base_w, head_w):
-    """All five packed weight buffers (pack_deform weights, pack_deform_tb weights, pack_deform_bwd, pack_field,
-    pack_field_bwd) of a training step with ONE cat, ONE gather and ONE cast (host time: ~25 torch ops -> 3)."""
+    """All four packed weight buffers (pack_deform_tb weights, pack_deform_bwd, pack_field, pack_field_bwd) of a
+    training step with ONE cat, ONE gather and ONE cast (host time: ~25 torch ops -> 3)."""
     dev = stem_w[0].device
     key = ("all", str(dev))
     if key not in _PLANS:
         d_shapes = _STEM_SHAPES + [(3, 128), (3, 128)]
         n_deform = sum(a * b for a, b in d_shapes)
-        plans = [gather_plan("deform", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()), d_shapes, dev),
-                 gather_plan("deform_tb", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()[:48]), d_shapes, dev),
+        plans = [gather_plan("deform_tb", lambda *w: _deform_weights(w[:6], w[6], w[7], deform_input_colmap()[:48]), d_shapes, dev),
                  gather_plan("deform_bwd", lambda *w: pack_deform_bwd(w[:6], w[6], w[7]), d_shapes, dev)]
         f_plans = [gather_plan("field", lambda *w: pack_field(w[:2], w[2:]), _FIELD_SHAPES, dev),
                    gather_plan("field_bwd", lambda *w: pack_field_bwd(w[:2], w[2:]), _FIELD_SHAPES, dev)]

@@ -195,7 +195,7 @@ class HashEnsemble(nn.Module):
             "If blend mixing type is chosen, conditioning code needs to have as many dimensions as there are " \
             "hashtables in the encoding"
         _no_autograd(in_tensor, conditioning_code, self.tables)
-        P = ops.NativeParams(self.native_tables(), None, None, None, None, None, torch.tensor([[0., 0, 0], [1, 1, 1]]),
+        P = ops.NativeParams(self.native_tables(), None, None, None, None, torch.tensor([[0., 0, 0], [1, 1, 1]]),
                              self.levels, 1)
         return ops.hash_blend_forward(P, in_tensor, conditioning_code, window_hash=window_hash_encodings, out_half=True,
                                       disable_initial=self.disable_initial_hash_ensemble,

@@ -10,7 +10,7 @@ from torch import Tensor, nn
 from torch.nn import Parameter, init
 
 from .. import ops
-from ..nerfstudio_shim import (FieldHeadNames, RayBundle, RaySamples, SceneBox, TrainingCallback,
+from ..nerfstudio_shim import (FieldHeadNames, Model, RayBundle, RaySamples, SceneBox, TrainingCallback,
                                TrainingCallbackAttributes, TrainingCallbackLocation)
 from .components import (GenericScheduler, HashEnsembleConfig, SE3DeformationField, SE3DeformationFieldConfig,
                          _no_autograd)
@@ -113,6 +113,8 @@ class _RenderFunction(torch.autograd.Function):
     def backward(ctx, g_rgb, g_acc, g_depth, g_weights, *unused):
         from .. import packing
         model, kw = ctx.model, ctx.kw
+        if g_rgb is None:                       # a loss that does not touch rgb (e.g. only the distortion term)
+            g_rgb = torch.zeros((ctx.packed_info.shape[0], 3), dtype=torch.float32, device=ctx.saved["sigma"].device)
         ls = float(getattr(model, "mlp_loss_scale", 128.0))
         d_sigma, d_rgb = ops.composite_backward(ctx.packed_info, kw["t_starts"], kw["t_ends"], ctx.saved["sigma"],
                                                 ctx.saved["rgb"], ctx.workspace, g_rgb,
@@ -125,6 +127,11 @@ class _RenderFunction(torch.autograd.Function):
                                defer_tables=defer, **kw, **model._blend_opts())
         if "pending" in g:
             he.pending_table_grad = g["pending"]
+            # GradScaler contract: the parked table gradient is no `.grad`, so the scaler's inf check cannot
+            # see it.  Its entries are sums of |w| <= 1 times d_feat, so d_feat is finite iff it is: fold that flag into
+            # a gradient the scaler DOES check (x - x = 0 for finite x, NaN otherwise) -- no host synchronisation.
+            flag = g["d_feat"].sum()
+            g["d_base_w"] = g["d_base_w"] + (flag - flag)
         grads = [g.get("d_tables"), g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
         if ctx.deform:
             d = ops.deform_backward(ctx.P, ctx.saved, g["d_xs"], window_deform=ctx.wd, loss_scale=ls, **kw)
@@ -160,30 +167,29 @@ def _segment_exclusive_sum(x: Tensor, ray_indices: Tensor, n_rays: int) -> Tenso
     return (inc - x.double() - before[ray_indices]).to(x.dtype)
 
 
-class NeRSembleNGPModel(nn.Module):
+class NeRSembleNGPModel(Model):
+    """Subclass of nerfstudio's `Model` (the real class when nerfstudio is importable, the 0.3.1-shaped stand-in of
+    nerfstudio_shim otherwise): the base constructor stores config / scene_box / num_train_data / kwargs, calls
+    populate_modules() and creates device_indicator_param, exactly as under VanillaPipeline (train_nersemble.py:163,184)."""
     config: NeRSembleNGPModelConfig
 
     def __init__(self, config: NeRSembleNGPModelConfig, scene_box: SceneBox, num_train_data: int, **kwargs):
-        super().__init__()
-        self.config = config
-        self.scene_box = scene_box
-        self.num_train_data = num_train_data
-        self.kwargs = kwargs
-        self.collider = None
-        self.populate_modules()
-        self.device_indicator_param = nn.Parameter(torch.empty(0))
+        super().__init__(config=config, scene_box=scene_box, num_train_data=num_train_data, **kwargs)
         self._native = None
         self._native_version = None
         self.sync_free_losses = True     # get_loss_dict without host syncs on CUDA (see _loss_dict_sync_free)
         self.fused_losses = True         # ... and, when the outputs come from get_outputs, in fused kernels (_loss_dict_fused)
-
-    @property
-    def device(self):
-        return self.device_indicator_param.device
+        self.lpips = None                # optional callable(image[1,3,H,W], rgb[1,3,H,W]) -> scalar (needs pretrained weights)
 
     def populate_modules(self):
         """models/nersemble_instant_ngp.py:81-179 (+ BaseModel.populate_modules, base.py:38-47)."""
         cfg = self.config
+        if cfg.use_hash_ensemble:
+            # hash_ensemble.py:115-117 asserts this at forward time; here the embedding rows ARE the kernel's blend codes
+            assert cfg.latent_dim_time == cfg.hash_ensemble_config.n_hash_encodings, \
+                "If blend mixing type is chosen, conditioning code needs to have as many dimensions as there are " \
+                f"hashtables in the encoding (latent_dim_time={cfg.latent_dim_time}, " \
+                f"n_hash_encodings={cfg.hash_ensemble_config.n_hash_encodings})"
         if cfg.lambda_empty_loss > 0 or cfg.lambda_near_loss > 0:
             self.sched_eps_depth = GenericScheduler(cfg.eps_depth_initial, cfg.eps_depth_final, cfg.eps_depth_begin_step,
                                                     cfg.eps_depth_end_step)
@@ -353,21 +359,12 @@ class NeRSembleNGPModel(nn.Module):
             outputs["deformation"] = out["deformation"]
         return outputs
 
-    def forward(self, ray_bundle: RayBundle):
-        return self.get_outputs(ray_bundle)
-
-    @torch.no_grad()
-    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
-        """nerfstudio Model.get_outputs_for_camera_ray_bundle: chunk loop; tuple-wrapped outputs are skipped."""
-        n = self.config.eval_num_rays_per_chunk
-        h, w = camera_ray_bundle.origins.shape[:2]
-        lists: Dict[str, list] = {}
-        for i in range(0, h * w, n):
-            rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + n)
-            for name, out in self.forward(ray_bundle=rb).items():
-                if torch.is_tensor(out):
-                    lists.setdefault(name, []).append(out)
-        return {k: torch.cat(v).view(h, w, -1) for k, v in lists.items()}
+    def update_to_step(self, step: int) -> None:
+        """nerfstudio Model.update_to_step: fast-forward the step-dependent schedules when a checkpoint is resumed
+        (the reference relies on the BEFORE_TRAIN_ITERATION callbacks, which fire on the first resumed iteration)."""
+        for sched in (self.sched_window_deform, self.sched_window_hash_encodings, self.sched_eps_depth):
+            if sched is not None:
+                sched.update(step)
 
     # ------------------------------------------------------------------ losses / metrics (models/base.py)
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
@@ -530,6 +527,79 @@ class NeRSembleNGPModel(nn.Module):
             mask = batch["alpha_map"].squeeze(1).to(rgb.device) > 127
             md["psnr_masked"] = psnr(rgb[mask], image[mask])
         return md
+
+    # ------------------------------------------------------------------ image metrics (evaluation)
+    @staticmethod
+    def _psnr(a: Tensor, b: Tensor) -> Tensor:
+        """torchmetrics PeakSignalNoiseRatio(data_range=1.0)."""
+        return -10.0 * torch.log10(torch.mean((a - b) ** 2))
+
+    @staticmethod
+    def _ssim(a: Tensor, b: Tensor, data_range: Optional[float] = None) -> Tensor:
+        """torchmetrics.functional.structural_similarity_index_measure defaults: 11x11 gaussian window, sigma 1.5,
+        k1 0.01, k2 0.03, reflect padding, mean over the image; data_range from the data when None.  a, b: [1,C,H,W]."""
+        if data_range is None:
+            data_range = float(max(a.max() - a.min(), b.max() - b.min()))
+        c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+        k = torch.arange(11, dtype=a.dtype, device=a.device) - 5
+        g = torch.exp(-(k / 1.5) ** 2 / 2); g = g / g.sum()
+        C = a.shape[1]
+        win = (g[:, None] * g[None, :]).expand(C, 1, 11, 11).contiguous()
+        pad = lambda t: torch.nn.functional.pad(t, (5, 5, 5, 5), mode="reflect")
+        conv = lambda t: torch.nn.functional.conv2d(pad(t), win, groups=C)
+        mu_a, mu_b = conv(a), conv(b)
+        s_aa, s_bb, s_ab = conv(a * a) - mu_a ** 2, conv(b * b) - mu_b ** 2, conv(a * b) - mu_a * mu_b
+        ssim = ((2 * mu_a * mu_b + c1) * (2 * s_ab + c2)) / ((mu_a ** 2 + mu_b ** 2 + c1) * (s_aa + s_bb + c2))
+        return ssim[..., 5:-5, 5:-5].mean() if min(ssim.shape[-2:]) > 10 else ssim.mean()
+
+    @staticmethod
+    def _colormap(x: Tensor, turbo: bool = False) -> Tensor:
+        """[H,W,1] in [0,1] -> [H,W,3].  nerfstudio's colormaps when importable (matplotlib tables), else a
+        dependency-free gradient (grey, or the polynomial turbo approximation) -- display only, no metric reads it."""
+        try:
+            from nerfstudio.utils import colormaps
+            from nerfstudio.utils.colormaps import ColormapOptions
+            return colormaps.apply_colormap(x, colormap_options=ColormapOptions(colormap="turbo")) if turbo else colormaps.apply_colormap(x)
+        except Exception:  # noqa: BLE001
+            x = torch.nan_to_num(x, 0.0).clamp(0, 1)
+            if not turbo:
+                return x.expand(*x.shape[:-1], 3)
+            r = (0.1357 + x * (4.5974 - x * (42.3277 - x * (130.5887 - x * (150.5666 - x * 58.1375))))).clamp(0, 1)
+            g = (0.0914 + x * (2.1856 + x * (4.8052 - x * (14.0195 - x * (4.2109 + x * 2.7747))))).clamp(0, 1)
+            b = (0.1067 + x * (12.5925 - x * (60.1097 - x * (109.0745 - x * (88.5066 - x * 26.8183))))).clamp(0, 1)
+            return torch.cat([r, g, b], -1)
+
+    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor]
+                                     ) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
+        """models/nersemble_instant_ngp.py:424-500: full-image PSNR / SSIM / (LPIPS) / MSE, the masked variants, and the
+        side-by-side images the trainer logs.  LPIPS needs pretrained network weights: `self.lpips` is an optional
+        callable; without one the `lpips*` keys are NaN."""
+        image = batch["image"].to(self.device)
+        rgb = outputs["rgb"]
+        acc_img = self._colormap(outputs["accumulation"])
+        depth = outputs["depth"]
+        near, far = float(torch.min(depth)), float(torch.max(depth))      # apply_depth_colormap: normalise, turbo, white where acc = 0
+        depth_img = self._colormap(((depth - near) / (far - near + 1e-10)).clamp(0, 1), turbo=True)
+        depth_img = depth_img * outputs["accumulation"] + (1 - outputs["accumulation"])
+        error_img = self._colormap(((rgb - image) ** 2).mean(dim=-1, keepdim=True), turbo=True)
+        images_dict = {"img": torch.cat([image, rgb], dim=1), "accumulation": acc_img, "depth": depth_img, "error": error_img}
+        im, rg = torch.moveaxis(image, -1, 0)[None], torch.moveaxis(rgb, -1, 0)[None]
+        lp = (lambda a, b: float(self.lpips(a, b))) if self.lpips is not None else (lambda a, b: float("nan"))
+        metrics_dict = {"psnr": float(self._psnr(im, rg)), "ssim": float(self._ssim(im, rg)), "lpips": lp(im, rg),
+                        "mse": float(torch.nn.functional.mse_loss(im, rg)), "cam_id": float(batch["cam_ids"])}
+        if "deformation" in outputs:
+            d = outputs["deformation"]                      # scene-flow colouring: direction -> colour, magnitude -> saturation
+            mag = d.norm(dim=-1, keepdim=True)
+            images_dict["deformation"] = (0.5 + 0.5 * d / (mag.max() + 1e-10)).clamp(0, 1)
+        if "alpha_map" in batch:
+            am = torch.as_tensor(batch["alpha_map"]).to(rgb) / 255.
+            image_m = am * image + (1 - am)
+            rgb_m = am * rgb + (1 - am)
+            images_dict["img_masked"] = torch.cat([image_m, rgb_m], dim=1)
+            im_m, rg_m = torch.moveaxis(image_m, -1, 0)[None], torch.moveaxis(rgb_m, -1, 0)[None]
+            metrics_dict.update(psnr_masked=float(self._psnr(im_m, rg_m)), ssim_masked=float(self._ssim(im_m, rg_m)),
+                                lpips_masked=lp(im_m, rg_m), mse_masked=float(torch.nn.functional.mse_loss(im_m, rg_m)))
+        return metrics_dict, images_dict
 
     def get_param_groups(self) -> Dict[str, List[Parameter]]:
         """models/nersemble_instant_ngp.py:502-514."""

@@ -26,7 +26,8 @@ import torch
 def extract_top_k_connected_component(density_grid: np.ndarray, threshold: float = 0.6, sigma_thinning: float = 1,
                                       sigma_erosion: float = 2, K: int = 1) -> List[np.ndarray]:
     from scipy import ndimage
-    s = 1.0 / (1.0 + np.exp(-np.asarray(density_grid, dtype=np.float64)))
+    x = np.asarray(density_grid)                # the sigmoid runs in the grid's own dtype (float32 occs) like :11-12, :53
+    s = 1 / (1 + np.exp(-x))
     g = ((s - 0.5) * 2 * 255).astype(np.uint8)
     g = ndimage.gaussian_filter(g, sigma=sigma_thinning)
     binary = g >= 255 * threshold

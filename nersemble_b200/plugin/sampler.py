@@ -96,15 +96,18 @@ class OccGridEstimator(nn.Module):
     def _update(self, step: int, occ_eval_fn: Callable, occ_thre: float = 0.01, ema_decay: float = 0.95,
                 warmup_steps: int = 256) -> None:
         lvl_indices = self._get_all_cells() if step < warmup_steps else self._sample_uniform_and_occupied_cells(self.cells_per_lvl // 4)
+        ids, vals = [], []
         for lvl, indices in enumerate(lvl_indices):
             grid_coords = self.grid_coords[indices]
             x = (grid_coords + torch.rand_like(grid_coords, dtype=torch.float32)) / self.resolution
             x = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
-            occ = occ_eval_fn(x).squeeze(-1)
-            cell_ids = lvl * self.cells_per_lvl + indices
-            self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ.to(self.occs.dtype))
-        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
-        self.binaries = (self.occs > thre).view(self.binaries.shape)
+            vals.append(occ_eval_fn(x).squeeze(-1))
+            ids.append(lvl * self.cells_per_lvl + indices)
+        # occs[cell] = max(occs[cell] * decay, occ); thre = min(mean(occs[occs >= 0]), occ_thre); binaries = occs > thre
+        # -- one C-ABI call (nsb_occ_update): no boolean-index host sync, duplicates resolved deterministically
+        if not self.binaries.is_contiguous():
+            self.binaries = self.binaries.contiguous()
+        ops.occ_update(self.occs, self.binaries, torch.cat(ids), torch.cat(vals), ema_decay, occ_thre)
 
 
 class NeRSembleVolumetricSampler(nn.Module):

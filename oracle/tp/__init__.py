@@ -17,7 +17,8 @@ from . import nerfacc_cpu, nerfstudio_cpu, tcnn_cpu
 
 
 def flatten_eff_distloss(w, m, interval, ray_id):
-    """torch_efficient_distloss.flatten_eff_distloss [3P-mem]:
+    """torch_efficient_distloss.flatten_eff_distloss [3P-mem] (sunset1995/torch_efficient_distloss,
+    torch_efficient_distloss/eff_distloss.py: FlattenEffDistLoss.forward; unpinned in environment.yml:26):
     loss = (sum_i 1/3*interval_i*w_i^2 + sum_i 2*w_i*(m_i*W_<i - WM_<i)) / n_rays,
     n_rays = ray_id.max()+1; prefixes are per-ray exclusive sums."""
     if w.numel() == 0:

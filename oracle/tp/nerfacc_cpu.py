@@ -18,6 +18,22 @@ model_components/nersemble_deformation_renderer.py:22-25.
 The marcher is a per-ray Python loop in numpy float32 scalars with the operation order
 of the CUDA kernel (no fused multiply-add) so the B200 marcher can be bit-exact to it.
 PARITY UNPINNED for this layer (no nerfacc source / golden vectors available).
+
+Upstream map (nerfacc v0.5.2, KAIR-BAIR/nerfacc):
+  pack_info                          nerfacc/pack.py: pack_info (index_add_ counts, exclusive cumsum)
+  exclusive_sum                      nerfacc/scan.py: exclusive_sum (packed segments)
+  render_transmittance_from_density  nerfacc/volrend.py: render_transmittance_from_density (exp(-exclusive_sum(sigma*dt)))
+  render_weight_from_density         nerfacc/volrend.py: render_weight_from_density (trans * alpha)
+  render_visibility_from_density     nerfacc/volrend.py: render_visibility_from_density ((T >= eps) & (alpha >= thre))
+  accumulate_along_rays              nerfacc/volrend.py: accumulate_along_rays (index_add_ over ray_indices)
+  ray_aabb_intersect_np              nerfacc/cuda/csrc/grid.cu: device::ray_aabb_intersect / include/utils_grid.cuh
+  _calc_dt                           nerfacc/cuda/csrc/include/utils_grid.cuh: calc_dt (clamp(t * cone_angle, dt_min, dt_max))
+  traverse_ray / traverse_grids      nerfacc/cuda/csrc/grid.cu: device::traverse_grids_kernel (sorted aabb hits over
+                                     levels, setup_traversal, the DDA with `continuous` skipping) behind
+                                     nerfacc/grid.py: traverse_grids
+  _enlarge_aabb                      nerfacc/grid.py: _enlarge_aabb
+  OccGridEstimator                   nerfacc/estimators/occ_grid.py: OccGridEstimator.{__init__, sampling,
+                                     update_every_n_steps, _get_all_cells, _sample_uniform_and_occupied_cells, _update}
 """
 from __future__ import annotations
 

@@ -9,6 +9,22 @@ not installed / not on disk.  Restated here (minimal, duck-typed):
   model_components.ray_samplers.VolumetricSampler, models.base_model.{Model,ModelConfig},
   models.instant_ngp.{NGPModel,InstantNGPModelConfig}, engine.callbacks.*
 Reference call sites are listed in SURVEY.md 8(c).  PARITY UNPINNED for this layer.
+
+Upstream map (nerfstudio v0.3.1, nerfstudio-project/nerfstudio):
+  Frustums / RaySamples / RayBundle   nerfstudio/cameras/rays.py (get_positions = o + d*(s+e)/2 [+ offsets], set_offsets,
+                                      get_row_major_sliced_ray_bundle)
+  SceneBox                            nerfstudio/data/scene_box.py: get_normalized_positions ((p - aabb[0]) / (aabb[1] - aabb[0]))
+  MLP                                 nerfstudio/field_components/mlp.py: MLP.build_nn_modules / forward (skip: cat([in_tensor, x]))
+  NeRFEncoding, expected_sin          nerfstudio/field_components/encodings.py, nerfstudio/utils/math.py
+  _TruncExp / trunc_exp               nerfstudio/field_components/activations.py (bwd: g * exp(clamp(x, -15, 15)))
+  shift_directions_for_tcnn           nerfstudio/fields/base_field.py
+  FieldHeadNames                      nerfstudio/field_components/field_heads.py
+  RGBRenderer / AccumulationRenderer / DepthRenderer   nerfstudio/model_components/renderers.py (combine_rgb, blend_background,
+                                      eval-mode nan_to_num + clamp_; 'expected' depth with global clip to steps.min/max)
+  VolumetricSampler                   nerfstudio/model_components/ray_samplers.py: VolumetricSampler.get_sigma_fn
+  TrainingCallback*                   nerfstudio/engine/callbacks.py
+  Model / ModelConfig                 nerfstudio/models/base_model.py
+  NGPModel / InstantNGPModelConfig    nerfstudio/models/instant_ngp.py
 """
 from __future__ import annotations
 

@@ -15,6 +15,24 @@ fields/nersemble_nerfacto_field.py:99-112,137-153,162-172,285,322,377.
 
 PARITY UNPINNED for this layer (no tcnn source / golden vectors available).
 Everything is plain torch on CPU so autograd gives the backward oracle too.
+
+Upstream map (tiny-cuda-nn master as of the reference's release, NVlabs/tiny-cuda-nn; a maintainer with the sources
+can diff function by function):
+  hashgrid_levels            include/tiny-cuda-nn/encodings/grid.h: GridEncodingTemplated ctor (offset table:
+                             params_in_level = min(next_multiple(res^n, 8), 2^log2_hashmap_size)), grid_scale(),
+                             grid_resolution()  [common_device.h in newer trees]
+  hashgrid_indices_weights   grid.h: kernel_grid<T,N_POS_DIMS,N_FEATURES_PER_LEVEL> (pos = fma(scale, x, 0.5); floor;
+                             Linear interpolation weights) + grid_index<N_DIMS,HASH_TYPE>() (stride walk while
+                             stride <= hashmap_size, else coherent_prime_hash: primes 1, 2654435761, 805459861;
+                             `% hashmap_size`)
+  HashGridEncoding           grid.h kernel_grid output layout [level][feature] + bindings/torch/tinycudann/modules.py
+                             Module.forward (input cast to float, params fp32 -> half per call, batch padded to 128)
+  IdentityEncoding           include/tiny-cuda-nn/encodings/identity.h: identity() kernel, padded outputs = 1.0
+  Network / fused_mlp        src/fully_fused_mlp.cu: kernel_mlp_fused / threadblock_layer (no bias, ReLU hidden, half
+                             accumulators), include/tiny-cuda-nn/networks/fully_fused_mlp.h (weight matrices [out,in]
+                             row-major, consecutive; padded_output_width = next_multiple(n_out, 16)),
+                             src/network.cu / network_with_input_encoding.h (encoding alignment to 16)
+  Network init               fully_fused_mlp.cu: initialize_params -> xavier_uniform per matrix; grid: U(-1e-4, 1e-4)
 """
 from __future__ import annotations
 

@@ -155,3 +155,59 @@ def test_fused_losses_match_the_torch_formulation_values_and_gradients(training)
     for a, b, name in zip(g_f, g_t, ("weights", "rgb", "acc", "depth")):
         scale = b.abs().max().item() + 1e-12
         assert (a - b).abs().max().item() <= 2e-4 * scale, (name, (a - b).abs().max().item(), scale)
+
+
+def test_fused_fields_adam_cooperates_with_grad_scaler():
+    """engine/nersemble_trainer.py:182-186 trains with `scaler.scale(loss).backward(); scaler.step(opt); scaler.update()`.
+    The parked rank-1 table gradient is no `.grad`: FusedFieldsAdam must unscale it itself (moments at the TRUE gradient
+    scale whatever the scaler does), and a non-finite parked gradient must skip the whole step and back the scale off."""
+    from nersemble_b200.optim import FusedFieldsAdam
+    from nersemble_b200.plugin.components import HashEnsemble, HashEnsembleConfig, TCNNHashEncodingConfig
+    gen = torch.Generator().manual_seed(3)
+
+    def make():
+        he = HashEnsemble(HashEnsembleConfig(32, TCNNHashEncodingConfig(log2_hashmap_size=12), True, True), seed=1).to(DEV)
+        other = torch.nn.Parameter(torch.ones(7, device=DEV))
+        return he, other, FusedFieldsAdam([he.tables, other], lr=5e-3, eps=1e-15)
+
+    E = make()[0].tables.shape[0]
+    pends = [_rand_pending(E, 4, gen)[0] for _ in range(3)]
+    og = [torch.randn(7, generator=gen).to(DEV) for _ in range(3)]
+
+    def run(scale_seq, use_scaler):
+        he, other, opt = make()
+        scaler = torch.amp.GradScaler("cuda", init_scale=scale_seq[0], growth_interval=10 ** 9) if use_scaler else None
+        if use_scaler:
+            scaler.scale(torch.zeros(1, device=DEV))         # lazy initialisation of the scale tensor
+        for it in range(3):
+            s = scale_seq[it]
+            opt.zero_grad()
+            he.pending_table_grad = {**pends[it], "g_rank1": pends[it]["g_rank1"] * s, "slots_are_timesteps": True}
+            other.grad = og[it] * s
+            if use_scaler:
+                scaler._scale.fill_(s)                       # what backoff/growth would do between steps
+                scaler.step(opt); scaler.update()
+                assert not opt.last_step_skipped
+            else:
+                opt.step()
+        st = opt.state[he.tables]
+        return he.tables.detach().clone(), st["exp_avg_sq"].clone(), other.detach().clone()
+
+    t_ref, v_ref, o_ref = run([1.0, 1.0, 1.0], False)
+    t_amp, v_amp, o_amp = run([65536.0, 1024.0, 32768.0], True)          # a scale that changes between steps
+    torch.testing.assert_close(v_amp, v_ref, rtol=1e-4, atol=1e-30)      # second moments at the true gradient scale
+    assert (t_amp - t_ref).abs().max().item() < 5e-3 * 1e-3
+    torch.testing.assert_close(o_amp, o_ref, rtol=1e-5, atol=1e-7)
+
+    # a non-finite gradient (the training backward poisons mlp_base's .grad when the table side overflows, see
+    # test_plugin_gpu.py): the WHOLE step is skipped -- table, moments, the other parameter untouched -- and the scale halves
+    he, other, opt = make()
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    scaler.scale(torch.zeros(1, device=DEV))
+    t0 = he.tables.detach().clone()
+    he.pending_table_grad = {**pends[0], "slots_are_timesteps": True}
+    other.grad = og[0] * 1024.0
+    other.grad[3] = float("nan")
+    scaler.step(opt); scaler.update()
+    assert opt.last_step_skipped and torch.equal(he.tables.detach(), t0) and torch.equal(other.detach(), torch.ones(7, device=DEV))
+    assert len(opt.state[he.tables]) == 0 and scaler.get_scale() == 512.0 and he.pending_table_grad is None

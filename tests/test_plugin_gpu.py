@@ -383,3 +383,65 @@ def test_training_step_gradients_vs_reference_glue_golden():
     cos = torch.nn.functional.cosine_similarity(flat[pick].reshape(1, -1).double(), g["tables_grad_sample"].reshape(1, -1).double()).item()
     assert cos > 0.99, cos
     assert abs((flat.double() ** 2).sum().item() / g["tables_grad_sums"][1].item() - 1.0) < 0.25
+
+
+def test_occupancy_update_vs_nerfacc_oracle(monkeypatch):
+    """OccGridEstimator._update (a14) against oracle/tp/nerfacc_cpu.OccGridEstimator._update on the SAME random draws
+    (torch.rand_like / torch.randint are patched to draw on the CPU from one seeded generator and move to the caller's
+    device): two warm-up steps over all cells, then two post-warm-up steps (uniform + occupied cells, WITH duplicate
+    cell ids).  Cells evaluated once must agree with the oracle; a cell evaluated k times must hold
+    max(old * decay, max of its k candidates) -- a valid outcome of nerfacc's order-dependent indexed assignment."""
+    from nersemble_b200.plugin.sampler import OccGridEstimator
+    from oracle.tp import nerfacc_cpu
+    aabb = torch.tensor([-2.5, -1.8, -2.5, 2.2, 1.8, 2.0])
+    res, decay, occ_thre = 64, 0.95, 1e-2
+    real_randint = torch.randint
+
+    def occ_fn(x):      # analytic density blob * step: the same float32 arithmetic on both devices up to exp() ulps
+        c = torch.tensor([0.1, -0.2, 0.3], device=x.device)
+        return 40.0 * torch.exp(-((x - c) ** 2).sum(-1, keepdim=True) / 0.8) * 0.011
+
+    def patch(seed):
+        gen = torch.Generator().manual_seed(seed)
+        monkeypatch.setattr(torch, "rand_like", lambda t, **kw: torch.rand(t.shape, generator=gen).to(t.device))
+        monkeypatch.setattr(torch, "randint", lambda high, size, **kw: real_randint(high, size, generator=gen).to(kw.get("device", "cpu")))
+
+    got = OccGridEstimator(aabb, resolution=res, levels=1).to(DEV).train()
+    want = nerfacc_cpu.OccGridEstimator(aabb, resolution=res, levels=1).train()
+    n_dup_total = 0
+    for step, seed in ((0, 1), (16, 2), (4096, 3), (4112, 4)):
+        prev, prev_bin = want.occs.clone(), want.binaries.clone()
+        for est in (got, want):
+            patch(seed)
+            est._update(step=step, occ_eval_fn=occ_fn, occ_thre=occ_thre, ema_decay=decay, warmup_steps=256)
+            monkeypatch.undo()
+        g_occs = got.occs.cpu()
+        if step < 256:
+            torch.testing.assert_close(g_occs, want.occs, rtol=2e-6, atol=1e-9)
+        else:
+            gen = torch.Generator().manual_seed(seed)           # rebuild the draws of _sample_uniform_and_occupied_cells
+            n = want.cells_per_lvl // 4
+            idx = real_randint(want.cells_per_lvl, (n,), generator=gen)
+            occ_idx = torch.nonzero(prev_bin.flatten())[:, 0]
+            if n < len(occ_idx):
+                occ_idx = occ_idx[real_randint(len(occ_idx), (n,), generator=gen)]
+            idx = torch.cat([idx, occ_idx])
+            x = (want.grid_coords[idx] + torch.rand((idx.numel(), 3), generator=gen)) / want.resolution
+            x = want.aabbs[0, :3] + x * (want.aabbs[0, 3:] - want.aabbs[0, :3])
+            amax = (prev * decay).scatter_reduce(0, idx, occ_fn(x).squeeze(-1), reduce="amax", include_self=True)
+            cnt = torch.bincount(idx, minlength=want.cells_per_lvl)
+            once, touched = cnt == 1, cnt > 0
+            n_dup_total += int((cnt > 1).sum())
+            torch.testing.assert_close(g_occs[once], want.occs[once], rtol=2e-6, atol=1e-9)      # vs the nerfacc restatement
+            torch.testing.assert_close(g_occs[touched], amax[touched], rtol=2e-6, atol=1e-9)    # duplicates: largest candidate
+            assert torch.equal(g_occs[~touched], prev[~touched])
+            want.occs.copy_(torch.where(touched, amax, prev))
+        # threshold / binaries: identical wherever occs is not within rounding of the threshold
+        thre = torch.clamp(want.occs[want.occs >= 0].mean(), max=occ_thre)
+        want_bin = want.occs > thre
+        safe = (want.occs - thre).abs() > 1e-6
+        assert torch.equal(got.binaries.cpu().flatten()[safe], want_bin[safe])
+        # continue from the CUDA state so that both sides draw the same occupied cells in the next step
+        want.occs.copy_(g_occs); want.binaries = got.binaries.cpu().clone()
+    assert n_dup_total > 100
+    assert 0.0 < float(got.binaries.float().mean()) < 1.0

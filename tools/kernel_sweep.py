@@ -7,7 +7,7 @@ import bench
 from nersemble_b200 import ops
 
 dev = torch.device("cuda", 0)
-P = bench.build_native_params(dev)
+P = bench.native_params(bench.synthetic_params(), dev)
 o, d, t = bench.synthetic_rays(bench.RAYS, 1000, dev)
 ts, te, ri, info = ops.march_fixed(o, d, P.aabb, bench.SAMPLES_PER_RAY, bench.STEP, bench.NEAR)
 n = ts.numel()

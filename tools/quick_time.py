@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from nersemble_b200 import ops
 dev = torch.device("cuda", 0)
-P = bench.build_native_params(dev)
+P = bench.native_params(bench.synthetic_params(), dev)
 o, d, t = bench.synthetic_rays(bench.RAYS, 1000, dev)
 ts, te, ri, info = ops.march_fixed(o, d, P.aabb, bench.SAMPLES_PER_RAY, bench.STEP, bench.NEAR)
 kw = dict(origins=o, directions=d, ray_times=t, t_starts=ts, t_ends=te, ray_indices=ri)
@@ -18,4 +18,4 @@ def timeit(fn, reps=10):
 full = timeit(lambda: ops.field_forward(P, window_hash=32.0, window_deform=7.0, want=("sigma", "rgb", "offsets"), **kw))
 nod = timeit(lambda: ops.field_forward(P, window_hash=32.0, window_deform=None, use_deformation=False, want=("sigma", "rgb"), **kw))
 off = timeit(lambda: ops.field_forward(P, window_hash=32.0, window_deform=7.0, want=("offsets",), **kw))
-print(f"CTAS={os.environ.get('NSB_CTAS_PER_SM','2')} STAGGER={os.environ.get('NSB_STAGGER_NS','0')}: full {full:.3f}  no_deform {nod:.3f}  offsets_only {off:.3f}")
+print(f"field kernel ms: full {full:.3f}  no_deform {nod:.3f}  offsets_only {off:.3f}")
