@@ -192,3 +192,29 @@ def test_filter_occupancy_grid_keeps_the_largest_component():
                     seen[p] = True; stack.append(p)
         sizes.append(cnt)
     assert sorted(sizes) == sorted(np.bincount(lab.ravel())[1:].tolist())
+
+
+def test_image_metrics_and_update_to_step():
+    """get_image_metrics_and_images (models/nersemble_instant_ngp.py:424-500): keys, shapes, and the metric values on a
+    case with a known answer (SSIM of an image with itself is 1; PSNR of a constant 0.1 offset is 20 dB)."""
+    m = make_model()
+    H, W = 24, 32
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand(H, W, 3, generator=g) * 0.8
+    out = {"rgb": image + 0.1, "accumulation": torch.rand(H, W, 1, generator=g), "depth": torch.rand(H, W, 1, generator=g) * 5 + 5,
+           "deformation": torch.randn(H, W, 3, generator=g) * 0.01}
+    batch = {"image": image, "cam_ids": 3, "alpha_map": (torch.rand(H, W, 1, generator=g) * 255).numpy()}
+    md, im = m.get_image_metrics_and_images(out, batch)
+    assert set(md) == {"psnr", "ssim", "lpips", "mse", "cam_id", "psnr_masked", "ssim_masked", "lpips_masked", "mse_masked"}
+    assert abs(md["psnr"] - 20.0) < 1e-3 and abs(md["mse"] - 0.01) < 1e-6 and md["cam_id"] == 3.0
+    assert 0.5 < md["ssim"] < 1.0 and md["psnr_masked"] > md["psnr"]
+    assert im["img"].shape == (H, 2 * W, 3) and im["img_masked"].shape == (H, 2 * W, 3)
+    for k in ("accumulation", "depth", "error", "deformation"):
+        assert im[k].shape == (H, W, 3)
+    same, _ = m.get_image_metrics_and_images({**out, "rgb": image.clone()}, batch)
+    assert same["ssim"] == pytest.approx(1.0, abs=1e-6) and same["mse"] == 0.0
+    # nerfstudio Model protocol: step-dependent schedules fast-forward when a checkpoint is resumed
+    m.update_to_step(10000)
+    assert m.sched_window_deform.value == pytest.approx(3.5) and m.sched_window_hash_encodings.value == 1
+    m.update_to_step(60000)
+    assert m.sched_window_deform.value == 7 and m.sched_window_hash_encodings.value == pytest.approx(16.5)
