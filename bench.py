@@ -221,11 +221,28 @@ def cpu_oracle(S, o, d, times, repeats=5, mode="none"):
     import torch
     from oracle import pipeline as pl
     from oracle.tp.tcnn_cpu import Precision
-    threads = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    torch.set_num_threads(threads)
+    avail = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     P = oracle_field_params(S)
     Precision.mode = mode
     ts, te, ri = pl.fixed_samples(o, d, P.aabb, SAMPLES_PER_RAY, STEP, near=NEAR)
+    # thread count: the oracle is gather-bound torch code that does NOT scale to every hardware thread (r1: the same
+    # code gave 0.0007 .. 0.0089 M samples/s between boxes with torch.set_num_threads(os.cpu_count())); calibrate on
+    # 8 rays and keep the fastest setting -- `cores` reports what was used
+    global _ORACLE_THREADS
+    if "_ORACLE_THREADS" not in globals():
+        best = None
+        n8 = 8 * SAMPLES_PER_RAY
+        for c in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+            torch.set_num_threads(c)
+            with torch.no_grad():
+                for it in range(2):
+                    t0 = time.perf_counter()
+                    pl.render(P, o[:8], d[:8], times[:8], ts[:n8], te[:n8], ri[:n8], window_hash=32.0, window_deform=7.0, training=False)
+                    dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, c)
+        _ORACLE_THREADS = best[1]
+    torch.set_num_threads(_ORACLE_THREADS)
     secs, out = [], None
     with torch.no_grad():
         for it in range(repeats + 1):

@@ -323,6 +323,46 @@ int nsb_occ_update(float *occs, uint8_t *binaries, int64_t n_cells, const int64_
                    int64_t n, float ema_decay, float occ_thre, void *scratch, void *stream);
 size_t nsb_occ_update_scratch_bytes(int64_t n_cells);
 
+/* ONE-LAUNCH fused inference render (SURVEY 8b `nsb_render_forward`; models/nersemble_instant_ngp.py:280-364 in eval
+ * mode): sampler (fixed-stride march or nerfacc occupancy march: count -> scan -> fill) -> fused field kernel
+ * (deformation MLP, hash ensemble, density / colour MLPs) -> alpha compositing + global depth clip, as phases of one
+ * persistent cooperative kernel (grid = number of SMs) separated by grid-wide barriers.  The packed-sample count never
+ * leaves the device, so the call is free of host synchronisation; the per-sample arrays live in a caller-provided
+ * workspace of `capacity` samples (an upper bound such as n_rays * ceil(aabb diagonal / step); if the march produces
+ * more, the samples beyond it are dropped and `status` in the workspace header is set to 1).
+ * Same device code as nsb_march_* / nsb_field_forward / nsb_composite_forward: results are bit-identical to that path. */
+typedef struct nsb_render_args {
+    int64_t n_rays;
+    const float *origins, *directions; /* [n_rays][3] */
+    const float *ray_times;            /* [n_rays] in [0,1] or NULL */
+    int32_t sampler;                   /* 0: fixed-stride march (n_per_ray steps from max(t_enter, near_plane)); 1: occupancy march */
+    int32_t n_per_ray;                 /* sampler 0 */
+    float near_plane;                  /* sampler 0 */
+    const float *near_planes, *far_planes; /* sampler 1: [n_rays] (jitter already added) */
+    const uint8_t *binaries;           /* sampler 1: [levels][res][res][res] */
+    const float *aabbs;                /* sampler 1: [levels][6] */
+    int32_t levels, res;
+    float step, cone_angle;
+    int32_t training;                  /* compositing mode (0: eval nan_to_num / clamp) */
+    int64_t capacity;                  /* samples the per-sample arrays below can hold */
+    float *t_starts, *t_ends;          /* [capacity] out */
+    int32_t *ray_indices;              /* [capacity] out */
+    float *sigma, *rgb, *offsets;      /* [capacity], [capacity][3], [capacity][3] out (offsets NULL iff no deformation) */
+    float *weights;                    /* [capacity] out or NULL */
+    int64_t *packed_info;              /* [n_rays][2] out: (start, count) */
+    float *out_rgb, *out_acc, *out_depth, *out_deform; /* [n_rays][3], [n_rays], [n_rays], [n_rays][3] | NULL */
+    void *workspace;                   /* nsb_render_workspace_bytes(n_rays) bytes; header = nsb_render_ws_header */
+} nsb_render_args;
+typedef struct nsb_render_ws_header {  /* first 64 bytes of the workspace; n_total / status are results */
+    uint32_t barrier;                  /* grid-barrier arrival counter (the call zeroes it) */
+    uint32_t depth_range[2];           /* ordered-int min / max of the sample midpoints */
+    int32_t status;                    /* 0 ok, 1 capacity exceeded */
+    int64_t n_total;                   /* packed samples the march produced */
+    int64_t reserved[5];
+} nsb_render_ws_header;
+size_t nsb_render_workspace_bytes(int64_t n_rays);
+int nsb_render_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_render_args *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,22 @@ class MarchArgs(C.Structure):
                 ("ray_indices", C.c_void_p)]
 
 
+class RenderArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("origins", C.c_void_p), ("directions", C.c_void_p), ("ray_times", C.c_void_p),
+                ("sampler", C.c_int32), ("n_per_ray", C.c_int32), ("near_plane", C.c_float),
+                ("near_planes", C.c_void_p), ("far_planes", C.c_void_p), ("binaries", C.c_void_p), ("aabbs", C.c_void_p),
+                ("levels", C.c_int32), ("res", C.c_int32), ("step", C.c_float), ("cone_angle", C.c_float),
+                ("training", C.c_int32), ("capacity", C.c_int64), ("t_starts", C.c_void_p), ("t_ends", C.c_void_p),
+                ("ray_indices", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p),
+                ("weights", C.c_void_p), ("packed_info", C.c_void_p), ("out_rgb", C.c_void_p), ("out_acc", C.c_void_p),
+                ("out_depth", C.c_void_p), ("out_deform", C.c_void_p), ("workspace", C.c_void_p)]
+
+
+class RenderWsHeader(C.Structure):
+    _fields_ = [("barrier", C.c_uint32), ("depth_range", C.c_uint32 * 2), ("status", C.c_int32), ("n_total", C.c_int64),
+                ("reserved", C.c_int64 * 5)]
+
+
 # every symbol include/nsb.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "nsb_version": (C.c_int, []),
@@ -137,6 +153,8 @@ SYMBOLS = {
     "nsb_occ_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                  C.c_float, C.c_void_p, C.c_void_p]),
     "nsb_occ_update_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "nsb_render_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "nsb_render_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(RenderArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -13,10 +13,12 @@
 // streamed through a cp.async.bulk ring; gather warps do nothing but the 128-byte-line hash gather).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #define NSB_NO_SPIN_GUARD 1   // see nsb_common.cuh mbar_wait
 #include "nsb_common.cuh"
 #include "nsb_gather.cuh"
+#include "nsb_march.cuh"
 #include "nsb_mlp.cuh"
 
 namespace nsb {
@@ -90,8 +92,14 @@ constexpr int kThreadsWS = (kTensorWarps + kGatherWarps) * 32;
 // setmaxnreg can only move registers WITHIN the CTA's allocation (inc blocks until a dec released
 // enough -- an inc that exceeds the pool hangs the kernel), so
 //   kTensorWarps*32*kTensorRegs + kGatherWarps*32*kGatherRegs <= 64512.
-constexpr int kGatherRegs = 64;
-constexpr int kTensorRegs = kMT == 1 ? 80 : 120;
+#ifndef NSB_GATHER_REGS
+#define NSB_GATHER_REGS 64
+#endif
+#ifndef NSB_TENSOR_REGS
+#define NSB_TENSOR_REGS (NSB_WS_MT == 1 ? 80 : 120)
+#endif
+constexpr int kGatherRegs = NSB_GATHER_REGS;
+constexpr int kTensorRegs = NSB_TENSOR_REGS;
 static_assert(kTensorWarps * 32 * kTensorRegs + kGatherWarps * 32 * kGatherRegs <= kThreadsWS * 72, "register pool");
 constexpr int kLaunchBoundWS = kThreadsWS;
 // Slab layout of deform_packed_tb: layers 0 and 4 without their 128 warp-code columns (those enter as the
@@ -124,6 +132,7 @@ struct alignas(128) SmemWS {
     uint64_t xs_full[2];
     uint64_t feat_full[2];
     int tile_ctr[2];
+    int64_t n_dyn;                          // fused render kernel: the packed sample count (known on the device only)
     alignas(16) float xs[2][NSB_TILE][4];  // normalised warped position (0 outside the box), w = timestep bits
     alignas(16) __half feat[2][NSB_TILE * kFeatStride];
     TensorScratch ts[kTensorWarps];
@@ -298,353 +307,224 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
     // suit the 88-register tensor role, and the 64-register gather role then pays for them with spills inside its
     // sample loop (measured: 2.59 -> 2.77 ms).  Each role derives its loop bounds itself.
 
-    if (FIELD) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(A.P.field_packed);
-        for (int i = tid; i < kFieldPackedU4; i += kThreadsWS) sm.field_w[i] = __ldg(src + i);
-    }
-    if (DEFORM)
-        for (int i = tid; i < kBiasFloats; i += kThreadsWS) sm.bias[i] = __ldg(A.P.deform_bias + i);
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], kTensorWarps);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm.xs_full[b], kTensorWarps);
-            mbar_init(&sm.feat_full[b], kGatherWarps);
-            sm.tile_ctr[b] = 0;
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
+#define NSB_N_SAMPLES A.S.n_samples
+#include "nsb_field_setup.inc"
     if (warp >= kTensorWarps) {
         // =============================== GATHER warps ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
-        if (!FIELD) return;
-        const int g = lane >> 2, q = lane & 3;
-        const uint8_t *tab = reinterpret_cast<const uint8_t *>(A.P.tables) + q * 32;
-        // 32-bit loop state: the gather role runs in 64 registers (n_tiles < 2^31 for any n_samples < 2^38)
-        uint32_t bid, nct;
-        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));     // volatile: not CSE'd with the tensor role's copy
-        asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(nct));
-        const int n_tiles32 = (int)((A.S.n_samples + NSB_TILE - 1) / NSB_TILE);
-        uint2 *bslot = sm.blend_b[warp - kTensorWarps];   // lane-private columns: no synchronisation needed
-        const BlendBSmem Bf{bslot + lane};
-        int cur_ts = -1;
-        for (int tile = (int)bid, it = 0; tile < n_tiles32; tile += (int)nct, ++it) {
-            const int b = it & 1;
-            const int rows_valid = (int)min((int64_t)NSB_TILE, A.S.n_samples - (int64_t)tile * NSB_TILE);
-            mbar_wait<20>(&sm.xs_full[b], (uint32_t)(it >> 1) & 1);
-            int row = 0, nrow = 0;
-            if (lane == 0) { row = atomicAdd(&sm.tile_ctr[b], 1); nrow = atomicAdd(&sm.tile_ctr[b], 1); }
-            row = __shfl_sync(0xffffffffu, row, 0);
-            nrow = __shfl_sync(0xffffffffu, nrow, 0);
-            GatherTile Ga;
-            QuadIdx Q;
-            Q.entry = 0; Q.w = 0.f;
-            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < rows_valid) {
-                xs = *reinterpret_cast<const float4 *>(sm.xs[b][row]);
-                Q = quad_compute<0>(A.P, xs.x, xs.y, xs.z, lane);
-                gather_issue_q<0, 0>(A.P, tab, Q, g, Ga);
-            }
-            while (row < rows_valid) {
-                // blend-weight fragments: rebuilt only when the timestep changes (a tile is 128 consecutive samples,
-                // i.e. one or two rays = one or two timesteps; the code row is a global load through an L1 that the
-                // table lines flood, at the head of the sample's dependent chain)
-                if (A.S.sample_blend_codes) {
-                    park_blend_b(make_blend_b(A.O, A.S.sample_blend_codes + ((int64_t)tile * NSB_TILE + row) * NSB_MEMBERS, lane),
-                                 bslot, lane);
-                } else if (__float_as_int(xs.w) != cur_ts) {
-                    cur_ts = __float_as_int(xs.w);
-                    park_blend_b(make_blend_b(A.O, A.P.blend_codes + (size_t)cur_ts * NSB_MEMBERS, lane), bslot, lane);
-                }
-                const bool has_next = nrow < rows_valid;
-                __half *feat_row = &sm.feat[b][row * kFeatStride];
-                float4 nx = xs;
-                // training: corner values are staged in this warp's 512 B of shared memory (one 32-bit address live across
-                // the sample instead of a 64-bit global pointer) and leave as ONE coalesced 16 B-per-lane store
-                __half2 *cv_row = SAVE ? reinterpret_cast<__half2 *>(sm.cv_stage[warp - kTensorWarps]) : nullptr;
-                gather_sample_quad<SAVE>(A.P, tab, xs.x, xs.y, xs.z,
-                                         has_next ? reinterpret_cast<const float4 *>(sm.xs[b][nrow]) : nullptr, nx, Bf, Ga, Q,
-                                         feat_row, cv_row, lane);
-                if (SAVE && A.out.corner_vals) {
-                    __syncwarp();
-                    reinterpret_cast<uint4 *>(A.out.corner_vals)[((int64_t)tile * NSB_TILE + row) * 32 + lane] =
-                        sm.cv_stage[warp - kTensorWarps][lane];
-                    __syncwarp();
-                }
-                if (A.out.feat) {   // feature output / training: the row goes to global too
-                    __syncwarp();
-                    reinterpret_cast<__half *>(A.out.feat)[((int64_t)tile * NSB_TILE + row) * 32 + lane] = feat_row[lane];
-                }
-                row = nrow;
-                xs = nx;
-                if (has_next) {
-                    int t = 0;
-                    if (lane == 0) t = atomicAdd(&sm.tile_ctr[b], 1);
-                    nrow = __shfl_sync(0xffffffffu, t, 0);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.feat_full[b]);
-        }
+        if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+#include "nsb_field_gather_role.inc"
         return;
     }
 
     // =============================== TENSOR warps ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
-    const int64_t n = A.S.n_samples;
-    const int64_t n_tiles = (n + NSB_TILE - 1) / NSB_TILE;
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    TensorScratch &ts = sm.ts[warp];
-    const int g = lane >> 2, q = lane & 3;
-    const float amin0 = A.P.aabb[0], amin1 = A.P.aabb[1], amin2 = A.P.aabb[2];
-    RingRefill rf;
-    rf.active = DEFORM && warp == 0 && lane == 0;
-    rf.total = (uint32_t)(my_tiles * kTbNumChunks);
-    rf.src = reinterpret_cast<const uint8_t *>(A.P.deform_packed_tb);
-    rf.gbase = 0;
-    if (DEFORM) {
-        for (uint32_t c = 0; c < kStages - 1; ++c) rf.issue(sm, c);
-        __syncwarp();
-    }
+    if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+#include "nsb_field_tensor_role.inc"
+#undef NSB_N_SAMPLES
+}
 
-    // D(i): per-row inputs + deformation of tile iteration `it` -> sm.xs[it&1]
-    auto deform_stage = [&](int64_t it) {
-        const int64_t tile = blockIdx.x + it * gridDim.x;
-        const int b = (int)(it & 1);
-        const int64_t row0 = tile * NSB_TILE + warp * kTRows;
-        __syncwarp();
-        if (lane < kTRows) {   // one row per lane
-            const int64_t s = row0 + lane;
-            float px = 0.f, py = 0.f, pz = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f, tt = 0.f;
-            if (s < n) {
-                if (A.S.origins != nullptr) {
-                    const int ri = A.S.ray_indices[s];
-                    const float mid = __fadd_rn(A.S.t_starts[s], A.S.t_ends[s]);
-                    ddx = A.S.directions[3 * (int64_t)ri + 0];
-                    ddy = A.S.directions[3 * (int64_t)ri + 1];
-                    ddz = A.S.directions[3 * (int64_t)ri + 2];
-                    px = __fadd_rn(A.S.origins[3 * (int64_t)ri + 0], __fmul_rn(__fmul_rn(ddx, mid), 0.5f));
-                    py = __fadd_rn(A.S.origins[3 * (int64_t)ri + 1], __fmul_rn(__fmul_rn(ddy, mid), 0.5f));
-                    pz = __fadd_rn(A.S.origins[3 * (int64_t)ri + 2], __fmul_rn(__fmul_rn(ddz, mid), 0.5f));
-                    if (A.S.ray_times) tt = A.S.ray_times[ri];
-                } else {
-                    px = A.S.positions[3 * s + 0]; py = A.S.positions[3 * s + 1]; pz = A.S.positions[3 * s + 2];
-                    ddx = ddy = ddz = 1.0f;
-                    if (A.S.sample_directions) {
-                        ddx = A.S.sample_directions[3 * s + 0]; ddy = A.S.sample_directions[3 * s + 1];
-                        ddz = A.S.sample_directions[3 * s + 2];
-                    }
-                    if (A.S.sample_times) tt = A.S.sample_times[s];
-                }
-            }
-            int tsi = __float2int_rn(__fmul_rn(tt, (float)(A.P.n_timesteps - 1)));
-            tsi = min(max(tsi, 0), A.P.n_timesteps - 1);
-            // component API (per-sample warp codes): the code-bias rows are indexed by SAMPLE instead of by timestep
-            // (n <= 2^24 and per-sample blend codes whenever the field is evaluated: checked on the host)
-            if (A.S.sample_code_bias) tsi = (int)min(s, n - 1);
-            ts.pos[lane][0] = px; ts.pos[lane][1] = py; ts.pos[lane][2] = pz; ts.pos[lane][3] = __int_as_float(tsi);
-            ts.dirsel[b][lane][0] = ddx; ts.dirsel[b][lane][1] = ddy; ts.dirsel[b][lane][2] = ddz;
-        }
-        __syncwarp();
-        float wx = 0.f, wy = 0.f, wz = 0.f;   // warped world position of row `lane`
-        if (DEFORM) {
-            rf.gbase = (uint32_t)(it * kTbNumChunks);
-            float pn[kMT][2][3];   // [m-tile][row g / g+8][xyz]
-#pragma unroll
-            for (int m = 0; m < kMT; ++m)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = m * 16 + g + 8 * h;
-                    pn[m][h][0] = __fdiv_rn(__fsub_rn(ts.pos[r][0], amin0), A.aabb_size[0]);
-                    pn[m][h][1] = __fdiv_rn(__fsub_rn(ts.pos[r][1], amin1), A.aabb_size[1]);
-                    pn[m][h][2] = __fdiv_rn(__fsub_rn(ts.pos[r][2], amin2), A.aabb_size[2]);
-                }
-#pragma unroll
-            for (int m = 0; m < kMT; ++m)
-#pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {
-                    uint32_t w4[4];
-#pragma unroll
-                    for (int hi = 0; hi < 2; ++hi) {
-                        const int i = kt * 8 + hi * 4 + q;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float e0 = 0.f, e1 = 0.f;
-                            if (i < 21) {
-                                const int d = i / 7, j = i - d * 7;
-                                const float pd = d == 0 ? pn[m][h][0] : (d == 1 ? pn[m][h][1] : pn[m][h][2]);   // no local-memory indexing
-                                const float arg = (6.283185307179586f * pd) * (float)(1 << j);
-                                const float wj = A.O.pe_window[j];
-                                e0 = wj * sinf(arg);
-                                e1 = wj * sinf(arg + 1.5707963267948966f);
-                            } else if (i == 21) {
-                                e0 = 6.283185307179586f * pn[m][h][0];
-                                e1 = 6.283185307179586f * pn[m][h][1];
-                            } else if (i == 22) {
-                                e0 = 6.283185307179586f * pn[m][h][2];
-                            }
-                            w4[hi * 2 + h] = pack_h2(e0, e1);
-                        }
-                    }
-                    ts.enc[m][kt][lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                    if (SAVE && kMT == 1 && A.out.deform_enc)
-                        reinterpret_cast<uint4 *>(A.out.deform_enc)[((tile * kTensorWarps + warp) * 3 + kt) * 32 + lane] =
-                            make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                }
-            // layers 0/4 read the per-timestep code bias: float offset of the bias row of rows g / g+8
-            uint32_t cb[kMT][2];
-#pragma unroll
-            for (int m = 0; m < kMT; ++m)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) cb[m][h] = (uint32_t)__float_as_int(ts.pos[m * 16 + g + 8 * h][3]) * 256u;
-            const float *const gcb = A.S.sample_code_bias ? A.S.sample_code_bias : A.P.deform_code_bias;
-            auto in_a = [&](int m, int kt, uint32_t(&a)[4]) {
-                const uint4 v = ts.enc[m][kt][lane];
-                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-            };
-            float acc[kMT][8][4];
-            // layer l reads act[src] (or the input), writes act[dst]
-            auto hid = [&](int src) {
-                return [&, src](int m, int kt, uint32_t(&a)[4]) {
-                    const uint4 v = ts.act[src][m][kt][lane];
-                    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-                };
-            };
-            auto hid1 = hid(1), hid0 = hid(0);
-            auto skip_a = [&](int m, int kt, uint32_t(&a)[4]) {
-                if (kt < 8) hid1(m, kt, a); else in_a(m, kt - 8, a);
-            };
-            auto save_act = [&](int layer, int buf) {   // training: keep the layer output for the backward pass
-                if (SAVE && kMT == 1 && A.out.deform_acts) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(A.out.deform_acts) + (((size_t)tile * kTensorWarps + warp) * 6 + layer) * 256;
-#pragma unroll 2      // fully unrolled = 32 transient registers in the 80-register tensor role
-                    for (int kt = 0; kt < 8; ++kt) dst[kt * 32 + lane] = ts.act[buf][0][kt][lane];
-                }
-            };
-            // layer 0: posenc (48) -> act[0]; the 128 warp-code columns are in the bias
-            zero_acc2(acc); ring_gemm2(acc, kT_L0, 3, in_a, sm, rf, lane); relu_store2<0, true>(acc, ts.act[0], nullptr, gcb, cb, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L0 + 3, 3, in_a, sm, rf, lane); relu_store2<1, true>(acc, ts.act[0], nullptr, gcb, cb, q, lane);
-            save_act(0, 0);
-            // layer 1: act[0] -> act[1]
-            zero_acc2(acc); ring_gemm2(acc, kT_L1, 8, hid0, sm, rf, lane); relu_store2<0, false>(acc, ts.act[1], sm.bias + 1 * 128, nullptr, cb, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L1 + 8, 8, hid0, sm, rf, lane); relu_store2<1, false>(acc, ts.act[1], sm.bias + 1 * 128, nullptr, cb, q, lane);
-            save_act(1, 1);
-            // layer 2: act[1] -> act[0]
-            zero_acc2(acc); ring_gemm2(acc, kT_L2, 8, hid1, sm, rf, lane); relu_store2<0, false>(acc, ts.act[0], sm.bias + 2 * 128, nullptr, cb, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L2 + 8, 8, hid1, sm, rf, lane); relu_store2<1, false>(acc, ts.act[0], sm.bias + 2 * 128, nullptr, cb, q, lane);
-            save_act(2, 0);
-            // layer 3: act[0] -> act[1]
-            zero_acc2(acc); ring_gemm2(acc, kT_L3, 8, hid0, sm, rf, lane); relu_store2<0, false>(acc, ts.act[1], sm.bias + 3 * 128, nullptr, cb, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L3 + 8, 8, hid0, sm, rf, lane); relu_store2<1, false>(acc, ts.act[1], sm.bias + 3 * 128, nullptr, cb, q, lane);
-            save_act(3, 1);
-            // layer 4 (skip): [act[1] | posenc] -> act[0]
-            zero_acc2(acc); ring_gemm2(acc, kT_L4, 11, skip_a, sm, rf, lane); relu_store2<0, true>(acc, ts.act[0], nullptr, gcb + 128, cb, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L4 + 11, 11, skip_a, sm, rf, lane); relu_store2<1, true>(acc, ts.act[0], nullptr, gcb + 128, cb, q, lane);
-            save_act(4, 0);
-            // layer 5: act[0] -> act[1]
-            zero_acc2(acc); ring_gemm2(acc, kT_L5, 8, hid0, sm, rf, lane); relu_store2<0, false>(acc, ts.act[1], sm.bias + 5 * 128, nullptr, cb, q, lane);
-            zero_acc2(acc); ring_gemm2(acc, kT_L5 + 8, 8, hid0, sm, rf, lane); relu_store2<1, false>(acc, ts.act[1], sm.bias + 5 * 128, nullptr, cb, q, lane);
-            save_act(5, 1);
-            // heads (last chunk: slabs 92,93)
-            float hacc[kMT][2][4];
-#pragma unroll
-            for (int m = 0; m < kMT; ++m)
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) hacc[m][i][k] = 0.f;
-            {
-                constexpr int chunk = kT_HEADS / kChunkSlabs, stage = chunk % kStages;
-                rf.issue(sm, rf.gbase + chunk + (kStages - 1));
-                __syncwarp();
-                mbar_wait<20>(&sm.full[stage], (chunk / kStages) & 1);
-                const uint4 *hw = reinterpret_cast<const uint4 *>(&sm.ring[stage][0]);
-#pragma unroll
-                for (int kt = 0; kt < 8; ++kt) {
-                    const uint4 bw = hw[kt * 32 + lane];
-#pragma unroll
-                    for (int m = 0; m < kMT; ++m) {
-                        uint32_t am[4];
-                        hid1(m, kt, am);
-                        mma16816(hacc[m][0], am, bw.x, bw.y);
-                        mma16816(hacc[m][1], am, bw.z, bw.w);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[stage]);
-            }
-            const float hb0 = sm.bias[6 * 128 + 2 * q], hb1 = sm.bias[6 * 128 + 2 * q + 1];
-#pragma unroll
-            for (int m = 0; m < kMT; ++m) {
-                const float c0 = hacc[m][0][0] + hb0, c1 = hacc[m][0][1] + hb1, c2 = hacc[m][0][2] + hb0, c3 = hacc[m][0][3] + hb1;
-                const int rsel = q & 1;
-                float vr[6];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int srcl = (lane & ~3) | k;
-                    const float a0 = __shfl_sync(0xffffffffu, c0, srcl), a1 = __shfl_sync(0xffffffffu, c1, srcl);
-                    const float b0 = __shfl_sync(0xffffffffu, c2, srcl), b1 = __shfl_sync(0xffffffffu, c3, srcl);
-                    vr[2 * k] = rsel ? b0 : a0;
-                    vr[2 * k + 1] = rsel ? b1 : a1;
-                }
-                const int r = m * 16 + g + 8 * rsel;
-                // recomputed (same ops => same bits as pn above): keeping pn live across the MLP costs 6 registers
-                const float p[3] = {__fdiv_rn(__fsub_rn(ts.pos[r][0], amin0), A.aabb_size[0]),
-                                    __fdiv_rn(__fsub_rn(ts.pos[r][1], amin1), A.aabb_size[1]),
-                                    __fdiv_rn(__fsub_rn(ts.pos[r][2], amin2), A.aabb_size[2])};
-                const float v[3] = {vr[0], vr[1], vr[2]}, rr[3] = {vr[3], vr[4], vr[5]};
-                float pw[3];
-                se3_apply(p, rr, v, pw);
-                __syncwarp();   // lanes q = 2, 3 read the rows lanes q = 0, 1 update below
-                if (q < 2) {
-                    const float o0 = pw[0] - p[0], o1 = pw[1] - p[1], o2 = pw[2] - p[2];
-                    const int64_t s = row0 + r;
-                    if (A.out.offsets && s < n) {
-                        A.out.offsets[3 * s + 0] = o0; A.out.offsets[3 * s + 1] = o1; A.out.offsets[3 * s + 2] = o2;
-                    }
-                    // reuse pos[] as the warped world position (normalised offsets added to world coords: ref quirk)
-                    ts.pos[r][0] += o0; ts.pos[r][1] += o1; ts.pos[r][2] += o2;
-                }
-            }
-            __syncwarp();
-        }
-        if (FIELD && lane < kTRows) {
-            wx = ts.pos[lane][0]; wy = ts.pos[lane][1]; wz = ts.pos[lane][2];
-            float x = __fdiv_rn(__fsub_rn(wx, amin0), A.aabb_size[0]);
-            float y = __fdiv_rn(__fsub_rn(wy, amin1), A.aabb_size[1]);
-            float z = __fdiv_rn(__fsub_rn(wz, amin2), A.aabb_size[2]);
-            const bool sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
-            float4 o4 = make_float4(sel ? x : 0.f, sel ? y : 0.f, sel ? z : 0.f, ts.pos[lane][3]);
-            *reinterpret_cast<float4 *>(sm.xs[b][warp * kTRows + lane]) = o4;
-            if (SAVE && A.out.xs && row0 + lane < n)
-                *reinterpret_cast<float4 *>(A.out.xs + 4 * (row0 + lane)) = make_float4(o4.x, o4.y, o4.z, sel ? 1.f : 0.f);
-            ts.dirsel[b][lane][3] = sel ? 1.f : 0.f;
-            if (warp == 0 && lane == 0) sm.tile_ctr[b] = 0;
-        }
-        if (FIELD) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.xs_full[b]);
-        }
-    };
+// ===========================================================================================
+// render_kernel_ws: sampler -> field -> composite in ONE launch (north star: "fused into one kernel").
+// A persistent cooperative kernel, one CTA per SM, whose phases are separated by grid-wide barriers:
+//   S  sampler.  Fixed stride: one warp per ray (march_fixed_warp).  Occupancy grid (nerfacc traverse_grids): count per ray
+//      (one thread per ray) | barrier | per-CTA chunk sums | barrier | exclusive scan -> packed_info, total | barrier |
+//      fill.  The packed sample count stays on the device (shared-memory word n_dyn): no host synchronisation.
+//   F  the field phase = the body of field_kernel_ws, textually (same setup / gather role / tensor role includes).
+//   C  compositing by the tensor warps (composite_ray, one warp per ray) | barrier | global depth clip.
+// Per-sample sigma / rgb / offsets cross from F to C through the caller's workspace (32 B per sample: L2-resident
+// at 2^20 samples, 0.2 % of the gather traffic).  Every phase runs the device code of the stand-alone kernels, so the
+// results are bit-identical to nsb_march_* + nsb_field_forward + nsb_composite_forward.
+// ===========================================================================================
+struct RenderKArgs {
+    FieldArgs F;              // S.* and out.* point into the caller's workspace
+    nsb_march_args M;         // occupancy sampler (counts / offsets / outputs in the workspace)
+    nsb_composite_args C;
+    int32_t sampler, n_per_ray;
+    float near_plane;
+    int64_t capacity;
+    nsb_render_ws_header *hdr;
+    int64_t *partials;        // [gridDim.x] chunk sums of the ray-count scan
+    int64_t *packed_info;     // [n_rays][2] out (C.packed_info is the same buffer, const)
+};
 
-    // it = -1 is the pipeline prologue: ONE inlined copy of deform_stage (two copies doubled the kernel's code size)
-#pragma unroll 1
-    for (int64_t it = -1; it < my_tiles; ++it) {
-        if (it + 1 < my_tiles) deform_stage(it + 1);
-        if (FIELD && it >= 0) {
-            const int64_t tile = blockIdx.x + it * gridDim.x;
-            const int b = (int)(it & 1);
-            mbar_wait<100>(&sm.feat_full[b], (uint32_t)(it >> 1) & 1);
-#pragma unroll 1
-            for (int m = 0; m < kMT; ++m)
-                field_mlp_tile<HEAD>(A, sm.field_w, &sm.feat[b][(warp * kTRows + m * 16) * kFeatStride],
-                                     &ts.dirsel[b][m * 16], tile * NSB_TILE + warp * kTRows + m * 16, n, lane);
-        }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Grid-wide barrier of the tensor warps (the only warps that run the sampler / compositing phases): one leader thread
+// per CTA on a global arrival counter (cooperative launch: all CTAs are resident).  `target` = arrivals expected so
+// far = (barrier index + 1) * gridDim.x; the counter is zeroed by the host before the launch.
+__device__ __forceinline__ void phase_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTensorWarps * 32) : "memory"); }
+__device__ __forceinline__ void grid_barrier(uint32_t *ctr, const uint32_t target) {
+    phase_sync();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_u32(ctr) < target) __nanosleep(40);
+        __threadfence();
     }
+    phase_sync();
+}
+
+__device__ __forceinline__ int64_t phase_sum_i64(int64_t v, int64_t *smem_warp /* [kTensorWarps] */, const int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    phase_sync();
+    if ((tid & 31) == 0) smem_warp[tid >> 5] = v;
+    phase_sync();
+    int64_t t = 0;
+    for (int w = 0; w < kTensorWarps; ++w) t += smem_warp[w];
+    return t;
+}
+
+// Where the extra phases run.  The 64-register gather role is allocated erratically by ptxas: with the sampler phase
+// inline, or as a call ahead of the role split, it went from 1 to 37-82 spill instructions (tools/spill_report.py;
+// a spill in the sample loop costs more than everything this kernel saves).  So BOTH extra phases run on the TENSOR
+// warps, as calls after the role split: the gather warps' code is the text of field_kernel_ws plus one named barrier
+// on which they wait for the sampler (and the sample count in shared memory) before their first tile.
+constexpr int kPhaseThreads = kTensorWarps * 32;
+
+#ifndef NSB_RK_SAMPLER_ATTR
+#define NSB_RK_SAMPLER_ATTR __forceinline__
+#endif
+#ifndef NSB_RK_COMPOSITE_ATTR
+#define NSB_RK_COMPOSITE_ATTR __forceinline__
+#endif
+// SAMPLER: 0 fixed-stride march fused; 1 occupancy march fused (count | scan | fill); 2 samples GIVEN: a preceding
+// launch (march_occ_coop_kernel, nsb_render.cu) filled the packed arrays and left the count in the workspace header.
+template <int SAMPLER>
+__device__ NSB_RK_SAMPLER_ATTR void render_sampler_phase(const RenderKArgs &K) {
+    constexpr bool OCC = SAMPLER == 1;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
+    const FieldArgs &A = K.F;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;      // tid < kPhaseThreads
+    uint32_t *const bar = &K.hdr->barrier;
+    const int64_t R = K.C.n_rays;
+    if (blockIdx.x == 0 && tid == 0) {
+        K.hdr->depth_range[0] = 0xffffffffu;
+        K.hdr->depth_range[1] = 0u;
+        if (SAMPLER != 2) K.hdr->status = 0;
+    }
+    if (SAMPLER == 2) {
+        if (tid == 0) sm.n_dyn = min(__ldcg(&K.hdr->n_total), K.capacity);
+        grid_barrier(bar, 1u * gridDim.x);          // depth_range initialised before any CTA composites
+    } else if (!OCC) {
+        for (int64_t r = (int64_t)blockIdx.x * kTensorWarps + warp; r < R; r += (int64_t)gridDim.x * kTensorWarps) {
+            const float t0 = march_fixed_t0(A.S.origins, A.S.directions, A.P.aabb, r, K.near_plane);
+            march_fixed_warp(t0, r, K.n_per_ray, K.M.step, K.M.t_starts, K.M.t_ends, K.M.ray_indices, lane);
+            if (lane == 0) { K.packed_info[2 * r] = r * K.n_per_ray; K.packed_info[2 * r + 1] = K.n_per_ray; }
+        }
+        if (tid == 0) {
+            sm.n_dyn = R * K.n_per_ray;     // the host sized the workspace for exactly this
+            if (blockIdx.x == 0) K.hdr->n_total = R * K.n_per_ray;
+        }
+        grid_barrier(bar, 1u * gridDim.x);
+    } else {
+        // S1: samples per ray
+        for (int64_t r = (int64_t)blockIdx.x * kPhaseThreads + tid; r < R; r += (int64_t)gridDim.x * kPhaseThreads)
+            K.M.counts[r] = march_occ_ray<false, 1>(K.M, r, 0, 0);
+        grid_barrier(bar, 1u * gridDim.x);
+        // S2: exclusive scan of the counts: CTA b owns the contiguous chunk [b * chunk, (b + 1) * chunk)
+        int64_t *red = reinterpret_cast<int64_t *>(sm.ring);          // scratch: the weight ring is not live yet
+        const int64_t chunk = (R + gridDim.x - 1) / gridDim.x;
+        const int64_t r0 = min(R, (int64_t)blockIdx.x * chunk), r1 = min(R, r0 + chunk);
+        {
+            int64_t v = 0;
+            for (int64_t r = r0 + tid; r < r1; r += kPhaseThreads) v += __ldcg(K.M.counts + r);
+            const int64_t tot = phase_sum_i64(v, red, tid);
+            if (tid == 0) K.partials[blockIdx.x] = tot;
+        }
+        grid_barrier(bar, 2u * gridDim.x);
+        {
+            int64_t before = 0, total = 0;
+            for (int b = tid; b < (int)gridDim.x; b += kPhaseThreads) {
+                const int64_t p = __ldcg(K.partials + b);
+                total += p;
+                if (b < (int)blockIdx.x) before += p;
+            }
+            total = phase_sum_i64(total, red, tid);
+            before = phase_sum_i64(before, red, tid);
+            if (tid == 0) {
+                sm.n_dyn = min(total, K.capacity);
+                if (blockIdx.x == 0) { K.hdr->n_total = total; if (total > K.capacity) K.hdr->status = 1; }
+            }
+            // slabs of kPhaseThreads rays: warp scan + warp totals in shared memory + running carry
+            int64_t carry = before;
+            for (int64_t s0 = r0; s0 < r1; s0 += kPhaseThreads) {
+                const int64_t r = s0 + tid;
+                const int64_t c = r < r1 ? (int64_t)__ldcg(K.M.counts + r) : 0;
+                int64_t inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int64_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += nb;
+                }
+                phase_sync();
+                if (lane == 31) red[warp] = inc;
+                phase_sync();
+                int64_t wbase = 0, slab = 0;
+                for (int w = 0; w < kTensorWarps; ++w) {
+                    const int64_t t = red[w];
+                    if (w < warp) wbase += t;
+                    slab += t;
+                }
+                if (r < r1) { K.packed_info[2 * r] = carry + wbase + inc - c; K.packed_info[2 * r + 1] = c; }
+                carry += slab;
+            }
+        }
+        grid_barrier(bar, 3u * gridDim.x);
+        // S3: fill (packed_info of a ray may come from another CTA: L2 reads)
+        for (int64_t r = (int64_t)blockIdx.x * kPhaseThreads + tid; r < R; r += (int64_t)gridDim.x * kPhaseThreads)
+            march_occ_ray<true, 1>(K.M, r, __ldcg(K.C.packed_info + 2 * r), K.capacity);
+        grid_barrier(bar, 4u * gridDim.x);
+    }
+}
+
+template <int SAMPLER>
+__device__ NSB_RK_COMPOSITE_ATTR void render_composite_phase(const RenderKArgs &K) {
+    constexpr uint32_t kBarS = SAMPLER == 1 ? 4u : 1u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *const bar = &K.hdr->barrier;
+    const int64_t R = K.C.n_rays;
+    grid_barrier(bar, (kBarS + 1u) * gridDim.x);
+    for (int64_t ray = (int64_t)blockIdx.x * kTensorWarps + warp; ray < R; ray += (int64_t)gridDim.x * kTensorWarps)
+        composite_ray(K.C, ray, lane);
+    grid_barrier(bar, (kBarS + 2u) * gridDim.x);
+    {   // DepthRenderer('expected'): clip to the global [min, max] of the sample midpoints
+        const uint32_t lo_u = __ldcg(&K.hdr->depth_range[0]), hi_u = __ldcg(&K.hdr->depth_range[1]);
+        // no sample in the whole batch: the reference inserts one fake sample with t_start = t_end = 1 on ray 0
+        // (nersemble_volumetric_sampler.py:110-114), whose midpoint clips every ray's depth (0) to 1
+        const float lo = lo_u != 0xffffffffu ? ordered_to_float(lo_u) : 1.0f, hi = lo_u != 0xffffffffu ? ordered_to_float(hi_u) : 1.0f;
+        for (int64_t r = (int64_t)blockIdx.x * kPhaseThreads + tid; r < R; r += (int64_t)gridDim.x * kPhaseThreads)
+            K.C.out_depth[r] = fminf(fmaxf(K.C.out_depth[r], lo), hi);
+    }
+}
+
+template <bool DEFORM, int SAMPLER>
+__global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_ws(const __grid_constant__ RenderKArgs K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
+    const FieldArgs &A = K.F;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FIELD = true, HEAD = true, SAVE = false;
+
+#define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
+#include "nsb_field_setup.inc"
+    if (warp >= kTensorWarps) {
+        if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+        asm volatile("bar.sync 2, %0;" ::"n"(kThreadsWS) : "memory");      // the sampler is done, sm.n_dyn is set
+#include "nsb_field_gather_role.inc"
+        return;
+    }
+    if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+    render_sampler_phase<SAMPLER>(K);                                      // S (ends with a grid barrier)
+    asm volatile("bar.sync 2, %0;" ::"n"(kThreadsWS) : "memory");
+    {
+#include "nsb_field_tensor_role.inc"
+    }
+#undef NSB_N_SAMPLES
+    render_composite_phase<SAMPLER>(K);                                    // C
 }
 
 // -------------------------------------------------------------------------------------------
@@ -780,4 +660,98 @@ extern "C" int nsb_hash_blend_forward(const nsb_field_params *params, const nsb_
     const int blocks = (int)std::min<int64_t>((warps_needed + 7) / 8, (int64_t)num_sms() * 8);
     hash_blend_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(H);
     return check_launch("hash_blend_kernel");
+}
+
+// -------------------------------------------------------------------------------------------
+// nsb_render_forward: host side of render_kernel_ws
+// -------------------------------------------------------------------------------------------
+namespace nsb {
+constexpr size_t kRenderHdrBytes = 64, kRenderPartials = 1024;
+static_assert(sizeof(nsb_render_ws_header) == kRenderHdrBytes, "workspace header layout");
+
+template <bool D, int SAMPLER>
+static int launch_render(const RenderKArgs &K, cudaStream_t st) {
+    const size_t smem = sizeof(SmemWS);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(render_kernel_ws<D, SAMPLER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(render_kernel_ws): %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    const int grid = num_sms();     // one CTA per SM, all resident: the grid barriers rely on it (cooperative launch checks)
+    if ((size_t)grid > kRenderPartials) { set_error("nsb_render_forward: more SMs than scan partials"); return 1; }
+    cudaError_t e = cudaMemsetAsync(&K.hdr->barrier, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) { set_error("nsb_render_forward: memset: %s", cudaGetErrorString(e)); return 2; }
+    void *kargs[] = {const_cast<RenderKArgs *>(&K)};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(render_kernel_ws<D, SAMPLER>), dim3(grid), dim3(kThreadsWS),
+                                    kargs, smem, st);
+    if (e != cudaSuccess) { set_error("render_kernel_ws: %s", cudaGetErrorString(e)); return 2; }
+    return check_launch("render_kernel_ws");
+}
+}  // namespace nsb
+
+extern "C" size_t nsb_render_workspace_bytes(int64_t n_rays) {
+    return kRenderHdrBytes + kRenderPartials * sizeof(int64_t) + (size_t)std::max<int64_t>(n_rays, 1) * sizeof(int32_t) + 64;
+}
+
+extern "C" int nsb_render_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_render_args *ra, void *stream) {
+    if (!params || !opts || !ra) { set_error("nsb_render_forward: null argument"); return 1; }
+    if (ra->n_rays <= 0) return 0;
+    if (params->levels.n_levels != NSB_MAX_LEVELS) { set_error("nsb_render_forward: n_levels must be 16"); return 1; }
+    const bool deform = opts->use_deformation != 0;
+    if (!ra->origins || !ra->directions || !ra->t_starts || !ra->t_ends || !ra->ray_indices || !ra->sigma || !ra->rgb ||
+        !ra->packed_info || !ra->out_rgb || !ra->out_acc || !ra->out_depth || !ra->workspace || (deform && !ra->offsets)) {
+        set_error("nsb_render_forward: null buffer");
+        return 1;
+    }
+    if (!params->tables || !params->field_packed || !params->blend_codes) { set_error("nsb_render_forward: tables/field_packed/blend_codes missing"); return 1; }
+    if (deform && (!params->deform_packed_tb || !params->deform_bias || !params->deform_code_bias)) {
+        set_error("nsb_render_forward: deformation parameters missing");
+        return 1;
+    }
+    if (params->n_timesteps < 1 || ra->capacity <= 0) { set_error("nsb_render_forward: n_timesteps < 1 or capacity <= 0"); return 1; }
+    if (ra->sampler == 0) {
+        if (ra->n_per_ray <= 0 || ra->capacity < ra->n_rays * (int64_t)ra->n_per_ray) { set_error("nsb_render_forward: capacity < n_rays * n_per_ray"); return 1; }
+    } else if (ra->sampler == 1 || ra->sampler == 3) {
+        if (!ra->near_planes || !ra->far_planes || !ra->binaries || !ra->aabbs) { set_error("nsb_render_forward: occupancy sampler arguments"); return 1; }
+        if (ra->levels < 1 || ra->levels > 8 || (ra->sampler == 3 && ra->levels != 1)) {
+            set_error("nsb_render_forward: levels must be in [1,8] (1 for the single-launch variant)");
+            return 1;
+        }
+    } else { set_error("nsb_render_forward: unknown sampler"); return 1; }
+    uint8_t *ws = reinterpret_cast<uint8_t *>(ra->workspace);
+    RenderKArgs K;
+    memset(&K, 0, sizeof(K));
+    K.hdr = reinterpret_cast<nsb_render_ws_header *>(ws);
+    K.partials = reinterpret_cast<int64_t *>(ws + kRenderHdrBytes);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + kRenderHdrBytes + kRenderPartials * sizeof(int64_t));
+    K.F.P = *params; K.F.O = *opts;
+    K.F.O.compute_rgb = 1;
+    for (int k = 0; k < 3; ++k) K.F.aabb_size[k] = params->aabb[3 + k] - params->aabb[k];
+    K.F.S.n_samples = 0;                 // device-side: sm.n_dyn
+    K.F.S.origins = ra->origins; K.F.S.directions = ra->directions; K.F.S.ray_times = ra->ray_times;
+    K.F.S.t_starts = ra->t_starts; K.F.S.t_ends = ra->t_ends; K.F.S.ray_indices = ra->ray_indices;
+    K.F.out.sigma = ra->sigma; K.F.out.rgb = ra->rgb; K.F.out.offsets = deform ? ra->offsets : nullptr;
+    K.M.n_rays = ra->n_rays; K.M.origins = ra->origins; K.M.directions = ra->directions;
+    K.M.near_planes = ra->near_planes; K.M.far_planes = ra->far_planes; K.M.binaries = ra->binaries; K.M.aabbs = ra->aabbs;
+    K.M.levels = ra->levels; K.M.res = ra->res; K.M.step = ra->step; K.M.cone_angle = ra->cone_angle;
+    K.M.counts = counts; K.M.offsets = nullptr; K.M.t_starts = ra->t_starts; K.M.t_ends = ra->t_ends; K.M.ray_indices = ra->ray_indices;
+    K.C.n_rays = ra->n_rays; K.C.n_samples = ra->capacity; K.C.packed_info = ra->packed_info; K.packed_info = ra->packed_info;
+    K.C.t_starts = ra->t_starts; K.C.t_ends = ra->t_ends; K.C.sigma = ra->sigma; K.C.rgb = ra->rgb;
+    K.C.offsets = deform ? ra->offsets : nullptr; K.C.training = ra->training;
+    K.C.out_rgb = ra->out_rgb; K.C.out_acc = ra->out_acc; K.C.out_depth = ra->out_depth;
+    K.C.out_deform = deform ? ra->out_deform : nullptr; K.C.out_weights = ra->weights;
+    K.C.workspace = K.hdr->depth_range;
+    K.sampler = ra->sampler; K.n_per_ray = ra->n_per_ray; K.near_plane = ra->near_plane; K.capacity = ra->capacity;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ra->sampler == 3) return deform ? launch_render<true, 1>(K, st) : launch_render<false, 1>(K, st);
+    if (ra->sampler == 1) {
+        // occupancy march as its own small cooperative launch (count | scan | fill, the count stays on the device), then
+        // field + composite in one: with the marcher inside render_kernel_ws ptxas spills 66-82 instructions in the gather
+        // role of the field phase (tools/spill_report.py); sampler == 3 selects that single-launch variant.
+        const int rc = launch_march_occ_coop(K.M, K.packed_info, K.hdr, K.partials, K.capacity, st);
+        if (rc) return rc;
+        return deform ? launch_render<true, 2>(K, st) : launch_render<false, 2>(K, st);
+    }
+    return deform ? launch_render<true, 0>(K, st) : launch_render<false, 0>(K, st);
 }

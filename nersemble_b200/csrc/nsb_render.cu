@@ -14,32 +14,24 @@
 #include <algorithm>
 
 #include "nsb_common.cuh"
+#include "nsb_march.cuh"
 
 namespace nsb {
 
 // ---------------------------------------------------------------------------------------------
 // fixed-stride marcher (BASELINE configs 1/2): n_per_ray steps from max(t_enter, near)
 // ---------------------------------------------------------------------------------------------
-__global__ void march_fixed_kernel(const float *__restrict__ origins, const float *__restrict__ directions,
-                                   int64_t n_rays, const float *__restrict__ aabb, int n_per_ray, float step,
-                                   float near_plane, float *__restrict__ t_starts, float *__restrict__ t_ends,
-                                   int32_t *__restrict__ ray_indices, int64_t *__restrict__ packed_info) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) march_fixed_kernel(const float *__restrict__ origins, const float *__restrict__ directions,
+                                                          int64_t n_rays, const float *__restrict__ aabb, int n_per_ray, float step,
+                                                          float near_plane, float *__restrict__ t_starts, float *__restrict__ t_ends,
+                                                          int32_t *__restrict__ ray_indices, int64_t *__restrict__ packed_info) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per ray
     if (r >= n_rays) return;
-    const float o[3] = {origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]};
-    const float d[3] = {directions[3 * r], directions[3 * r + 1], directions[3 * r + 2]};
-    float tmin, tmax;
-    const bool hit = ray_aabb(o, d, aabb, tmin, tmax);
-    float t = hit ? fmaxf(tmin, near_plane) : near_plane;
-    const int64_t base = r * n_per_ray;
-    for (int k = 0; k < n_per_ray; ++k) {
-        t_starts[base + k] = t;
-        t = __fadd_rn(t, step);
-        t_ends[base + k] = t;
-        ray_indices[base + k] = (int32_t)r;
-    }
-    if (packed_info) {
-        packed_info[2 * r] = base;
+    const float t0 = march_fixed_t0(origins, directions, aabb, r, near_plane);
+    march_fixed_warp(t0, r, n_per_ray, step, t_starts, t_ends, ray_indices, lane);
+    if (packed_info && lane == 0) {
+        packed_info[2 * r] = r * n_per_ray;
         packed_info[2 * r + 1] = n_per_ray;
     }
 }
@@ -51,158 +43,19 @@ struct MarchArgs {
     nsb_march_args a;
 };
 
-__device__ __forceinline__ float calc_dt(float t, float cone_angle, float dt_min, float dt_max) {
-    return fminf(fmaxf(__fmul_rn(t, cone_angle), dt_min), dt_max);
-}
 
 template <bool FILL>
 __global__ void __launch_bounds__(128) march_occ_kernel(const __grid_constant__ MarchArgs M) {
     const nsb_march_args &a = M.a;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_rays) return;
-    const float o[3] = {a.origins[3 * r], a.origins[3 * r + 1], a.origins[3 * r + 2]};
-    const float d[3] = {a.directions[3 * r], a.directions[3 * r + 1], a.directions[3 * r + 2]};
-    const float near_plane = a.near_planes[r], far_plane = a.far_planes[r];
-    const float step = a.step, cone = a.cone_angle;
-    if (!(isfinite(o[0]) && isfinite(o[1]) && isfinite(o[2]) && isfinite(d[0]) && isfinite(d[1]) && isfinite(d[2])) ||
-        (d[0] == 0.f && d[1] == 0.f && d[2] == 0.f)) {
-        if (!FILL) a.counts[r] = 0;   // degenerate ray: no samples (never hang)
-        return;
-    }
-    const int res = a.res, levels = a.levels;
-    const float eps = 1e-6f;
-    float inv_d[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) inv_d[k] = __fdiv_rn(1.0f, d[k]);
-
-    // sorted aabb intersections over levels (tiny insertion sort, stable like torch.sort on ties)
-    constexpr int kMaxLevels = 8;
-    float tv[2 * kMaxLevels];
-    int ti[2 * kMaxLevels];
-    bool hits[kMaxLevels];
-    for (int lv = 0; lv < levels; ++lv) {
-        float t0, t1;
-        bool h = ray_aabb(o, d, a.aabbs + 6 * lv, t0, t1);
-        hits[lv] = h;
-        tv[lv] = h ? t0 : INFINITY;
-        tv[levels + lv] = h ? t1 : INFINITY;
-        ti[lv] = lv;
-        ti[levels + lv] = levels + lv;
-    }
-    for (int i = 1; i < 2 * levels; ++i) {
-        float v = tv[i]; int id = ti[i]; int j = i - 1;
-        while (j >= 0 && tv[j] > v) { tv[j + 1] = tv[j]; ti[j + 1] = ti[j]; --j; }
-        tv[j + 1] = v; ti[j + 1] = id;
-    }
-
-    int64_t out = FILL ? a.offsets[r] : 0;
-    int32_t count = 0;
-    float t_last = near_plane;
-    bool continuous = false;
-    const float resf = (float)res;
-    for (int i = 0; i < 2 * levels - 1; ++i) {
-        const int level = ti[i] % levels;
-        if (!hits[level]) continue;
-        const float this_tmin = fmaxf(tv[i], near_plane);
-        const float this_tmax = fminf(tv[i + 1], far_plane);
-        if (!(this_tmin < this_tmax)) continue;
-        if (!continuous) {
-            if (step <= 0.0f) {
-                t_last = this_tmin;
-            } else {
-                while (true) {
-                    const float dt = calc_dt(t_last, cone, step, 1e10f);
-                    if (__fadd_rn(t_last, __fmul_rn(dt, 0.5f)) >= this_tmin) break;
-                    t_last = __fadd_rn(t_last, dt);
-                }
-            }
-        }
-        const float *ab = a.aabbs + 6 * level;
-        float tdist[3], delta[3];
-        int cur[3], fin[3], stp[3];
-        const float ts_eps = __fadd_rn(this_tmin, eps), te_eps = __fsub_rn(this_tmax, eps);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float ext = __fsub_rn(ab[3 + k], ab[k]);
-            const float voxel = __fdiv_rn(ext, resf);
-            const float rs = __fadd_rn(o[k], __fmul_rn(d[k], ts_eps));
-            const float re = __fadd_rn(o[k], __fmul_rn(d[k], te_eps));
-            int c = (int)__fmul_rn(__fdiv_rn(__fsub_rn(rs, ab[k]), ext), resf);
-            int f = (int)__fmul_rn(__fdiv_rn(__fsub_rn(re, ab[k]), ext), resf);
-            c = min(max(c, 0), res - 1);
-            f = min(max(f, 0), res - 1);
-            cur[k] = c; fin[k] = f;
-            const int start_index = c + (d[k] > 0.0f ? 1 : 0);
-            const float tmax_k =
-                __fadd_rn(__fmul_rn(__fadd_rn(ab[k], __fsub_rn(__fmul_rn((float)start_index, voxel), rs)), inv_d[k]), this_tmin);
-            const float sf = d[k] == 0.0f ? 0.0f : (d[k] > 0.0f ? 1.0f : -1.0f);
-            tdist[k] = d[k] == 0.0f ? this_tmax : tmax_k;
-            delta[k] = d[k] == 0.0f ? this_tmax : __fmul_rn(__fmul_rn(voxel, inv_d[k]), sf);
-            stp[k] = (int)sf;
-        }
-        const int ovf[3] = {fin[0] + stp[0], fin[1] + stp[1], fin[2] + stp[2]};
-        for (int guard = 0; guard < 3 * res + 3; ++guard) {
-            const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
-            const size_t cell = ((size_t)level * res + cur[0]) * res * res + (size_t)cur[1] * res + cur[2];
-            if (!a.binaries[cell]) {
-                if (step <= 0.0f) {
-                    t_last = t_trav;
-                } else {
-                    while (true) {
-                        const float dt = calc_dt(t_last, cone, step, 1e10f);
-                        if (__fadd_rn(t_last, __fmul_rn(dt, 0.5f)) >= t_trav) break;
-                        t_last = __fadd_rn(t_last, dt);
-                    }
-                }
-                continuous = false;
-            } else {
-                while (true) {
-                    float t_next;
-                    if (step <= 0.0f) {
-                        t_next = t_trav;
-                    } else {
-                        const float dt = calc_dt(t_last, cone, step, 1e10f);
-                        if (__fadd_rn(t_last, __fmul_rn(dt, 0.5f)) >= t_trav) break;
-                        t_next = __fadd_rn(t_last, dt);
-                    }
-                    if (FILL) {
-                        a.t_starts[out] = t_last;
-                        a.t_ends[out] = t_next;
-                        a.ray_indices[out] = (int32_t)r;
-                        ++out;
-                    }
-                    ++count;
-                    continuous = true;
-                    t_last = t_next;
-                    if (t_next >= t_trav) break;
-                }
-            }
-            int ax;
-            if (tdist[0] < tdist[1] && tdist[0] < tdist[2]) ax = 0;
-            else if (tdist[1] < tdist[2]) ax = 1;
-            else ax = 2;
-            // (dynamic register-array indexing avoided)
-            bool done;
-            if (ax == 0) { cur[0] += stp[0]; tdist[0] = __fadd_rn(tdist[0], delta[0]); done = cur[0] == ovf[0]; }
-            else if (ax == 1) { cur[1] += stp[1]; tdist[1] = __fadd_rn(tdist[1], delta[1]); done = cur[1] == ovf[1]; }
-            else { cur[2] += stp[2]; tdist[2] = __fadd_rn(tdist[2], delta[2]); done = cur[2] == ovf[2]; }
-            if (done) break;
-        }
-    }
+    const int32_t count = march_occ_ray<FILL>(a, r, FILL ? a.offsets[r] : 0, INT64_MAX);
     if (!FILL) a.counts[r] = count;
 }
 
 // ---------------------------------------------------------------------------------------------
 // visibility mask (nerfacc render_visibility_from_density): one warp per ray
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        float n = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += n;
-    }
-    return v;
-}
 
 __global__ void __launch_bounds__(256) visibility_kernel(const int64_t *__restrict__ packed_info, int64_t n_rays,
                                                          const float *__restrict__ t_starts,
@@ -240,66 +93,12 @@ struct CompArgs {
     nsb_composite_args a;
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ CompArgs C) {
-    const nsb_composite_args &a = C.a;
     const int lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (ray >= a.n_rays) return;
-    const int64_t start = a.packed_info[2 * ray], cnt = a.packed_info[2 * ray + 1];
-    float carry = 0.f;
-    float acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-    float mn = INFINITY, mx = -INFINITY;
-    for (int64_t b = 0; b < cnt; b += 32) {
-        const int64_t i = b + lane;
-        const bool ok = i < cnt;
-        const int64_t s = start + (ok ? i : 0);
-        const float ts = ok ? a.t_starts[s] : 0.f, te = ok ? a.t_ends[s] : 0.f;
-        const float sd = ok ? a.sigma[s] * (te - ts) : 0.f;
-        // render_weight_from_density: T = exp(-exclusive_sum(sigma*dt)), alpha = 1 - exp(-sigma*dt)
-        const float incl = warp_incl_scan(sd, lane);
-        const float excl = carry + (incl - sd);
-        const float w = ok ? expf(-excl) * (1.0f - expf(-sd)) : 0.f;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        if (ok) {
-            if (a.out_weights) a.out_weights[s] = w;
-            float r = a.rgb[3 * s], g = a.rgb[3 * s + 1], bl = a.rgb[3 * s + 2];
-            if (!a.training) {  // RGBRenderer eval path: nan_to_num before compositing
-                r = isnan(r) ? 0.f : (isinf(r) ? (r > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f) : r);
-                g = isnan(g) ? 0.f : (isinf(g) ? (g > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f) : g);
-                bl = isnan(bl) ? 0.f : (isinf(bl) ? (bl > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f) : bl);
-            }
-            const float mid = (ts + te) / 2.0f;
-            acc += w; cr += w * r; cg += w * g; cb += w * bl; dep += w * mid;
-            mn = fminf(mn, mid); mx = fmaxf(mx, mid);
-            if (a.offsets) { d0 += w * a.offsets[3 * s]; d1 += w * a.offsets[3 * s + 1]; d2 += w * a.offsets[3 * s + 2]; }
-        }
-    }
-    acc = warp_sum(acc); cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dep = warp_sum(dep);
-    if (a.offsets) { d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if (lane == 0) {
-        // white background: rgb + 1*(1-acc); eval clamps to [0,1]
-        float r = cr + (1.0f - acc), g = cg + (1.0f - acc), bl = cb + (1.0f - acc);
-        if (!a.training) { r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f); }
-        a.out_rgb[3 * ray] = r; a.out_rgb[3 * ray + 1] = g; a.out_rgb[3 * ray + 2] = bl;
-        a.out_acc[ray] = acc;
-        a.out_depth[ray] = dep / (acc + 1e-10f);   // clipped by depth_clip_kernel
-        if (a.out_deform) { a.out_deform[3 * ray] = d0; a.out_deform[3 * ray + 1] = d1; a.out_deform[3 * ray + 2] = d2; }
-        if (cnt > 0) {
-            atomicMin(&a.workspace[0], float_to_ordered(mn));
-            atomicMax(&a.workspace[1], float_to_ordered(mx));
-        }
-    }
+    if (ray >= C.a.n_rays) return;
+    composite_ray(C.a, ray, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +247,123 @@ __global__ void occ_binarise_kernel(const float *__restrict__ occs, int64_t n_ce
     binaries[i] = occs[i] > (isnan(mean) ? occ_thre : thre) ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// occupancy march in ONE cooperative launch: samples per ray | grid barrier | per-CTA chunk sums | barrier | exclusive
+// scan -> packed_info + total | barrier | fill.  No host synchronisation: the packed count goes to the workspace header
+// (nsb_render_ws_header.n_total) where the fused field + composite kernel (render_kernel_ws, sampler GIVEN) reads it.
+// ---------------------------------------------------------------------------------------------
+struct MarchCoopArgs {
+    nsb_march_args M;
+    int64_t *packed_info;
+    nsb_render_ws_header *hdr;
+    int64_t *partials;
+    int64_t capacity;
+};
+constexpr int kCoopThreads = 256;
+
+__device__ __forceinline__ void coop_grid_barrier(uint32_t *ctr, const uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v < target) __nanosleep(40);
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ int64_t coop_block_sum(int64_t v, int64_t *red, const int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    int64_t t = 0;
+    for (int w = 0; w < kCoopThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+template <int LV>
+__global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __grid_constant__ MarchCoopArgs K) {
+    __shared__ int64_t red[kCoopThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t R = K.M.n_rays;
+    uint32_t *const bar = &K.hdr->barrier;
+    for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
+        K.M.counts[r] = march_occ_ray<false, LV>(K.M, r, 0, 0);
+    coop_grid_barrier(bar, 1u * gridDim.x);
+    const int64_t chunk = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = min(R, (int64_t)blockIdx.x * chunk), r1 = min(R, r0 + chunk);
+    {
+        int64_t v = 0;
+        for (int64_t r = r0 + tid; r < r1; r += kCoopThreads) v += __ldcg(K.M.counts + r);
+        const int64_t tot = coop_block_sum(v, red, tid);
+        if (tid == 0) K.partials[blockIdx.x] = tot;
+    }
+    coop_grid_barrier(bar, 2u * gridDim.x);
+    {
+        int64_t before = 0, total = 0;
+        for (int b = tid; b < (int)gridDim.x; b += kCoopThreads) {
+            const int64_t p = __ldcg(K.partials + b);
+            total += p;
+            if (b < (int)blockIdx.x) before += p;
+        }
+        total = coop_block_sum(total, red, tid);
+        before = coop_block_sum(before, red, tid);
+        if (blockIdx.x == 0 && tid == 0) { K.hdr->n_total = total; K.hdr->status = total > K.capacity ? 1 : 0; }
+        int64_t carry = before;
+        for (int64_t s0 = r0; s0 < r1; s0 += kCoopThreads) {
+            const int64_t r = s0 + tid;
+            const int64_t c = r < r1 ? (int64_t)__ldcg(K.M.counts + r) : 0;
+            int64_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += nb;
+            }
+            __syncthreads();
+            if (lane == 31) red[warp] = inc;
+            __syncthreads();
+            int64_t wbase = 0, slab = 0;
+            for (int w = 0; w < kCoopThreads / 32; ++w) {
+                const int64_t t = red[w];
+                if (w < warp) wbase += t;
+                slab += t;
+            }
+            if (r < r1) { K.packed_info[2 * r] = carry + wbase + inc - c; K.packed_info[2 * r + 1] = c; }
+            carry += slab;
+        }
+    }
+    coop_grid_barrier(bar, 3u * gridDim.x);
+    for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
+        march_occ_ray<true, LV>(K.M, r, __ldcg(K.packed_info + 2 * r), K.capacity);
+}
+
+int launch_march_occ_coop(const nsb_march_args &M, int64_t *packed_info, nsb_render_ws_header *hdr, int64_t *partials,
+                          int64_t capacity, cudaStream_t st) {
+    MarchCoopArgs K;
+    K.M = M; K.packed_info = packed_info; K.hdr = hdr; K.partials = partials; K.capacity = capacity;
+    static int grid = 0;
+    if (grid == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_occ_coop_kernel<1>, kCoopThreads, 0);
+        grid = std::max(1, std::min(sms * std::max(1, std::min(per_sm, 4)), 1024));     // <= 1024 scan partials
+    }
+    cudaError_t e = cudaMemsetAsync(&hdr->barrier, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) { set_error("march_occ_coop: memset: %s", cudaGetErrorString(e)); return 2; }
+    void *kargs[] = {&K};
+    const void *fn = M.levels == 1 ? reinterpret_cast<const void *>(march_occ_coop_kernel<1>)
+                                   : reinterpret_cast<const void *>(march_occ_coop_kernel<0>);
+    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopThreads), kargs, 0, st);
+    if (e != cudaSuccess) { set_error("march_occ_coop_kernel: %s", cudaGetErrorString(e)); return 2; }
+    return check_launch("march_occ_coop_kernel");
+}
+
 }  // namespace nsb
 
 using namespace nsb;
@@ -460,8 +376,8 @@ extern "C" int nsb_march_fixed(const float *origins, const float *directions, in
         return 1;
     }
     if (n_rays <= 0 || n_per_ray <= 0) return 0;
-    const int threads = 128;
-    const int blocks = (int)((n_rays + threads - 1) / threads);
+    const int threads = 256;
+    const int blocks = (int)((n_rays + 7) / 8);
     march_fixed_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(origins, directions, n_rays, aabb6, n_per_ray, step,
                                                                    near_plane, t_starts, t_ends, ray_indices, packed_info);
     return check_launch("march_fixed_kernel");

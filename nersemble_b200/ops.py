@@ -624,6 +624,89 @@ def occ_update(occs: torch.Tensor, binaries: torch.Tensor, cell_ids: torch.Tenso
                                   float(ema_decay), float(occ_thre), _ptr(ws), _stream()), "nsb_occ_update")
 
 
+class RenderResult(dict):
+    """Per-ray outputs of render_rays plus lazy access to the packed per-sample arrays (`packed()` synchronises once)."""
+
+    def packed(self) -> Dict[str, torch.Tensor]:
+        b = self["_buffers"]
+        n = int(b["header"][2].item())                # n_total: the ONE host synchronisation, only when asked for
+        if n > b["capacity"]:
+            raise RuntimeError(f"render_rays: the march produced {n} samples, capacity {b['capacity']}")
+        out = {k: b[k][:n] for k in ("t_starts", "t_ends", "ray_indices", "sigma", "rgb", "offsets", "weights") if b.get(k) is not None}
+        out["weights"] = out["weights"][:, None]
+        return out
+
+
+def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=None, window_deform=None,
+                use_deformation=True, training=False, sampler: str = "occupancy", n_per_ray: int = 0,
+                near_plane: float = 0.0, near_planes=None, far_planes=None, binaries=None, aabbs=None,
+                step: float = 1e-3, cone_angle: float = 0.0, capacity: Optional[int] = None,
+                disable_initial=True, soft_transition=True, single_launch: bool = False) -> RenderResult:
+    """The fused inference render (nsb_render_forward): sampler -> field -> composite without a host synchronisation.
+    sampler 'fixed' (n_per_ray steps from the box entry: ONE launch) or 'occupancy' (nerfacc march of `binaries`
+    [levels,res,res,res] within per-ray near_planes / far_planes: the cooperative march launch + one fused launch;
+    single_launch=True marches inside the fused kernel, levels == 1 only).  Returns the per-ray outputs (rgb, accumulation,
+    depth, deformation, num_samples_per_ray, packed_info); `.packed()` gives the per-sample arrays (one sync).
+    capacity: per-sample workspace size; default = an upper bound of the march (rays x ceil(largest diagonal / step) + 2)."""
+    lib = _lib.load()
+    origins, directions = _f32c(origins).reshape(-1, 3), _f32c(directions).reshape(-1, 3)
+    ray_times = None if ray_times is None else _f32c(ray_times).reshape(-1)
+    _need_cuda(origins, directions, ray_times, near_planes, far_planes, binaries)
+    dev, R = origins.device, int(origins.shape[0])
+    a = _lib.RenderArgs()
+    keep = [origins, directions, ray_times]
+    a.n_rays, a.origins, a.directions, a.ray_times = R, _ptr(origins), _ptr(directions), _ptr(ray_times)
+    a.step, a.cone_angle, a.training = float(step), float(cone_angle), int(training)
+    if sampler == "fixed":
+        a.sampler, a.n_per_ray, a.near_plane = 0, int(n_per_ray), float(near_plane)
+        cap = R * int(n_per_ray)
+    elif sampler == "occupancy":
+        near_planes, far_planes = _f32c(near_planes).reshape(-1), _f32c(far_planes).reshape(-1)
+        b8 = binaries.detach().contiguous()
+        b8 = b8.view(torch.uint8) if b8.dtype == torch.bool else b8.to(torch.uint8)
+        levels, res = int(b8.shape[0]), int(b8.shape[1])
+        assert b8.shape[1] == b8.shape[2] == b8.shape[3], "cubic grids only"
+        ab = aabbs.detach().to(dev, _F32).reshape(levels, 6).contiguous()
+        keep += [near_planes, far_planes, b8, ab]
+        a.sampler = 3 if single_launch else 1
+        a.near_planes, a.far_planes, a.binaries, a.aabbs, a.levels, a.res = _ptr(near_planes), _ptr(far_planes), _ptr(b8), _ptr(ab), levels, res
+        if capacity is None:
+            diag = float((ab[:, 3:] - ab[:, :3]).norm(dim=-1).max())      # host-side: aabbs is a tiny constant buffer
+            capacity = R * (int(diag / float(step)) + 2 * levels + 2)
+        cap = int(capacity)
+    else:
+        raise ValueError(sampler)
+    cap = max(cap, 1)
+    a.capacity = cap
+    buf = {"capacity": cap,
+           "t_starts": torch.empty((cap,), dtype=_F32, device=dev), "t_ends": torch.empty((cap,), dtype=_F32, device=dev),
+           "ray_indices": torch.empty((cap,), dtype=torch.int32, device=dev),
+           "sigma": torch.empty((cap,), dtype=_F32, device=dev), "rgb": torch.empty((cap, 3), dtype=_F32, device=dev),
+           "offsets": torch.empty((cap, 3), dtype=_F32, device=dev) if use_deformation else None,
+           "weights": torch.empty((cap,), dtype=_F32, device=dev)}
+    a.t_starts, a.t_ends, a.ray_indices = _ptr(buf["t_starts"]), _ptr(buf["t_ends"]), _ptr(buf["ray_indices"])
+    a.sigma, a.rgb, a.offsets, a.weights = _ptr(buf["sigma"]), _ptr(buf["rgb"]), _ptr(buf["offsets"]), _ptr(buf["weights"])
+    info = torch.empty((R, 2), dtype=torch.int64, device=dev)
+    out = RenderResult(rgb=torch.empty((R, 3), dtype=_F32, device=dev), accumulation=torch.empty((R, 1), dtype=_F32, device=dev),
+                       depth=torch.empty((R, 1), dtype=_F32, device=dev), packed_info=info)
+    if use_deformation:
+        out["deformation"] = torch.empty((R, 3), dtype=_F32, device=dev)
+    a.packed_info, a.out_rgb, a.out_acc, a.out_depth = _ptr(info), _ptr(out["rgb"]), _ptr(out["accumulation"]), _ptr(out["depth"])
+    a.out_deform = _ptr(out.get("deformation"))
+    ws = torch.empty((int(lib.nsb_render_workspace_bytes(R)) + 7) // 8, dtype=torch.int64, device=dev)   # per call: results live in its header
+    a.workspace = _ptr(ws)
+    buf["header"] = ws          # int64 view: [barrier|depth0, depth1|status, n_total, ...]
+    out["_buffers"] = buf
+    out["_keep"] = keep
+    out["num_samples_per_ray"] = info[:, 1]
+    if R == 0:
+        return out
+    opts = make_opts(window_hash, window_deform, use_deformation, True, disable_initial, soft_transition)
+    cp = P.c_params()
+    _lib.check(lib.nsb_render_forward(C.byref(cp), C.byref(opts), C.byref(a), _stream()), "nsb_render_forward")
+    return out
+
+
 def render_packed(P: NativeParams, origins, directions, ray_times, t_starts, t_ends, ray_indices, packed_info, *,
                   window_hash=None, window_deform=None, use_deformation=True, training=False,
                   disable_initial=True, soft_transition=True) -> Dict[str, torch.Tensor]:

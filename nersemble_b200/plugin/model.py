@@ -180,6 +180,7 @@ class NeRSembleNGPModel(Model):
         self.sync_free_losses = True     # get_loss_dict without host syncs on CUDA (see _loss_dict_sync_free)
         self.fused_losses = True         # ... and, when the outputs come from get_outputs, in fused kernels (_loss_dict_fused)
         self.lpips = None                # optional callable(image[1,3,H,W], rgb[1,3,H,W]) -> scalar (needs pretrained weights)
+        self.use_fused_render = True     # eval renders: sampler -> field -> composite fused, no host sync (ops.render_rays)
 
     def populate_modules(self):
         """models/nersemble_instant_ngp.py:81-179 (+ BaseModel.populate_modules, base.py:38-47)."""
@@ -301,6 +302,45 @@ class NeRSembleNGPModel(Model):
                                 sample_times=times.reshape(-1).float(), want=("sigma",), **self._blend_opts())
         return out["sigma"][:, None]
 
+    def _ray_times(self, ray_bundle: RayBundle) -> Tensor:
+        if ray_bundle.times is not None:
+            return ray_bundle.times.reshape(-1).float()
+        return ray_bundle.metadata['timesteps'].reshape(-1).float() / max(self.config.n_timesteps - 1, 1)
+
+    def _fused_render(self, ray_bundle: RayBundle) -> "ops.RenderResult":
+        """Eval render of a (flat) ray bundle through nsb_render_forward: the nerfacc occupancy march as one cooperative
+        launch + field and compositing fused into one launch; the packed sample count stays on the device."""
+        cfg = self.config
+        wh, wd = self._windows()
+        near_planes, far_planes = self.sampler.eval_planes(ray_bundle, cfg.near_plane, cfg.far_plane)
+        og = self.occupancy_grid
+        return ops.render_rays(self.native_params(), ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3),
+                               self._ray_times(ray_bundle), window_hash=wh, window_deform=wd,
+                               use_deformation=cfg.use_deformation_field, training=self.training, sampler="occupancy",
+                               near_planes=near_planes, far_planes=far_planes, binaries=og.binaries, aabbs=og.aabbs,
+                               step=cfg.render_step_size, cone_angle=cfg.cone_angle, **self._blend_opts())
+
+    def _fused_ok(self) -> bool:
+        return self.use_fused_render and not self.sampler.training and self.scene_aabb.is_cuda
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle (the eval entry point: evaluate_nersemble.py:143,
+        util/render.py:39): chunk loop over eval_num_rays_per_chunk rays; tuple-wrapped per-sample outputs are skipped
+        upstream, so the fused render's per-ray outputs are all that is needed -- no host synchronisation per chunk."""
+        if not self._fused_ok():
+            return super().get_outputs_for_camera_ray_bundle(camera_ray_bundle)
+        n = self.config.eval_num_rays_per_chunk
+        h, w = camera_ray_bundle.origins.shape[:2]
+        lists: Dict[str, list] = {}
+        for i in range(0, h * w, n):
+            rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + n)
+            res = self._fused_render(rb)
+            for name in ("rgb", "accumulation", "depth", "num_samples_per_ray", "deformation"):
+                if name in res:
+                    lists.setdefault(name, []).append(res[name])
+        return {k: torch.cat(v).view(h, w, -1) for k, v in lists.items()}
+
     def get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None):
         """models/nersemble_instant_ngp.py:280-364."""
         cfg = self.config
@@ -308,6 +348,29 @@ class NeRSembleNGPModel(Model):
         num_rays = len(ray_bundle)
         # the differentiable path is the TRAINING path (training-mode compositing); eval renders are inference-only
         needs_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not needs_grad and self._fused_ok() and jitter is None:
+            # eval: fused render; ONE host synchronisation (the packed sample count) to hand out exact-size per-sample tensors
+            res = self._fused_render(ray_bundle)
+            pk = res.packed()
+            if pk["t_starts"].shape[0] > 0:
+                ri = pk["ray_indices"].long()
+                from ..nerfstudio_shim import Frustums
+                o, d = ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3)
+                origins = o[ri]
+                ray_samples = RaySamples(frustums=Frustums(origins=origins, directions=d[ri], starts=pk["t_starts"][:, None],
+                                                           ends=pk["t_ends"][:, None], pixel_area=torch.zeros_like(origins[:, :1])),
+                                         camera_indices=None if ray_bundle.camera_indices is None else ray_bundle.camera_indices.reshape(-1, ray_bundle.camera_indices.shape[-1])[ri])
+                if ray_bundle.times is not None:
+                    ray_samples.times = ray_bundle.times.reshape(-1, 1)[ri]
+                ray_samples.metadata = dict()
+                outputs = {"rgb": res["rgb"], "accumulation": res["accumulation"], "depth": res["depth"],
+                           "num_samples_per_ray": res["num_samples_per_ray"], "ray_samples": (ray_samples,),
+                           "ray_indices": (ri,), "weights": (pk["weights"],)}
+                if cfg.use_deformation_field:
+                    ray_samples.frustums.set_offsets(pk["offsets"])
+                    outputs["deformation"] = res["deformation"]
+                return outputs
+            # no sample at all: the reference inserts one fake sample (nersemble_volumetric_sampler.py:110-114) -> general path
         with torch.no_grad():
             ray_samples, ray_indices = self.sampler(
                 ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
@@ -315,10 +378,7 @@ class NeRSembleNGPModel(Model):
                 early_stop_eps=cfg.early_stop_eps, jitter=jitter)
         if ray_samples.metadata is None:
             ray_samples.metadata = dict()
-        if ray_bundle.times is not None:
-            ray_times = ray_bundle.times.reshape(-1).float()
-        else:
-            ray_times = ray_bundle.metadata['timesteps'].reshape(-1).float() / max(cfg.n_timesteps - 1, 1)
+        ray_times = self._ray_times(ray_bundle)
         starts = ray_samples.frustums.starts[..., 0].contiguous()
         ends = ray_samples.frustums.ends[..., 0].contiguous()
         cnt = torch.zeros(num_rays, dtype=torch.long, device=starts.device).index_add_(

@@ -149,6 +149,21 @@ class NeRSembleVolumetricSampler(nn.Module):
 
         return sigma_fn
 
+    def eval_planes(self, ray_bundle: RayBundle, near_plane: float = 0.0, far_plane: Optional[float] = None) -> Tuple[Tensor, Tensor]:
+        """Per-ray near / far planes exactly as forward() + OccGridEstimator.sampling() build them in eval mode (no
+        stratified jitter), and the frustum-cull AND of the grid: the inputs of the fused render (ops.render_rays)."""
+        rays_o = ray_bundle.origins.reshape(-1, 3)
+        if far_plane is None:
+            far_plane = 1e10
+        near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+        far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            near_planes = torch.clamp(near_planes, min=ray_bundle.nears.contiguous().reshape(-1))
+            far_planes = torch.clamp(far_planes, max=ray_bundle.fars.contiguous().reshape(-1))
+        if self.camera_frustum_grid is not None:
+            self.occupancy_grid.binaries[0] = self.occupancy_grid.binaries[0] & self.camera_frustum_grid.to(self.occupancy_grid.binaries.device)
+        return near_planes, far_planes
+
     def forward(self, ray_bundle: RayBundle, render_step_size: float, near_plane: float = 0.0,
                 far_plane: Optional[float] = None, alpha_thre: float = 0.01, cone_angle: float = 0.0,
                 early_stop_eps: float = 1e-4, jitter: Optional[Tensor] = None) -> Tuple[RaySamples, Tensor]:

@@ -1,0 +1,143 @@
+"""nsb_render_forward (ops.render_rays): sampler -> field -> composite in one launch (fixed march) / the cooperative
+march launch + one fused launch (occupancy grid), without host synchronisation.  The fused path runs the device code of
+the stand-alone kernels, so every output must be BIT-IDENTICAL to nsb_march_* + nsb_field_forward + nsb_composite_forward."""
+import pytest
+import torch
+
+from conftest import native_from_oracle, oracle_params
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TRAINED = dict(seed=19980801, n_timesteps=4, log2_hashmap_size=14, table_scale=0.5, time_std_scale=100.0,
+               deform_last_scale=1e-3)
+
+
+@pytest.fixture(scope="module")
+def trained():
+    P = oracle_params(TRAINED)
+    return P, native_from_oracle(P, DEV)
+
+
+def _rays(R, seed):
+    from oracle.gen_golden import ring_rays
+    o, d, t, _ = ring_rays(R, seed)
+    return o.to(DEV), d.to(DEV), t.to(DEV)
+
+
+def _same(a, b):
+    return a.shape == b.shape and bool(torch.equal(a, b))
+
+
+@pytest.mark.parametrize("w_hash,w_deform,deform", [(32.0, 7.0, True), (1.5, 3.3, True), (32.0, None, False)])
+@pytest.mark.parametrize("R,n_per", [(300, 77), (5, 1), (1, 200)])
+def test_fixed_march_one_launch_is_bit_identical_to_the_three_kernel_path(trained, w_hash, w_deform, deform, R, n_per):
+    from nersemble_b200 import ops
+    P, NP = trained
+    o, d, t = _rays(R, 3)
+    ts, te, ri, info = ops.march_fixed(o, d, P.aabb, n_per, 0.011, 0.2)
+    want = ops.render_packed(NP, o, d, t, ts, te, ri, info, window_hash=w_hash, window_deform=w_deform,
+                             use_deformation=deform, training=False)
+    got = ops.render_rays(NP, o, d, t, window_hash=w_hash, window_deform=w_deform, use_deformation=deform, sampler="fixed",
+                          n_per_ray=n_per, near_plane=0.2, step=0.011)
+    for k in ("rgb", "accumulation", "depth") + (("deformation",) if deform else ()):
+        assert _same(got[k], want[k]), k
+    assert _same(got["packed_info"], info) and _same(got["num_samples_per_ray"], want["num_samples_per_ray"])
+    pk = got.packed()
+    assert _same(pk["t_starts"], ts) and _same(pk["t_ends"], te) and _same(pk["ray_indices"], ri)
+    assert _same(pk["sigma"], want["density"][:, 0]) and _same(pk["rgb"], want["rgb_samples"]) and _same(pk["weights"], want["weights"])
+    if deform:
+        assert _same(pk["offsets"], want["offsets"])
+
+
+@pytest.mark.parametrize("single_launch", [False, True])
+@pytest.mark.parametrize("levels", [1, 2])
+def test_occupancy_march_fused_is_bit_identical(trained, levels, single_launch):
+    from nersemble_b200 import ops
+    from oracle.gen_golden import blob_grid
+    from oracle.tp import nerfacc_cpu
+    if single_launch and levels != 1:
+        pytest.skip("the single-launch variant marches single-level grids")
+    P, NP = trained
+    R = 700                                            # > 256 * ... several scan slabs per CTA chunk is covered by R = 40 000 below
+    o, d, t = _rays(R, 11)
+    d[5] = torch.tensor([0.0, 0.0, -1.0]); o[5] = torch.tensor([0.1, 0.2, 9.0])
+    o[6] = torch.tensor([50.0, 50.0, 50.0]); d[6] = torch.tensor([0.0, 1.0, 0.0])          # misses the box: zero samples
+    occ = torch.stack([blob_grid(20 + l) for l in range(levels)]).to(DEV)
+    aabbs = torch.stack([nerfacc_cpu._enlarge_aabb(P.aabb.reshape(-1), 2 ** l) for l in range(levels)]).to(DEV)
+    gen = torch.Generator().manual_seed(2)
+    near = (torch.full((R,), 0.2) + torch.rand((R,), generator=gen) * 0.011).to(DEV)
+    far = torch.full((R,), 1e3, device=DEV)
+    ts, te, ri, info = ops.march_occupancy(o, d, near, far, occ, aabbs, 0.011, 0.0)
+    want = ops.render_packed(NP, o, d, t, ts, te, ri, info, window_hash=32.0, window_deform=7.0, training=False)
+    got = ops.render_rays(NP, o, d, t, window_hash=32.0, window_deform=7.0, sampler="occupancy", near_planes=near,
+                          far_planes=far, binaries=occ, aabbs=aabbs, step=0.011, single_launch=single_launch)
+    assert _same(got["packed_info"], info)
+    for k in ("rgb", "accumulation", "depth", "deformation"):
+        assert _same(got[k], want[k]), k
+    pk = got.packed()
+    assert pk["t_starts"].shape[0] == ts.shape[0] > 1000
+    assert _same(pk["t_starts"], ts) and _same(pk["t_ends"], te) and _same(pk["ray_indices"], ri)
+    assert _same(pk["sigma"], want["density"][:, 0]) and _same(pk["weights"], want["weights"])
+
+
+def test_occupancy_scan_over_many_rays_and_capacity_overflow(trained):
+    """40 000 rays: every CTA of the cooperative march scans several slabs; then a too-small capacity must raise the
+    status flag (and never write out of bounds) instead of corrupting memory."""
+    from nersemble_b200 import ops
+    from oracle.gen_golden import blob_grid
+    P, NP = trained
+    R = 40000
+    o, d, t = _rays(R, 5)
+    occ = blob_grid(7)[None].to(DEV)
+    aabbs = P.aabb.reshape(1, 6).to(DEV)
+    near = torch.full((R,), 0.2, device=DEV); far = torch.full((R,), 1e3, device=DEV)
+    ts, te, ri, info = ops.march_occupancy(o, d, near, far, occ, aabbs, 0.011, 0.0)
+    got = ops.render_rays(NP, o, d, t, window_hash=32.0, window_deform=7.0, sampler="occupancy", near_planes=near,
+                          far_planes=far, binaries=occ, aabbs=aabbs, step=0.011)
+    assert _same(got["packed_info"], info)
+    want = ops.render_packed(NP, o, d, t, ts, te, ri, info, window_hash=32.0, window_deform=7.0, training=False)
+    assert _same(got["rgb"], want["rgb"]) and _same(got["depth"], want["depth"])
+    n = int(ts.shape[0])
+    small = ops.render_rays(NP, o, d, t, window_hash=32.0, window_deform=7.0, sampler="occupancy", near_planes=near,
+                            far_planes=far, binaries=occ, aabbs=aabbs, step=0.011, capacity=n // 2)
+    torch.cuda.synchronize()
+    hdr = small["_buffers"]["header"]
+    assert int(hdr[2]) == n and (int(hdr[1]) >> 32) == 1          # n_total, status
+    with pytest.raises(RuntimeError):
+        small.packed()
+
+
+def test_plugin_eval_paths_use_the_fused_render(trained):
+    """NeRSembleNGPModel eval: get_outputs_for_camera_ray_bundle (no host sync) and get_outputs (full contract) agree bit
+    for bit with the training-path kernels run in eval mode."""
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    from oracle.gen_golden import blob_grid
+    from test_plugin_cpu import make_model
+    from test_plugin_gpu import load_oracle_params_into
+    P, _ = trained
+    m = make_model(T=4, log2T=14, eval_num_rays_per_chunk=500)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).eval()
+    m.sched_window_hash_encodings.value = 32.0; m.sched_window_deform.value = 7.0
+    m.occupancy_grid.binaries[0] = blob_grid(5).to(DEV)
+    H, W = 30, 40
+    o, d, t = _rays(H * W, 9)
+    rb = RayBundle(origins=o.view(H, W, 3), directions=d.view(H, W, 3), pixel_area=torch.ones(H, W, 1, device=DEV),
+                   camera_indices=torch.zeros(H, W, 1, dtype=torch.long, device=DEV), times=t.view(H, W, 1))
+    with torch.no_grad():
+        img = m.get_outputs_for_camera_ray_bundle(rb)
+        m.use_fused_render = False
+        ref = m.get_outputs_for_camera_ray_bundle(rb)
+        m.use_fused_render = True
+        flat = RayBundle(origins=o, directions=d, pixel_area=torch.ones(H * W, 1, device=DEV),
+                         camera_indices=torch.zeros(H * W, 1, dtype=torch.long, device=DEV), times=t)
+        full = m.get_outputs(flat)
+        m.use_fused_render = False
+        full_ref = m.get_outputs(flat)
+    for k in ("rgb", "accumulation", "depth", "deformation", "num_samples_per_ray"):
+        assert _same(img[k], ref[k]), k
+        assert _same(full[k], full_ref[k]), k
+    assert _same(full["weights"][0], full_ref["weights"][0]) and _same(full["ray_indices"][0], full_ref["ray_indices"][0])
+    rs, rs_ref = full["ray_samples"][0], full_ref["ray_samples"][0]
+    assert _same(rs.frustums.starts, rs_ref.frustums.starts) and _same(rs.frustums.offsets, rs_ref.frustums.offsets)
+    assert _same(rs.frustums.origins, rs_ref.frustums.origins) and _same(rs.times, rs_ref.times)
