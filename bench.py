@@ -6,7 +6,8 @@
 Default (what the driver runs): BASELINE.json config 2 -- 4096 rays x 256 samples = 2^20 samples, 32-member hash
 ensemble with full-size tables (16 levels x 2^19), T = 24, fused forward + alpha composite.
 
-  value     device-resident inputs, march -> fused field kernel -> composite through the op layer (C ABI).
+  value     device-resident inputs, ONE kernel launch per step: fixed-stride march -> fused field -> composite
+            (nsb_render_forward through the op layer).
             N > 1: STRONG scaling of the 4096-ray batch ("partition the ray batch 1/N per GPU"), the
             per-ray RGB all-gathered to every rank INSIDE the timed region (NCCL); the weak-scaling number (every
             rank renders its own 4096 rays, no collective) is measured in the same run and reported under "weak".
@@ -15,7 +16,7 @@ ensemble with full-size tables (16 levels x 2^19), T = 24, fused forward + alpha
             region, occupancy-grid sampler, 256 samples per ray via the bundle's nears / fars.
   parity    RGB of the first 64 rays of the SAME batch and parameters against the CPU oracle (north-star tolerance:
             per-pixel L2 < 1e-3); the run fails when it is exceeded.
-  roofline  HBM: 16 384 algorithmic bytes per sample / fused field kernel time (CUDA events around the launch).
+  roofline  HBM: 16 384 algorithmic bytes per sample / time of the fused render kernel (CUDA events around its launch).
   cpu_baseline  the oracle port timed on the host cores on those 64 rays (1 warm-up + median of 5).
 
 Other configs (BASELINE.json configs[2..4]; `--config`): 2occ = config 2 with a seeded blob occupancy grid through the
@@ -381,15 +382,15 @@ def run_config2(args, occ=False):
     ev_field = []
 
     def render(o, d, t, time_field=False):
-        ts, te, ri, info = ops.march_fixed(o, d, aabb, SAMPLES_PER_RAY, STEP, NEAR)
+        """ONE launch: fixed-stride march -> fused field -> composite + depth clip (nsb_render_forward)."""
         if time_field:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        f = ops.field_forward(P, window_hash=32.0, window_deform=7.0, origins=o, directions=d, ray_times=t,
-                              t_starts=ts, t_ends=te, ray_indices=ri, want=("sigma", "rgb", "offsets"))
+        out = ops.render_rays(P, o, d, t, window_hash=32.0, window_deform=7.0, sampler="fixed", n_per_ray=SAMPLES_PER_RAY,
+                              near_plane=NEAR, step=STEP)
         if time_field:
             e1.record(); ev_field.append((e0, e1))
-        return ops.composite(info, ts, te, f["sigma"], f["rgb"], f["offsets"], training=False, want_weights=True)
+        return out
 
     # ---- parity: the first 64 rays of the global batch, CUDA vs CPU oracle on the same parameters (rank 0) ----
     parity = cpu = None
@@ -450,6 +451,7 @@ def run_config2(args, occ=False):
     rgb_pin = torch.empty((n_loc, 3), dtype=torch.float32).pin_memory()
     with torch.no_grad():     # per-ray far plane = entry + 256 steps: the sampler marches exactly the config's samples
         ts0 = ops.march_fixed(o_s, d_s, aabb, 1, STEP, NEAR)[0]
+    torch.cuda.synchronize()
     nears_h = ts0.cpu().reshape(n_loc, 1).pin_memory()
     fars_h = (nears_h + SAMPLES_PER_RAY * STEP).pin_memory()
     model.config.eval_num_rays_per_chunk = n_loc
@@ -512,10 +514,11 @@ def run_config2(args, occ=False):
                        "l2": "806 MB of hash tables are gathered every step (>> 126 MB L2); no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "M ray-samples/s", "h2d_bytes_per_step": RAYS * 9 * 4 * (1 if strong or world == 1 else world),
                     "d2h_bytes_per_step": RAYS * 3 * 4 * (1 if strong or world == 1 else world),
-                    "call": "NeRSembleNGPModel.get_outputs_for_camera_ray_bundle (occupancy sampler, nears/fars = 256 steps)",
+                    "call": "NeRSembleNGPModel.get_outputs_for_camera_ray_bundle (occupancy sampler, nears/fars = 256 steps): "
+                            "cooperative march launch + one fused field/composite launch, no host sync",
                     "samples_per_step": samples_e2e_total, "ms_per_step": ms_e2e / K, "rgb_l2_max_vs_op_path": e2e_l2},
-            "gpu_launches": 5 * K,
-            "roofline": {"bound": "hbm", "kernel": "nsb::field_kernel_ws<deform,field,head>", "achieved": achieved,
+            "gpu_launches": 1 * K,
+            "roofline": {"bound": "hbm", "kernel": "nsb::render_kernel_ws<deform, fixed march> (march + field + composite, one launch)", "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "kernel_ms": field_ms, "samples_per_launch": field_samples},
             "clocks": sampler.summary(),

@@ -469,7 +469,11 @@ __device__ NSB_RK_SAMPLER_ATTR void render_sampler_phase(const RenderKArgs &K) {
                     if (w < warp) wbase += t;
                     slab += t;
                 }
-                if (r < r1) { K.packed_info[2 * r] = carry + wbase + inc - c; K.packed_info[2 * r + 1] = c; }
+                if (r < r1) {   // beyond the caller's capacity (status = 1) rays are truncated: nothing downstream reads out of bounds
+                    const int64_t st = min(carry + wbase + inc - c, K.capacity);
+                    K.packed_info[2 * r] = st;
+                    K.packed_info[2 * r + 1] = min(c, K.capacity - st);
+                }
                 carry += slab;
             }
         }

@@ -44,12 +44,12 @@ struct MarchArgs {
 };
 
 
-template <bool FILL>
+template <bool FILL, int LV>
 __global__ void __launch_bounds__(128) march_occ_kernel(const __grid_constant__ MarchArgs M) {
     const nsb_march_args &a = M.a;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_rays) return;
-    const int32_t count = march_occ_ray<FILL>(a, r, FILL ? a.offsets[r] : 0, INT64_MAX);
+    const int32_t count = march_occ_ray<FILL, LV>(a, r, FILL ? a.offsets[r] : 0, INT64_MAX);
     if (!FILL) a.counts[r] = count;
 }
 
@@ -333,7 +333,11 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
                 if (w < warp) wbase += t;
                 slab += t;
             }
-            if (r < r1) { K.packed_info[2 * r] = carry + wbase + inc - c; K.packed_info[2 * r + 1] = c; }
+            if (r < r1) {   // beyond the caller's capacity (status = 1) rays are truncated: nothing downstream reads out of bounds
+                    const int64_t st = min(carry + wbase + inc - c, K.capacity);
+                    K.packed_info[2 * r] = st;
+                    K.packed_info[2 * r + 1] = min(c, K.capacity - st);
+                }
             carry += slab;
         }
     }
@@ -396,10 +400,12 @@ extern "C" int nsb_march_occupancy(const nsb_march_args *args, void *stream) {
     const int blocks = (int)((args->n_rays + threads - 1) / threads);
     if (args->t_starts == nullptr) {
         if (!args->counts) { set_error("nsb_march_occupancy: pass 1 needs counts"); return 1; }
-        march_occ_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(M);
+        if (args->levels == 1) march_occ_kernel<false, 1><<<blocks, threads, 0, (cudaStream_t)stream>>>(M);
+        else march_occ_kernel<false, 0><<<blocks, threads, 0, (cudaStream_t)stream>>>(M);
     } else {
         if (!args->offsets || !args->t_ends || !args->ray_indices) { set_error("nsb_march_occupancy: pass 2 needs offsets/t_ends/ray_indices"); return 1; }
-        march_occ_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(M);
+        if (args->levels == 1) march_occ_kernel<true, 1><<<blocks, threads, 0, (cudaStream_t)stream>>>(M);
+        else march_occ_kernel<true, 0><<<blocks, threads, 0, (cudaStream_t)stream>>>(M);
     }
     return check_launch("march_occ_kernel");
 }
