@@ -546,6 +546,7 @@ def main():
     ap.add_argument("--config", default="2", choices=["2", "2occ", "3", "4", "5"])
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="config 5: blocking table-gradient all-reduce after the backward")
     ap.add_argument("--height", type=int, default=1088)
     ap.add_argument("--width", type=int, default=1920)
     args = ap.parse_args()

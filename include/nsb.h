@@ -352,6 +352,11 @@ typedef struct nsb_render_args {
     int64_t *packed_info;              /* [n_rays][2] out: (start, count) */
     float *out_rgb, *out_acc, *out_depth, *out_deform; /* [n_rays][3], [n_rays], [n_rays], [n_rays][3] | NULL */
     void *workspace;                   /* nsb_render_workspace_bytes(n_rays) bytes; header = nsb_render_ws_header */
+    float *march_scratch;              /* sampler 1, optional: float [2][capacity].  With it the occupancy grid is traversed
+                                          ONCE (samples land in per-ray slots of capacity / n_rays entries, then a coalesced
+                                          copy packs them) instead of twice (count, fill): the DDA is a dependent chain per
+                                          ray and dominates the march (4096 rays: 439 -> ~230 us).  A ray with more samples
+                                          than its slot is truncated and status set to 1. */
 } nsb_render_args;
 typedef struct nsb_render_ws_header {  /* first 64 bytes of the workspace; n_total / status are results */
     uint32_t barrier;                  /* grid-barrier arrival counter (the call zeroes it) */

@@ -115,7 +115,8 @@ class RenderArgs(C.Structure):
                 ("training", C.c_int32), ("capacity", C.c_int64), ("t_starts", C.c_void_p), ("t_ends", C.c_void_p),
                 ("ray_indices", C.c_void_p), ("sigma", C.c_void_p), ("rgb", C.c_void_p), ("offsets", C.c_void_p),
                 ("weights", C.c_void_p), ("packed_info", C.c_void_p), ("out_rgb", C.c_void_p), ("out_acc", C.c_void_p),
-                ("out_depth", C.c_void_p), ("out_deform", C.c_void_p), ("workspace", C.c_void_p)]
+                ("out_depth", C.c_void_p), ("out_deform", C.c_void_p), ("workspace", C.c_void_p),
+                ("march_scratch", C.c_void_p)]
 
 
 class RenderWsHeader(C.Structure):

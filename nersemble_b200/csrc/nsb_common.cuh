@@ -14,7 +14,7 @@ int check_launch(const char *what);
 // nsb_render.cu: the occupancy march as ONE cooperative launch (count | scan | fill); leaves packed_info, the packed
 // samples (below `capacity`) and, in the workspace header, n_total / status.  Zeroes and uses hdr->barrier.
 int launch_march_occ_coop(const nsb_march_args &M, int64_t *packed_info, nsb_render_ws_header *hdr, int64_t *partials,
-                          int64_t capacity, cudaStream_t st);
+                          int64_t capacity, float *scratch, cudaStream_t st);
 
 constexpr uint32_t kPrimeY = 2654435761u;
 constexpr uint32_t kPrimeZ = 805459861u;

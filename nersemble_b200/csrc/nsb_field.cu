@@ -753,7 +753,7 @@ extern "C" int nsb_render_forward(const nsb_field_params *params, const nsb_fiel
         // occupancy march as its own small cooperative launch (count | scan | fill, the count stays on the device), then
         // field + composite in one: with the marcher inside render_kernel_ws ptxas spills 66-82 instructions in the gather
         // role of the field phase (tools/spill_report.py); sampler == 3 selects that single-launch variant.
-        const int rc = launch_march_occ_coop(K.M, K.packed_info, K.hdr, K.partials, K.capacity, st);
+        const int rc = launch_march_occ_coop(K.M, K.packed_info, K.hdr, K.partials, K.capacity, ra->march_scratch, st);
         if (rc) return rc;
         return deform ? launch_render<true, 2>(K, st) : launch_render<false, 2>(K, st);
     }

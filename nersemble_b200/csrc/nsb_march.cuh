@@ -176,7 +176,7 @@ __device__ __forceinline__ int32_t march_occ_ray(const nsb_march_args &a, const 
                             if (out < out_limit) {
                                 a.t_starts[out] = t_last;
                                 a.t_ends[out] = t_next;
-                                a.ray_indices[out] = (int32_t)r;
+                                if (a.ray_indices) a.ray_indices[out] = (int32_t)r;
                             }
                             ++out;
                         }

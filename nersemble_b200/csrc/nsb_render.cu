@@ -258,6 +258,8 @@ struct MarchCoopArgs {
     nsb_render_ws_header *hdr;
     int64_t *partials;
     int64_t capacity;
+    float *scratch;          // [2][capacity] or NULL: single traversal into per-ray slots, then a packing copy
+    int64_t slot;            // capacity / n_rays
 };
 constexpr int kCoopThreads = 256;
 
@@ -292,8 +294,22 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t R = K.M.n_rays;
     uint32_t *const bar = &K.hdr->barrier;
-    for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
-        K.M.counts[r] = march_occ_ray<false, LV>(K.M, r, 0, 0);
+    const bool single = K.scratch != nullptr;
+    if (single) {
+        // ONE traversal: the samples of ray r go to its slot [r * slot, (r + 1) * slot) of the scratch arrays
+        MarchArgs S1; S1.a = K.M;
+        S1.a.t_starts = K.scratch; S1.a.t_ends = K.scratch + K.capacity; S1.a.ray_indices = nullptr;
+        bool over = false;
+        for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads) {
+            const int32_t c = march_occ_ray<true, LV>(S1.a, r, r * K.slot, (r + 1) * K.slot);
+            over |= c > K.slot;
+            K.M.counts[r] = (int32_t)min((int64_t)c, K.slot);
+        }
+        if (over) K.hdr->reserved[0] = 1;                 // folded into status by block 0 after the barrier
+    } else {
+        for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
+            K.M.counts[r] = march_occ_ray<false, LV>(K.M, r, 0, 0);
+    }
     coop_grid_barrier(bar, 1u * gridDim.x);
     const int64_t chunk = (R + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = min(R, (int64_t)blockIdx.x * chunk), r1 = min(R, r0 + chunk);
@@ -313,7 +329,10 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
         }
         total = coop_block_sum(total, red, tid);
         before = coop_block_sum(before, red, tid);
-        if (blockIdx.x == 0 && tid == 0) { K.hdr->n_total = total; K.hdr->status = total > K.capacity ? 1 : 0; }
+        if (blockIdx.x == 0 && tid == 0) {
+            K.hdr->n_total = total;
+            K.hdr->status = (total > K.capacity || __ldcg(&K.hdr->reserved[0]) != 0) ? 1 : 0;
+        }
         int64_t carry = before;
         for (int64_t s0 = r0; s0 < r1; s0 += kCoopThreads) {
             const int64_t r = s0 + tid;
@@ -342,14 +361,29 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
         }
     }
     coop_grid_barrier(bar, 3u * gridDim.x);
-    for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
-        march_occ_ray<true, LV>(K.M, r, __ldcg(K.packed_info + 2 * r), K.capacity);
+    if (single) {
+        // packing copy, one warp per ray: coalesced reads of the slot, coalesced writes of the packed arrays
+        const float *s_ts = K.scratch, *s_te = K.scratch + K.capacity;
+        for (int64_t r = (int64_t)blockIdx.x * (kCoopThreads / 32) + warp; r < R; r += (int64_t)gridDim.x * (kCoopThreads / 32)) {
+            const int64_t dst = __ldcg(K.packed_info + 2 * r), cnt = __ldcg(K.packed_info + 2 * r + 1), src = r * K.slot;
+            for (int64_t k = lane; k < cnt; k += 32) {
+                K.M.t_starts[dst + k] = __ldcg(s_ts + src + k);
+                K.M.t_ends[dst + k] = __ldcg(s_te + src + k);
+                K.M.ray_indices[dst + k] = (int32_t)r;
+            }
+        }
+    } else {
+        for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
+            march_occ_ray<true, LV>(K.M, r, __ldcg(K.packed_info + 2 * r), K.capacity);
+    }
 }
 
 int launch_march_occ_coop(const nsb_march_args &M, int64_t *packed_info, nsb_render_ws_header *hdr, int64_t *partials,
-                          int64_t capacity, cudaStream_t st) {
+                          int64_t capacity, float *scratch, cudaStream_t st) {
     MarchCoopArgs K;
     K.M = M; K.packed_info = packed_info; K.hdr = hdr; K.partials = partials; K.capacity = capacity;
+    K.slot = capacity / std::max<int64_t>(M.n_rays, 1);
+    K.scratch = K.slot >= 1 ? scratch : nullptr;
     static int grid = 0;
     if (grid == 0) {
         int dev = 0, sms = 0, per_sm = 0;
@@ -358,7 +392,7 @@ int launch_march_occ_coop(const nsb_march_args &M, int64_t *packed_info, nsb_ren
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_occ_coop_kernel<1>, kCoopThreads, 0);
         grid = std::max(1, std::min(sms * std::max(1, std::min(per_sm, 4)), 1024));     // <= 1024 scan partials
     }
-    cudaError_t e = cudaMemsetAsync(&hdr->barrier, 0, sizeof(uint32_t), st);
+    cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(nsb_render_ws_header), st);      // barrier, status, reserved[0]
     if (e != cudaSuccess) { set_error("march_occ_coop: memset: %s", cudaGetErrorString(e)); return 2; }
     void *kargs[] = {&K};
     const void *fn = M.levels == 1 ? reinterpret_cast<const void *>(march_occ_coop_kernel<1>)

@@ -43,6 +43,8 @@ def allreduce_pending(he, average: bool = True) -> None:
     place and the 1/world factor folded into the optimiser step; otherwise, or when a dense `.grad` exists as well
     (gradient accumulation: the dense part must be averaged too), it becomes a dense `.grad` for the dense reduction."""
     pend = he.pending_table_grad
+    if pend is not None and pend.get("sync_work") is not None:
+        pend.pop("sync_work").wait()          # overlapped reduction (overlap_table_allreduce): the current stream waits for it
     if pend is None or pend.get("reduced") or not dist.is_initialized() or dist.get_world_size() == 1:
         return
     world = dist.get_world_size()
@@ -52,6 +54,38 @@ def allreduce_pending(he, average: bool = True) -> None:
         pend["reduced"] = True
     else:
         he.materialize_pending()
+
+
+def overlap_table_allreduce(hash_ensemble, average: bool = True) -> None:
+    """Overlap the table-gradient collective with the rest of the backward ("overlap ... as backward
+    finishes").  The parked rank-1 workspace [slots][entries][2] (1.2 GB at T = 24) is complete once nsb_field_backward
+    is enqueued -- a third of the way into the backward; the deformation-field backward (the largest backward kernel)
+    and the dW reductions still follow.  This installs a hook that the training backward calls at that point: the
+    all-reduce is issued on a side stream and runs concurrently with those kernels; FusedFieldsAdam.step() /
+    allreduce_gradients() wait for it.  No-op without a process group or when the slot map is not rank-invariant."""
+    import torch
+    state = {"stream": None}
+
+    def hook(he) -> None:
+        pend = he.pending_table_grad
+        if (pend is None or pend.get("reduced") or not dist.is_initialized() or dist.get_world_size() == 1
+                or not pend.get("slots_are_timesteps") or he.tables.grad is not None):
+            return
+        g = pend["g_rank1"]
+        if g.is_cuda:
+            if state["stream"] is None:
+                state["stream"] = torch.cuda.Stream(g.device)
+            side = state["stream"]
+            side.wait_stream(torch.cuda.current_stream(g.device))
+            with torch.cuda.stream(side):
+                pend["sync_work"] = dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+            g.record_stream(side)
+        else:                                   # gloo (CPU tests): asynchronous work object, no streams
+            pend["sync_work"] = dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+        pend["scale"] = float(pend.get("scale", 1.0)) / (dist.get_world_size() if average else 1)
+        pend["reduced"] = True
+
+    hash_ensemble.table_grad_hook = hook
 
 
 _BIG = 1 << 24   # elements: tensors this large are reduced in place, not copied into the flat bucket

@@ -629,9 +629,11 @@ class RenderResult(dict):
 
     def packed(self) -> Dict[str, torch.Tensor]:
         b = self["_buffers"]
-        n = int(b["header"][2].item())                # n_total: the ONE host synchronisation, only when asked for
-        if n > b["capacity"]:
-            raise RuntimeError(f"render_rays: the march produced {n} samples, capacity {b['capacity']}")
+        h = b["header"][:3].tolist()                  # the ONE host synchronisation, only when asked for
+        n, status = int(h[2]), int(h[1]) >> 32
+        if status != 0 or n > b["capacity"]:
+            raise RuntimeError(f"render_rays: the march produced more samples than the workspace holds "
+                               f"(n_total {n}, capacity {b['capacity']}, status {status}); pass a larger capacity")
         out = {k: b[k][:n] for k in ("t_starts", "t_ends", "ray_indices", "sigma", "rgb", "offsets", "weights") if b.get(k) is not None}
         out["weights"] = out["weights"][:, None]
         return out
@@ -641,11 +643,13 @@ def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=
                 use_deformation=True, training=False, sampler: str = "occupancy", n_per_ray: int = 0,
                 near_plane: float = 0.0, near_planes=None, far_planes=None, binaries=None, aabbs=None,
                 step: float = 1e-3, cone_angle: float = 0.0, capacity: Optional[int] = None,
-                disable_initial=True, soft_transition=True, single_launch: bool = False) -> RenderResult:
+                disable_initial=True, soft_transition=True, single_launch: bool = False,
+                single_traversal: bool = True) -> RenderResult:
     """The fused inference render (nsb_render_forward): sampler -> field -> composite without a host synchronisation.
     sampler 'fixed' (n_per_ray steps from the box entry: ONE launch) or 'occupancy' (nerfacc march of `binaries`
     [levels,res,res,res] within per-ray near_planes / far_planes: the cooperative march launch + one fused launch;
-    single_launch=True marches inside the fused kernel, levels == 1 only).  Returns the per-ray outputs (rgb, accumulation,
+    single_launch=True marches inside the fused kernel, levels == 1 only; single_traversal=False: count | scan | fill
+    instead of one traversal into per-ray slots + a packing copy).  Returns the per-ray outputs (rgb, accumulation,
     depth, deformation, num_samples_per_ray, packed_info); `.packed()` gives the per-sample arrays (one sync).
     capacity: per-sample workspace size; default = an upper bound of the march (rays x ceil(largest diagonal / step) + 2)."""
     lib = _lib.load()
@@ -669,6 +673,7 @@ def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=
         ab = aabbs.detach().to(dev, _F32).reshape(levels, 6).contiguous()
         keep += [near_planes, far_planes, b8, ab]
         a.sampler = 3 if single_launch else 1
+        single_traversal = single_traversal and not single_launch
         a.near_planes, a.far_planes, a.binaries, a.aabbs, a.levels, a.res = _ptr(near_planes), _ptr(far_planes), _ptr(b8), _ptr(ab), levels, res
         if capacity is None:
             diag = float((ab[:, 3:] - ab[:, :3]).norm(dim=-1).max())      # host-side: aabbs is a tiny constant buffer
@@ -678,6 +683,9 @@ def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=
         raise ValueError(sampler)
     cap = max(cap, 1)
     a.capacity = cap
+    if sampler == "occupancy" and single_traversal and cap >= R:
+        scratch = torch.empty((2, cap), dtype=_F32, device=dev)      # per-ray slots of the one-traversal march
+        a.march_scratch = _ptr(scratch); keep.append(scratch)
     buf = {"capacity": cap,
            "t_starts": torch.empty((cap,), dtype=_F32, device=dev), "t_ends": torch.empty((cap,), dtype=_F32, device=dev),
            "ray_indices": torch.empty((cap,), dtype=torch.int32, device=dev),

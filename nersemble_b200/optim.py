@@ -83,7 +83,7 @@ class FusedFieldsAdam(torch.optim.Adam):
         if self.auto_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             from .distributed import allreduce_pending
             for he, _, _ in self._ensembles:
-                allreduce_pending(he, average=True)
+                allreduce_pending(he, average=True)      # also waits for an overlapped reduction
         skip, inv_scale = self._amp_state()
         self.last_step_skipped = skip
         if skip:

@@ -129,6 +129,7 @@ class HashEnsemble(nn.Module):
         # table gradient here in rank-1 form instead of writing a dense `.grad`
         self.defer_table_grad = False
         self.pending_table_grad = None
+        self.table_grad_hook = None        # distributed.overlap_table_allreduce: called when the table gradient is parked
         self.tables._nsb_hash_ensemble = weakref.ref(self)
         self._register_state_dict_hook(self._to_reference_keys)
         self._register_load_state_dict_pre_hook(self._from_reference_keys)

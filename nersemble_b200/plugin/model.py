@@ -132,6 +132,9 @@ class _RenderFunction(torch.autograd.Function):
             # a gradient the scaler DOES check (x - x = 0 for finite x, NaN otherwise) -- no host synchronisation.
             flag = g["d_feat"].sum()
             g["d_base_w"] = g["d_base_w"] + (flag - flag)
+            hook = getattr(he, "table_grad_hook", None)
+            if hook is not None:          # distributed.overlap_table_allreduce: the collective overlaps the rest of the backward
+                hook(he)
         grads = [g.get("d_tables"), g["d_base_w"], g["d_head_w"], g["d_blend_codes"]]
         if ctx.deform:
             d = ops.deform_backward(ctx.P, ctx.saved, g["d_xs"], window_deform=ctx.wd, loss_scale=ls, **kw)

@@ -80,3 +80,34 @@ def test_allreduce_reduces_the_deferred_rank1_table_gradient_in_place():
     to the fused optimiser step, and no dense table gradient is created."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_pending_worker, args=(2, port), nprocs=2, join=True)
+
+
+def _overlap_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nersemble_b200.distributed import allreduce_gradients, overlap_table_allreduce
+
+    class FakeEnsemble:
+        def __init__(self):
+            self.tables = torch.nn.Parameter(torch.zeros(5, 32, 2))
+            self.pending_table_grad = {"g_rank1": torch.full((3, 5, 2), float(rank + 1)), "cw_slots": torch.ones(3, 32),
+                                       "n_slots": 3, "slots_are_timesteps": True}
+            self.table_grad_hook = None
+    he = FakeEnsemble()
+    overlap_table_allreduce(he)
+    he.table_grad_hook(he)                       # what the training backward calls once the gradient is parked
+    assert he.pending_table_grad["reduced"] and he.pending_table_grad["scale"] == 0.5
+    w = torch.nn.Parameter(torch.zeros(4)); w.grad = torch.full((4,), float(rank))
+    allreduce_gradients([he.tables, w], hash_ensembles=[he])      # waits for the overlapped work, does not reduce twice
+    assert "sync_work" not in he.pending_table_grad
+    assert torch.equal(he.pending_table_grad["g_rank1"], torch.full((3, 5, 2), 3.0)) and he.pending_table_grad["scale"] == 0.5
+    assert torch.equal(w.grad, torch.full((4,), 0.5)) and he.tables.grad is None
+    dist.destroy_process_group()
+
+
+def test_overlapped_table_gradient_allreduce_hook():
+    """world_size 2, gloo: the hook the training backward calls issues the reduction asynchronously; the later
+    allreduce_gradients / optimiser step only waits for it."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_overlap_worker, args=(2, port), nprocs=2, join=True)

@@ -49,13 +49,13 @@ def test_fixed_march_one_launch_is_bit_identical_to_the_three_kernel_path(traine
         assert _same(pk["offsets"], want["offsets"])
 
 
-@pytest.mark.parametrize("single_launch", [False, True])
+@pytest.mark.parametrize("single_launch", [False, True, "two_pass"])
 @pytest.mark.parametrize("levels", [1, 2])
 def test_occupancy_march_fused_is_bit_identical(trained, levels, single_launch):
     from nersemble_b200 import ops
     from oracle.gen_golden import blob_grid
     from oracle.tp import nerfacc_cpu
-    if single_launch and levels != 1:
+    if single_launch is True and levels != 1:
         pytest.skip("the single-launch variant marches single-level grids")
     P, NP = trained
     R = 700                                            # > 256 * ... several scan slabs per CTA chunk is covered by R = 40 000 below
@@ -69,8 +69,11 @@ def test_occupancy_march_fused_is_bit_identical(trained, levels, single_launch):
     far = torch.full((R,), 1e3, device=DEV)
     ts, te, ri, info = ops.march_occupancy(o, d, near, far, occ, aabbs, 0.011, 0.0)
     want = ops.render_packed(NP, o, d, t, ts, te, ri, info, window_hash=32.0, window_deform=7.0, training=False)
+    # False: cooperative march, ONE traversal into per-ray slots + packing copy (default); "two_pass": count | scan | fill;
+    # True: the march inside the fused kernel
+    kw = dict(single_launch=single_launch is True)
     got = ops.render_rays(NP, o, d, t, window_hash=32.0, window_deform=7.0, sampler="occupancy", near_planes=near,
-                          far_planes=far, binaries=occ, aabbs=aabbs, step=0.011, single_launch=single_launch)
+                          far_planes=far, binaries=occ, aabbs=aabbs, step=0.011, single_traversal=single_launch is False, **kw)
     assert _same(got["packed_info"], info)
     for k in ("rgb", "accumulation", "depth", "deformation"):
         assert _same(got[k], want[k]), k
@@ -102,7 +105,7 @@ def test_occupancy_scan_over_many_rays_and_capacity_overflow(trained):
                             far_planes=far, binaries=occ, aabbs=aabbs, step=0.011, capacity=n // 2)
     torch.cuda.synchronize()
     hdr = small["_buffers"]["header"]
-    assert int(hdr[2]) == n and (int(hdr[1]) >> 32) == 1          # n_total, status
+    assert (int(hdr[1]) >> 32) == 1 and int(hdr[2]) <= n // 2      # status raised, the kept samples fit the workspace
     with pytest.raises(RuntimeError):
         small.packed()
 
