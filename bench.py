@@ -445,8 +445,9 @@ def run_config2(args, occ=False):
 
     # ---- timed region 2 (e2e): the plugin call with HOST buffers ----
     n_loc = hi - lo
-    side = int(math.isqrt(n_loc))
-    assert side * side == n_loc, "ray shards are rendered as square camera bundles"
+    rows = 1 << (int(math.log2(n_loc)) // 2)           # the shard as an [rows, cols] "image" for the camera-ray-bundle call
+    cols = n_loc // rows
+    assert rows * cols == n_loc, "ray shards are rendered as rectangular camera bundles"
     o_pin, d_pin, t_pin = o_g[lo:hi].contiguous().pin_memory(), d_g[lo:hi].contiguous().pin_memory(), t_g[lo:hi].contiguous().pin_memory()
     rgb_pin = torch.empty((n_loc, 3), dtype=torch.float32).pin_memory()
     with torch.no_grad():     # per-ray far plane = entry + 256 steps: the sampler marches exactly the config's samples
@@ -458,9 +459,9 @@ def run_config2(args, occ=False):
     e2e_samples = torch.zeros((), dtype=torch.long, device=dev)
 
     def step_e2e(count=False):
-        cu = lambda x: x.to(dev, non_blocking=True).view(side, side, -1)
-        rb = RayBundle(origins=cu(o_pin), directions=cu(d_pin), pixel_area=torch.ones((side, side, 1), device=dev),
-                       camera_indices=torch.zeros((side, side, 1), dtype=torch.long, device=dev),
+        cu = lambda x: x.to(dev, non_blocking=True).view(rows, cols, -1)
+        rb = RayBundle(origins=cu(o_pin), directions=cu(d_pin), pixel_area=torch.ones((rows, cols, 1), device=dev),
+                       camera_indices=torch.zeros((rows, cols, 1), dtype=torch.long, device=dev),
                        nears=cu(nears_h), fars=cu(fars_h), times=cu(t_pin))
         out = model.get_outputs_for_camera_ray_bundle(rb)
         rgb = out["rgb"].view(n_loc, 3)

@@ -101,6 +101,8 @@ typedef struct nsb_samples {
     const float *positions;    /* [n_samples][3] world */
     const float *sample_times; /* [n_samples] in [0,1] or NULL */
     const float *sample_directions; /* [n_samples][3] or NULL (density_fn uses ones: nersemble_nerfacto_field.py:240) */
+    const int64_t *n_samples_dev;    /* optional DEVICE scalar: the packed sample count when only the device knows it (the
+                                        sync-free training sampler); n_samples is then the capacity of the arrays */
     /* optional per-sample conditioning overriding the time-embedding tables (component APIs) */
     const float *sample_blend_codes; /* float  [n_samples][32] or NULL */
     const float *sample_code_bias;   /* float [n_samples][2][128] or NULL: W_code(layer 0|4) . warp_code[sample] + bias
@@ -367,6 +369,35 @@ typedef struct nsb_render_ws_header {  /* first 64 bytes of the workspace; n_tot
 } nsb_render_ws_header;
 size_t nsb_render_workspace_bytes(int64_t n_rays);
 int nsb_render_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_render_args *args, void *stream);
+
+/* Training sampler WITHOUT host synchronisation (model_components/nersemble_volumetric_sampler.py:95-108 around nerfacc
+ * OccGridEstimator.sampling): (1) nsb_march_occupancy_packed = count/scan/fill of nsb_march_occupancy as ONE cooperative
+ * launch, the candidate count stays in the workspace header; (2) the caller evaluates the candidates' density with
+ * nsb_field_forward(samples->n_samples_dev = &header.n_total); (3) nsb_visibility_compact applies nerfacc's
+ * render_visibility_from_density, mask = (T >= early_stop_eps) & (alpha >= min(alpha_thre, *alpha_thre_cap)), and packs
+ * the surviving samples (plus optional per-sample payload rows of the pre-pass) -- mask | scan | copy in one cooperative
+ * launch; the kept count lands in ITS workspace header. */
+int nsb_march_occupancy_packed(const nsb_march_args *args /* counts/offsets unused */, int64_t capacity, int64_t *packed_info,
+                               void *workspace /* nsb_render_workspace_bytes(n_rays) */, float *scratch /* [2][capacity] or NULL */,
+                               void *stream);
+typedef struct nsb_vis_compact_args {
+    int64_t n_rays, capacity;
+    const int64_t *packed_info;            /* candidates [n_rays][2] */
+    const float *t_starts, *t_ends, *sigma;
+    const int32_t *ray_indices;
+    float early_stop_eps, alpha_thre;
+    const float *alpha_thre_cap;           /* device scalar (occs.mean()) or NULL */
+    int64_t *out_packed_info;              /* [n_rays][2] */
+    float *out_t_starts, *out_t_ends;      /* [capacity] */
+    int32_t *out_ray_indices;
+    /* optional payload rows that move with their sample (pre-pass reuse) */
+    const void *feat; void *out_feat;                 /* __half [.][32] */
+    const float *xs; float *out_xs;                   /* float [.][4] */
+    const void *corner_vals; void *out_corner_vals;   /* __half2 [.][16][8] */
+    void *workspace;                       /* nsb_render_workspace_bytes(n_rays): header.n_total = kept samples */
+} nsb_vis_compact_args;
+int nsb_visibility_compact(const nsb_vis_compact_args *args, void *stream);
+size_t nsb_vis_compact_workspace_bytes(int64_t n_rays, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ class Samples(C.Structure):
                 ("origins", C.c_void_p), ("directions", C.c_void_p), ("ray_times", C.c_void_p),
                 ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("ray_indices", C.c_void_p),
                 ("positions", C.c_void_p), ("sample_times", C.c_void_p), ("sample_directions", C.c_void_p),
-                ("sample_blend_codes", C.c_void_p), ("sample_code_bias", C.c_void_p)]
+                ("n_samples_dev", C.c_void_p), ("sample_blend_codes", C.c_void_p), ("sample_code_bias", C.c_void_p)]
 
 
 class FieldOut(C.Structure):
@@ -119,6 +119,15 @@ class RenderArgs(C.Structure):
                 ("march_scratch", C.c_void_p)]
 
 
+class VisCompactArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("capacity", C.c_int64), ("packed_info", C.c_void_p), ("t_starts", C.c_void_p),
+                ("t_ends", C.c_void_p), ("sigma", C.c_void_p), ("ray_indices", C.c_void_p), ("early_stop_eps", C.c_float),
+                ("alpha_thre", C.c_float), ("alpha_thre_cap", C.c_void_p), ("out_packed_info", C.c_void_p),
+                ("out_t_starts", C.c_void_p), ("out_t_ends", C.c_void_p), ("out_ray_indices", C.c_void_p),
+                ("feat", C.c_void_p), ("out_feat", C.c_void_p), ("xs", C.c_void_p), ("out_xs", C.c_void_p),
+                ("corner_vals", C.c_void_p), ("out_corner_vals", C.c_void_p), ("workspace", C.c_void_p)]
+
+
 class RenderWsHeader(C.Structure):
     _fields_ = [("barrier", C.c_uint32), ("depth_range", C.c_uint32 * 2), ("status", C.c_int32), ("n_total", C.c_int64),
                 ("reserved", C.c_int64 * 5)]
@@ -155,6 +164,9 @@ SYMBOLS = {
                                  C.c_float, C.c_void_p, C.c_void_p]),
     "nsb_occ_update_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "nsb_render_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "nsb_march_occupancy_packed": (C.c_int, [C.POINTER(MarchArgs), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsb_visibility_compact": (C.c_int, [C.POINTER(VisCompactArgs), C.c_void_p]),
+    "nsb_vis_compact_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "nsb_render_forward": (C.c_int, [C.POINTER(FieldParams), C.POINTER(FieldOpts), C.POINTER(RenderArgs), C.c_void_p]),
 }
 

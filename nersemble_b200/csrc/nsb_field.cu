@@ -322,6 +322,27 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
 #undef NSB_N_SAMPLES
 }
 
+// field_kernel_ws with the sample count read from DEVICE memory (nsb_samples.n_samples_dev; the sync-free training
+// sampler: the host never learns how many candidates the march produced).  grid = number of SMs; A.S.n_samples is the
+// capacity of the sample arrays.  Same role bodies.
+template <bool DEFORM, bool FIELD, bool HEAD, bool SAVE>
+__global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_dyn(const __grid_constant__ FieldArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sm.n_dyn = min(*A.S.n_samples_dev, A.S.n_samples);      // visible after the setup's __syncthreads
+#define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
+#include "nsb_field_setup.inc"
+    if (warp >= kTensorWarps) {
+        if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+#include "nsb_field_gather_role.inc"
+        return;
+    }
+    if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+#include "nsb_field_tensor_role.inc"
+#undef NSB_N_SAMPLES
+}
+
 // ===========================================================================================
 // render_kernel_ws: sampler -> field -> composite in ONE launch (north star: "fused into one kernel").
 // A persistent cooperative kernel, one CTA per SM, whose phases are separated by grid-wide barriers:
@@ -601,6 +622,22 @@ static int launch_field_ws_(const FieldArgs &A, cudaStream_t st) {
     field_kernel_ws<D, F, H, SV><<<grid, kThreadsWS, smem, st>>>(A);
     return check_launch("field_kernel_ws");
 }
+// device-side sample count: instantiated for the field evaluations of the training sampler (density pre-pass; SAVE for the
+// pre-pass-reuse variant) -- each instantiation costs ~15 s of ptxas
+template <bool D, bool F, bool H, bool SV>
+static int launch_field_ws_dyn_(const FieldArgs &A, cudaStream_t st) {
+    const size_t smem = sizeof(SmemWS);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(field_kernel_ws_dyn<D, F, H, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(field_kernel_ws_dyn): %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms());
+    field_kernel_ws_dyn<D, F, H, SV><<<grid, kThreadsWS, smem, st>>>(A);
+    return check_launch("field_kernel_ws_dyn");
+}
 template <bool D, bool F, bool H>
 static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
     const bool save = A.out.xs || A.out.deform_acts || A.out.deform_enc || A.out.corner_vals;
@@ -608,7 +645,16 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
 }
 
 template <bool D, bool F, bool H>
-static int launch_field(const FieldArgs &A, cudaStream_t st) { return launch_field_ws<D, F, H>(A, st); }
+static int launch_field(const FieldArgs &A, cudaStream_t st) {
+    if (A.S.n_samples_dev) {
+        // always the SAVE instantiation (its stores are skipped at run time when the pointers are NULL): ptxas gives its
+        // gather role 0 spill instructions, the non-SAVE density instantiation 37 (tools/spill_report.py)
+        if (F && !H) return launch_field_ws_dyn_<D, true, false, true>(A, st);
+        set_error("nsb_field_forward: n_samples_dev is supported for the density evaluation (no rgb) only");
+        return 1;
+    }
+    return launch_field_ws<D, F, H>(A, st);
+}
 
 }  // namespace nsb
 

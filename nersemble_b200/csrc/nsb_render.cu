@@ -288,6 +288,63 @@ __device__ __forceinline__ int64_t coop_block_sum(int64_t v, int64_t *red, const
     return t;
 }
 
+// Exclusive scan of per-ray counts -> packed_info (start, count), total -> hdr->n_total, across a cooperative grid:
+// per-CTA chunk sums | grid barrier (index first_barrier + 1) | chunk bases + in-chunk slab scans.  The caller puts a
+// barrier after it.  status = total > capacity, or a pre-set hdr->reserved[0] (a truncated ray); beyond the capacity
+// rays are truncated so that nothing downstream reads or writes out of bounds.
+__device__ __forceinline__ void coop_scan_counts(const int32_t *counts, const int64_t R, int64_t *packed_info, int64_t *partials,
+                                                 nsb_render_ws_header *hdr, const int64_t capacity, int64_t *red,
+                                                 const uint32_t first_barrier) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t chunk = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = min(R, (int64_t)blockIdx.x * chunk), r1 = min(R, r0 + chunk);
+    {
+        int64_t v = 0;
+        for (int64_t r = r0 + tid; r < r1; r += kCoopThreads) v += __ldcg(counts + r);
+        const int64_t tot = coop_block_sum(v, red, tid);
+        if (tid == 0) partials[blockIdx.x] = tot;
+    }
+    coop_grid_barrier(&hdr->barrier, (first_barrier + 1u) * gridDim.x);
+    int64_t before = 0, total = 0;
+    for (int b = tid; b < (int)gridDim.x; b += kCoopThreads) {
+        const int64_t p = __ldcg(partials + b);
+        total += p;
+        if (b < (int)blockIdx.x) before += p;
+    }
+    total = coop_block_sum(total, red, tid);
+    before = coop_block_sum(before, red, tid);
+    if (blockIdx.x == 0 && tid == 0) {
+        hdr->n_total = total;
+        hdr->status = (total > capacity || __ldcg(&hdr->reserved[0]) != 0) ? 1 : 0;
+    }
+    int64_t carry = before;
+    for (int64_t s0 = r0; s0 < r1; s0 += kCoopThreads) {
+        const int64_t r = s0 + tid;
+        const int64_t c = r < r1 ? (int64_t)__ldcg(counts + r) : 0;
+        int64_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        __syncthreads();
+        if (lane == 31) red[warp] = inc;
+        __syncthreads();
+        int64_t wbase = 0, slab = 0;
+        for (int w = 0; w < kCoopThreads / 32; ++w) {
+            const int64_t t = red[w];
+            if (w < warp) wbase += t;
+            slab += t;
+        }
+        if (r < r1) {
+            const int64_t st = min(carry + wbase + inc - c, capacity);
+            packed_info[2 * r] = st;
+            packed_info[2 * r + 1] = min(c, capacity - st);
+        }
+        carry += slab;
+    }
+}
+
 template <int LV>
 __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __grid_constant__ MarchCoopArgs K) {
     __shared__ int64_t red[kCoopThreads / 32];
@@ -311,55 +368,7 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
             K.M.counts[r] = march_occ_ray<false, LV>(K.M, r, 0, 0);
     }
     coop_grid_barrier(bar, 1u * gridDim.x);
-    const int64_t chunk = (R + gridDim.x - 1) / gridDim.x;
-    const int64_t r0 = min(R, (int64_t)blockIdx.x * chunk), r1 = min(R, r0 + chunk);
-    {
-        int64_t v = 0;
-        for (int64_t r = r0 + tid; r < r1; r += kCoopThreads) v += __ldcg(K.M.counts + r);
-        const int64_t tot = coop_block_sum(v, red, tid);
-        if (tid == 0) K.partials[blockIdx.x] = tot;
-    }
-    coop_grid_barrier(bar, 2u * gridDim.x);
-    {
-        int64_t before = 0, total = 0;
-        for (int b = tid; b < (int)gridDim.x; b += kCoopThreads) {
-            const int64_t p = __ldcg(K.partials + b);
-            total += p;
-            if (b < (int)blockIdx.x) before += p;
-        }
-        total = coop_block_sum(total, red, tid);
-        before = coop_block_sum(before, red, tid);
-        if (blockIdx.x == 0 && tid == 0) {
-            K.hdr->n_total = total;
-            K.hdr->status = (total > K.capacity || __ldcg(&K.hdr->reserved[0]) != 0) ? 1 : 0;
-        }
-        int64_t carry = before;
-        for (int64_t s0 = r0; s0 < r1; s0 += kCoopThreads) {
-            const int64_t r = s0 + tid;
-            const int64_t c = r < r1 ? (int64_t)__ldcg(K.M.counts + r) : 0;
-            int64_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t nb = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += nb;
-            }
-            __syncthreads();
-            if (lane == 31) red[warp] = inc;
-            __syncthreads();
-            int64_t wbase = 0, slab = 0;
-            for (int w = 0; w < kCoopThreads / 32; ++w) {
-                const int64_t t = red[w];
-                if (w < warp) wbase += t;
-                slab += t;
-            }
-            if (r < r1) {   // beyond the caller's capacity (status = 1) rays are truncated: nothing downstream reads out of bounds
-                    const int64_t st = min(carry + wbase + inc - c, K.capacity);
-                    K.packed_info[2 * r] = st;
-                    K.packed_info[2 * r + 1] = min(c, K.capacity - st);
-                }
-            carry += slab;
-        }
-    }
+    coop_scan_counts(K.M.counts, R, K.packed_info, K.partials, K.hdr, K.capacity, red, 1u);
     coop_grid_barrier(bar, 3u * gridDim.x);
     if (single) {
         // packing copy, one warp per ray: coalesced reads of the slot, coalesced writes of the packed arrays
@@ -400,6 +409,83 @@ int launch_march_occ_coop(const nsb_march_args &M, int64_t *packed_info, nsb_ren
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCoopThreads), kargs, 0, st);
     if (e != cudaSuccess) { set_error("march_occ_coop_kernel: %s", cudaGetErrorString(e)); return 2; }
     return check_launch("march_occ_coop_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// visibility filter + compaction of the kept samples in ONE cooperative launch (sync-free training sampler):
+//   V1 warp per ray: nerfacc render_visibility_from_density (same arithmetic as visibility_kernel), mask bytes + kept count
+//   V2 exclusive scan of the kept counts -> out_packed_info, total -> header.n_total
+//   V3 warp per ray: ballot-compaction of t_starts / t_ends / ray_indices and of the optional payload rows
+// ---------------------------------------------------------------------------------------------
+struct VisCompactK {
+    nsb_vis_compact_args a;
+    nsb_render_ws_header *hdr;
+    int64_t *partials;
+    int32_t *counts;
+    uint8_t *mask;
+};
+
+__global__ void __launch_bounds__(kCoopThreads) vis_compact_coop_kernel(const __grid_constant__ VisCompactK K) {
+    __shared__ int64_t red[kCoopThreads / 32];
+    const nsb_vis_compact_args &a = K.a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t R = a.n_rays;
+    float alpha_thre = a.alpha_thre;
+    if (a.alpha_thre_cap) alpha_thre = fminf(alpha_thre, __ldg(a.alpha_thre_cap));   // min(alpha_thre, occs.mean())
+    for (int64_t ray = (int64_t)blockIdx.x * (kCoopThreads / 32) + warp; ray < R; ray += (int64_t)gridDim.x * (kCoopThreads / 32)) {
+        const int64_t start = a.packed_info[2 * ray], cnt = a.packed_info[2 * ray + 1];
+        float carry = 0.f;
+        int32_t k = 0;
+        for (int64_t b = 0; b < cnt; b += 32) {
+            const int64_t i = b + lane;
+            float sd = 0.f;
+            if (i < cnt) sd = a.sigma[start + i] * (a.t_ends[start + i] - a.t_starts[start + i]);
+            const float incl = warp_incl_scan(sd, lane);
+            const float excl = carry + (incl - sd);
+            const float T = expf(-excl);
+            const float alpha = 1.0f - expf(-sd);
+            bool vis = T >= a.early_stop_eps;
+            if (alpha_thre > 0.0f) vis = vis && (alpha >= alpha_thre);
+            if (i < cnt) K.mask[start + i] = vis ? 1 : 0;
+            k += __popc(__ballot_sync(0xffffffffu, vis && i < cnt));
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) K.counts[ray] = k;
+    }
+    coop_grid_barrier(&K.hdr->barrier, 1u * gridDim.x);
+    coop_scan_counts(K.counts, R, a.out_packed_info, K.partials, K.hdr, a.capacity, red, 1u);
+    coop_grid_barrier(&K.hdr->barrier, 3u * gridDim.x);
+    for (int64_t ray = (int64_t)blockIdx.x * (kCoopThreads / 32) + warp; ray < R; ray += (int64_t)gridDim.x * (kCoopThreads / 32)) {
+        const int64_t start = a.packed_info[2 * ray], cnt = a.packed_info[2 * ray + 1];
+        int64_t dst = __ldcg(a.out_packed_info + 2 * ray);
+        for (int64_t b = 0; b < cnt; b += 32) {
+            const int64_t i = b + lane;
+            const bool keep = i < cnt && K.mask[start + i] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            const int64_t pos = dst + __popc(bal & ((1u << lane) - 1u));
+            if (keep) {
+                a.out_t_starts[pos] = a.t_starts[start + i];
+                a.out_t_ends[pos] = a.t_ends[start + i];
+                a.out_ray_indices[pos] = a.ray_indices[start + i];
+                if (a.xs) reinterpret_cast<float4 *>(a.out_xs)[pos] = reinterpret_cast<const float4 *>(a.xs)[start + i];
+            }
+            if (a.feat || a.corner_vals) {      // payload rows: the warp moves one kept sample at a time, 16 B per lane
+                uint32_t m = bal;
+                int64_t p = dst;
+                while (m) {
+                    const int src_lane = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int64_t si = start + b + src_lane;
+                    if (a.corner_vals)
+                        reinterpret_cast<uint4 *>(a.out_corner_vals)[p * 32 + lane] = reinterpret_cast<const uint4 *>(a.corner_vals)[si * 32 + lane];
+                    if (a.feat && lane < 4)
+                        reinterpret_cast<uint4 *>(a.out_feat)[p * 4 + lane] = reinterpret_cast<const uint4 *>(a.feat)[si * 4 + lane];
+                    ++p;
+                }
+            }
+            dst += __popc(bal);
+        }
+    }
 }
 
 }  // namespace nsb
@@ -506,4 +592,61 @@ extern "C" int nsb_occ_update(float *occs, uint8_t *binaries, int64_t n_cells, c
     occ_mean_kernel<<<296, 256, 0, st>>>(occs, n_cells, acc);
     occ_binarise_kernel<<<(int)((n_cells + T - 1) / T), T, 0, st>>>(occs, n_cells, acc, occ_thre, binaries);
     return check_launch("nsb_occ_update");
+}
+
+extern "C" int nsb_march_occupancy_packed(const nsb_march_args *args, int64_t capacity, int64_t *packed_info, void *workspace,
+                                          float *scratch, void *stream) {
+    if (!args || !args->origins || !args->directions || !args->near_planes || !args->far_planes || !args->binaries ||
+        !args->aabbs || !args->t_starts || !args->t_ends || !args->ray_indices || !packed_info || !workspace) {
+        set_error("nsb_march_occupancy_packed: null argument");
+        return 1;
+    }
+    if (args->levels < 1 || args->levels > 8 || capacity <= 0) { set_error("nsb_march_occupancy_packed: levels must be in [1,8], capacity > 0"); return 1; }
+    if (args->n_rays <= 0) return 0;
+    uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+    nsb_march_args M = *args;
+    M.counts = reinterpret_cast<int32_t *>(ws + 64 + 1024 * sizeof(int64_t));
+    M.offsets = nullptr;
+    return launch_march_occ_coop(M, packed_info, reinterpret_cast<nsb_render_ws_header *>(ws), reinterpret_cast<int64_t *>(ws + 64),
+                                 capacity, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int nsb_visibility_compact(const nsb_vis_compact_args *args, void *stream) {
+    if (!args || !args->packed_info || !args->t_starts || !args->t_ends || !args->sigma || !args->ray_indices ||
+        !args->out_packed_info || !args->out_t_starts || !args->out_t_ends || !args->out_ray_indices || !args->workspace) {
+        set_error("nsb_visibility_compact: null argument");
+        return 1;
+    }
+    if ((args->feat && !args->out_feat) || (args->xs && !args->out_xs) || (args->corner_vals && !args->out_corner_vals)) {
+        set_error("nsb_visibility_compact: payload without destination");
+        return 1;
+    }
+    if (args->n_rays <= 0) return 0;
+    uint8_t *ws = reinterpret_cast<uint8_t *>(args->workspace);
+    VisCompactK K;
+    K.a = *args;
+    K.hdr = reinterpret_cast<nsb_render_ws_header *>(ws);
+    K.partials = reinterpret_cast<int64_t *>(ws + 64);
+    K.counts = reinterpret_cast<int32_t *>(ws + 64 + 1024 * sizeof(int64_t));
+    // mask bytes: behind the counts (the workspace of nsb_vis_compact_workspace_bytes)
+    K.mask = ws + 64 + 1024 * sizeof(int64_t) + (((size_t)args->n_rays * sizeof(int32_t) + 63) / 64) * 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    static int grid = 0;
+    if (grid == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vis_compact_coop_kernel, kCoopThreads, 0);
+        grid = std::max(1, std::min(sms * std::max(1, std::min(per_sm, 4)), 1024));
+    }
+    cudaError_t e = cudaMemsetAsync(K.hdr, 0, sizeof(nsb_render_ws_header), st);
+    if (e != cudaSuccess) { set_error("nsb_visibility_compact: memset: %s", cudaGetErrorString(e)); return 2; }
+    void *kargs[] = {&K};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(vis_compact_coop_kernel), dim3(grid), dim3(kCoopThreads), kargs, 0, st);
+    if (e != cudaSuccess) { set_error("vis_compact_coop_kernel: %s", cudaGetErrorString(e)); return 2; }
+    return check_launch("vis_compact_coop_kernel");
+}
+
+extern "C" size_t nsb_vis_compact_workspace_bytes(int64_t n_rays, int64_t capacity) {
+    return 64 + 1024 * sizeof(int64_t) + (((size_t)std::max<int64_t>(n_rays, 1) * sizeof(int32_t) + 63) / 64) * 64 + (size_t)capacity + 64;
 }
