@@ -41,6 +41,19 @@ def _workspace(name: str, nbytes: int, dev) -> torch.Tensor:
     return t
 
 
+_ROW_QUANTUM = 1 << 16
+
+
+def _rows(n: int, tail=(), dtype=_F32, device=None, zero: bool = False) -> torch.Tensor:
+    """[n, *tail] as a view of an allocation rounded up to 65 536 rows.  The packed sample count changes every training
+    step (stratified jitter); exact-size allocations of the large per-sample buffers (2.7 GB of saved activations at
+    1.8 M samples) then miss the caching allocator's free blocks whenever the count grows and fall through to
+    cudaMalloc -- measured: 11 ms of host time per forward, 47 ms per step with the backward buffers (r2 profile)."""
+    n_alloc = max(((int(n) + _ROW_QUANTUM - 1) // _ROW_QUANTUM) * _ROW_QUANTUM, 1)
+    t = (torch.zeros if zero else torch.empty)((n_alloc,) + tuple(tail), dtype=dtype, device=device)
+    return t[:n]
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -166,7 +179,7 @@ def _make_opts(window_hash, window_deform, use_deformation, compute_rgb, disable
 def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_deformation=True,
                   origins=None, directions=None, ray_times=None, t_starts=None, t_ends=None, ray_indices=None,
                   positions=None, sample_times=None, sample_directions=None, sample_blend_codes=None,
-                  sample_warp_codes=None,
+                  sample_warp_codes=None, n_samples_dev: Optional[torch.Tensor] = None,
                   want: Sequence[str] = ("sigma", "rgb", "offsets"),
                   disable_initial: bool = True, soft_transition: bool = True) -> Dict[str, torch.Tensor]:
     """Fused deformation + hash ensemble + field MLPs for packed samples (nsb_field_forward)."""
@@ -208,28 +221,31 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
         scb = packing.deform_code_bias({0: w0, 4: w4}, {0: b0, 4: b4}, sample_warp_codes.to(dev))
         s.sample_code_bias = _ptr(scb); keep.append(scb)
     s.n_samples = n
+    if n_samples_dev is not None:      # the arrays hold `n` slots, the device scalar says how many are samples (no host sync)
+        assert n_samples_dev.dtype == torch.int64 and n_samples_dev.is_cuda and n_samples_dev.numel() == 1
+        s.n_samples_dev = _ptr(n_samples_dev); keep.append(n_samples_dev)
     out = {}
     o = _lib.FieldOut()
     if "sigma" in want:
-        out["sigma"] = torch.empty((n,), dtype=_F32, device=dev); o.sigma = _ptr(out["sigma"])
+        out["sigma"] = _rows(n, (), _F32, dev); o.sigma = _ptr(out["sigma"])
     if "rgb" in want:
-        out["rgb"] = torch.empty((n, 3), dtype=_F32, device=dev); o.rgb = _ptr(out["rgb"])
+        out["rgb"] = _rows(n, (3,), _F32, dev); o.rgb = _ptr(out["rgb"])
     if "offsets" in want:
         if use_deformation:
-            out["offsets"] = torch.empty((n, 3), dtype=_F32, device=dev); o.offsets = _ptr(out["offsets"])
+            out["offsets"] = _rows(n, (3,), _F32, dev); o.offsets = _ptr(out["offsets"])
         else:
-            out["offsets"] = torch.zeros((n, 3), dtype=_F32, device=dev)
+            out["offsets"] = _rows(n, (3,), _F32, dev, zero=True)
     if "feat" in want:
-        out["feat"] = torch.empty((n, 32), dtype=torch.float16, device=dev); o.feat = _ptr(out["feat"])
+        out["feat"] = _rows(n, (32,), torch.float16, dev); o.feat = _ptr(out["feat"])
     if "xs" in want:
-        out["xs"] = torch.empty((n, 4), dtype=_F32, device=dev); o.xs = _ptr(out["xs"])
+        out["xs"] = _rows(n, (4,), _F32, dev); o.xs = _ptr(out["xs"])
     if "corner_vals" in want:   # training forward: blended corner values, so the backward does not re-gather the tables
-        out["corner_vals"] = torch.empty((n, 16, 8, 2), dtype=torch.float16, device=dev)
+        out["corner_vals"] = _rows(n, (16, 8, 2), torch.float16, dev)
         o.corner_vals = _ptr(out["corner_vals"])
     if "deform_acts" in want:   # training forward: stem activations + posenc fragments for nsb_deform_backward
         n_tiles = (n + 127) // 128
-        out["deform_acts"] = torch.empty((n_tiles, 8, 6, 8, 32, 4), dtype=torch.int32, device=dev)
-        out["deform_enc"] = torch.empty((n_tiles, 8, 3, 32, 4), dtype=torch.int32, device=dev)
+        out["deform_acts"] = _rows(n_tiles * 128, (384,), torch.int32, dev).view(n_tiles, 8, 6, 8, 32, 4)
+        out["deform_enc"] = _rows(n_tiles * 128, (24,), torch.int32, dev).view(n_tiles, 8, 3, 32, 4)
         o.deform_acts, o.deform_enc = _ptr(out["deform_acts"]), _ptr(out["deform_enc"])
     if n == 0:
         return out
@@ -288,7 +304,7 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
     a.loss_scale = float(loss_scale)
     if saved.get("corner_vals") is not None:
         a.corner_vals = _ptr(saved["corner_vals"])
-    out = {"d_feat": torch.zeros((n, 32), dtype=_F32, device=dev),
+    out = {"d_feat": _rows(n, (32,), _F32, dev, zero=True),
            "d_base_w": torch.zeros((3072,), dtype=_F32, device=dev), "d_head_w": torch.zeros((7168,), dtype=_F32, device=dev)}
     a.d_feat, a.d_base_w, a.d_head_w = _ptr(out["d_feat"]), _ptr(out["d_base_w"]), _ptr(out["d_head_w"])
     # defer_tables: leave the table gradient in its rank-1 form (out["pending"]) for table_adam_step / rank1_expand
@@ -302,7 +318,7 @@ def field_backward(P: NativeParams, saved: Dict[str, torch.Tensor], d_sigma: Opt
         out["d_blend_codes"] = torch.zeros((P.n_timesteps, 32), dtype=_F32, device=dev)
         a.d_blend_codes = _ptr(out["d_blend_codes"])
     if want_dx:
-        out["d_xs"] = torch.zeros((n, 3), dtype=_F32, device=dev)
+        out["d_xs"] = _rows(n, (3,), _F32, dev, zero=True)
         a.d_xs = _ptr(out["d_xs"])
     if n == 0:
         return out
@@ -432,7 +448,7 @@ def losses_backward(state: dict, upstream: torch.Tensor):
     d_rgb = torch.empty((a.n_rays, 3), dtype=_F32, device=dev)
     d_acc = torch.empty((a.n_rays,), dtype=_F32, device=dev)
     d_depth = torch.empty((a.n_rays,), dtype=_F32, device=dev)
-    d_w = torch.zeros((a.n_samples,), dtype=_F32, device=dev)
+    d_w = _rows(a.n_samples, (), _F32, dev, zero=True)
     a.upstream, a.d_rgb, a.d_acc, a.d_depth, a.d_weights = _ptr(up), _ptr(d_rgb), _ptr(d_acc), _ptr(d_depth), _ptr(d_w)
     _lib.check(lib.nsb_losses_backward(C.byref(a), _stream()), "nsb_losses_backward")
     return d_rgb, d_acc, d_depth, d_w
@@ -510,7 +526,7 @@ def composite(packed_info: torch.Tensor, t_starts, t_ends, sigma, rgb, offsets=N
     if off is not None:
         out["deformation"] = torch.empty((R, 3), dtype=_F32, device=dev); a.out_deform = _ptr(out["deformation"])
     if want_weights:
-        out["weights"] = torch.empty((n, 1), dtype=_F32, device=dev); a.out_weights = _ptr(out["weights"])
+        out["weights"] = _rows(n, (1,), _F32, dev); a.out_weights = _ptr(out["weights"])
     ws = torch.empty((2,), dtype=torch.int32, device=dev)
     a.workspace = _ptr(ws)
     rc = lib.nsb_composite_forward(C.byref(a), _stream())
@@ -536,8 +552,8 @@ def composite_backward(packed_info, t_starts, t_ends, sigma, rgb, workspace, d_o
     a.t_starts, a.t_ends, a.sigma, a.rgb = _ptr(ts), _ptr(te), _ptr(sg), _ptr(cc)
     a.d_out_rgb, a.d_out_acc, a.d_out_depth, a.d_weights = _ptr(g_rgb), _ptr(g_acc), _ptr(g_dep), _ptr(g_w)
     a.workspace = _ptr(workspace)
-    d_sigma = torch.zeros((n,), dtype=_F32, device=ts.device)
-    d_rgb = torch.zeros((n, 3), dtype=_F32, device=ts.device)
+    d_sigma = _rows(n, (), _F32, ts.device, zero=True)
+    d_rgb = _rows(n, (3,), _F32, ts.device, zero=True)
     a.d_sigma, a.d_rgb = _ptr(d_sigma), _ptr(d_rgb)
     _lib.check(lib.nsb_composite_backward(C.byref(a), _stream()), "nsb_composite_backward")
     return d_sigma, d_rgb
@@ -551,8 +567,8 @@ def march_fixed(origins, directions, aabb: torch.Tensor, n_per_ray: int, step: f
     R = origins.shape[0]
     aabb_d = aabb.detach().to(dev, _F32).reshape(-1).contiguous()
     n = R * n_per_ray
-    ts = torch.empty((n,), dtype=_F32, device=dev); te = torch.empty((n,), dtype=_F32, device=dev)
-    ri = torch.empty((n,), dtype=torch.int32, device=dev)
+    ts, te = _rows(n, (), _F32, dev), _rows(n, (), _F32, dev)
+    ri = _rows(n, (), torch.int32, dev)
     info = torch.empty((R, 2), dtype=torch.int64, device=dev)
     rc = lib.nsb_march_fixed(_ptr(origins), _ptr(directions), R, _ptr(aabb_d), n_per_ray, float(step), float(near_plane),
                              _ptr(ts), _ptr(te), _ptr(ri), _ptr(info), _stream())
@@ -585,8 +601,8 @@ def march_occupancy(origins, directions, near_planes, far_planes, binaries: torc
     incl = torch.cumsum(cnt64, 0)
     offsets = (incl - cnt64).contiguous()
     n = int(incl[-1].item()) if R > 0 else 0       # host sync: the packed size is data dependent
-    ts = torch.empty((n,), dtype=_F32, device=dev); te = torch.empty((n,), dtype=_F32, device=dev)
-    ri = torch.empty((n,), dtype=torch.int32, device=dev)
+    ts, te = _rows(n, (), _F32, dev), _rows(n, (), _F32, dev)
+    ri = _rows(n, (), torch.int32, dev)
     if n > 0:
         a.offsets, a.t_starts, a.t_ends, a.ray_indices = _ptr(offsets), _ptr(ts), _ptr(te), _ptr(ri)
         _lib.check(lib.nsb_march_occupancy(C.byref(a), _stream()), "nsb_march_occupancy(fill)")
@@ -599,7 +615,7 @@ def visibility_mask(packed_info, t_starts, t_ends, sigma, early_stop_eps: float,
     packed_info = packed_info.to(torch.int64).contiguous()
     ts, te, sg = map(_f32c, (t_starts, t_ends, sigma))
     R = packed_info.shape[0]; n = ts.shape[0]
-    mask = torch.zeros((n,), dtype=torch.uint8, device=ts.device)
+    mask = _rows(n, (), torch.uint8, ts.device, zero=True)
     kept = torch.zeros((R,), dtype=torch.int32, device=ts.device)
     rc = lib.nsb_visibility_mask(_ptr(packed_info), R, _ptr(ts), _ptr(te), _ptr(sg), float(early_stop_eps),
                                  float(alpha_thre), _ptr(mask), _ptr(kept), _stream())
@@ -622,6 +638,89 @@ def occ_update(occs: torch.Tensor, binaries: torch.Tensor, cell_ids: torch.Tenso
     ws = _workspace("occ_update", int(lib.nsb_occ_update_scratch_bytes(n_cells)), occs.device)
     _lib.check(lib.nsb_occ_update(_ptr(occs), _ptr(binaries), n_cells, _ptr(ids), _ptr(new), int(ids.numel()),
                                   float(ema_decay), float(occ_thre), _ptr(ws), _stream()), "nsb_occ_update")
+
+
+def march_occupancy_packed(origins, directions, near_planes, far_planes, binaries: torch.Tensor, aabbs: torch.Tensor,
+                           step: float, cone_angle: float = 0.0, capacity: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """nerfacc traverse_grids as ONE cooperative launch without host synchronisation (nsb_march_occupancy_packed): the
+    samples land in arrays of `capacity` slots (default: an upper bound of the march), the count stays on the device.
+    Returns t_starts / t_ends / ray_indices [capacity], packed_info [R,2], `n_total` (int64 device scalar), `header`."""
+    lib = _lib.load()
+    origins, directions, near_planes, far_planes = map(_f32c, (origins, directions, near_planes, far_planes))
+    _need_cuda(origins, directions, near_planes, far_planes, binaries, aabbs)
+    dev, R = origins.device, int(origins.shape[0])
+    b8 = binaries.detach().contiguous()
+    b8 = b8.view(torch.uint8) if b8.dtype == torch.bool else b8.to(torch.uint8)
+    levels, res = int(b8.shape[0]), int(b8.shape[1])
+    assert b8.shape[1] == b8.shape[2] == b8.shape[3], "cubic grids only"
+    ab = aabbs.detach().to(dev, _F32).reshape(levels, 6).contiguous()
+    if capacity is None:
+        diag = float((ab[:, 3:] - ab[:, :3]).norm(dim=-1).max())
+        capacity = R * (int(diag / float(step)) + 2 * levels + 2)
+    cap = max(int(capacity), 1)
+    a = _lib.MarchArgs()
+    a.n_rays = R
+    a.origins, a.directions, a.near_planes, a.far_planes = _ptr(origins), _ptr(directions), _ptr(near_planes), _ptr(far_planes)
+    a.binaries, a.aabbs, a.levels, a.res = _ptr(b8), _ptr(ab), levels, res
+    a.step, a.cone_angle = float(step), float(cone_angle)
+    out = {"t_starts": torch.empty((cap,), dtype=_F32, device=dev), "t_ends": torch.empty((cap,), dtype=_F32, device=dev),
+           "ray_indices": torch.empty((cap,), dtype=torch.int32, device=dev),
+           "packed_info": torch.empty((R, 2), dtype=torch.int64, device=dev), "capacity": cap}
+    a.t_starts, a.t_ends, a.ray_indices = _ptr(out["t_starts"]), _ptr(out["t_ends"]), _ptr(out["ray_indices"])
+    ws = torch.empty((int(lib.nsb_render_workspace_bytes(R)) + 7) // 8, dtype=torch.int64, device=dev)
+    scratch = torch.empty((2, cap), dtype=_F32, device=dev) if cap >= R else None
+    out["header"], out["n_total"] = ws, ws[2:3]
+    out["_keep"] = [origins, directions, near_planes, far_planes, b8, ab, scratch]
+    if R > 0:
+        _lib.check(lib.nsb_march_occupancy_packed(C.byref(a), cap, _ptr(out["packed_info"]), _ptr(ws), _ptr(scratch), _stream()),
+                   "nsb_march_occupancy_packed")
+    else:
+        ws.zero_()
+    return out
+
+
+def visibility_compact(cand: Dict[str, torch.Tensor], sigma: torch.Tensor, early_stop_eps: float, alpha_thre: float,
+                       alpha_thre_cap: Optional[torch.Tensor] = None, payload: Optional[Dict[str, torch.Tensor]] = None
+                       ) -> Dict[str, torch.Tensor]:
+    """nerfacc render_visibility_from_density + packing of the surviving samples, one cooperative launch, no host sync
+    (nsb_visibility_compact).  cand: march_occupancy_packed's result; sigma [capacity]; alpha_thre_cap: device scalar
+    (occs.mean()) -> alpha_thre = min(alpha_thre, cap).  payload: optional {feat [cap,32] half, xs [cap,4], corner_vals
+    [cap,16,8,2] half} rows that move with their samples.  Returns the packed arrays [capacity], packed_info, n_total."""
+    lib = _lib.load()
+    dev = sigma.device
+    cap, R = int(cand["capacity"]), int(cand["packed_info"].shape[0])
+    sg = _f32c(sigma).reshape(-1)
+    assert sg.shape[0] >= cap
+    a = _lib.VisCompactArgs()
+    a.n_rays, a.capacity = R, cap
+    a.packed_info, a.t_starts, a.t_ends, a.sigma, a.ray_indices = (_ptr(cand["packed_info"]), _ptr(cand["t_starts"]), _ptr(cand["t_ends"]),
+                                                                   _ptr(sg), _ptr(cand["ray_indices"]))
+    a.early_stop_eps, a.alpha_thre = float(early_stop_eps), float(alpha_thre)
+    keep = [sg]
+    if alpha_thre_cap is not None:
+        capt = _f32c(alpha_thre_cap).reshape(1)
+        a.alpha_thre_cap = _ptr(capt); keep.append(capt)
+    out = {"t_starts": torch.empty((cap,), dtype=_F32, device=dev), "t_ends": torch.empty((cap,), dtype=_F32, device=dev),
+           "ray_indices": torch.empty((cap,), dtype=torch.int32, device=dev),
+           "packed_info": torch.empty((R, 2), dtype=torch.int64, device=dev), "capacity": cap}
+    a.out_packed_info, a.out_t_starts, a.out_t_ends, a.out_ray_indices = (_ptr(out["packed_info"]), _ptr(out["t_starts"]),
+                                                                          _ptr(out["t_ends"]), _ptr(out["ray_indices"]))
+    if payload:
+        for name, shape, dt in (("feat", (cap, 32), torch.float16), ("xs", (cap, 4), _F32), ("corner_vals", (cap, 16, 8, 2), torch.float16)):
+            if payload.get(name) is not None:
+                src = payload[name]
+                assert src.dtype == dt and src.is_contiguous() and tuple(src.shape) == shape, (name, src.shape, src.dtype)
+                out[name] = torch.empty(shape, dtype=dt, device=dev)
+                setattr(a, name, _ptr(src)); setattr(a, "out_" + name, _ptr(out[name])); keep.append(src)
+    ws = torch.empty((int(lib.nsb_vis_compact_workspace_bytes(R, cap)) + 7) // 8, dtype=torch.int64, device=dev)
+    a.workspace = _ptr(ws)
+    out["header"], out["n_total"] = ws, ws[2:3]
+    out["_keep"] = keep + [cand]
+    if R > 0:
+        _lib.check(lib.nsb_visibility_compact(C.byref(a), _stream()), "nsb_visibility_compact")
+    else:
+        ws.zero_()
+    return out
 
 
 class RenderResult(dict):

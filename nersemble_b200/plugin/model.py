@@ -184,6 +184,7 @@ class NeRSembleNGPModel(Model):
         self.fused_losses = True         # ... and, when the outputs come from get_outputs, in fused kernels (_loss_dict_fused)
         self.lpips = None                # optional callable(image[1,3,H,W], rgb[1,3,H,W]) -> scalar (needs pretrained weights)
         self.use_fused_render = True     # eval renders: sampler -> field -> composite fused, no host sync (ops.render_rays)
+        self.use_fused_sampler = True    # training: march / density pre-pass / visibility / packing with one host sync
 
     def populate_modules(self):
         """models/nersemble_instant_ngp.py:81-179 (+ BaseModel.populate_modules, base.py:38-47)."""
@@ -323,6 +324,39 @@ class NeRSembleNGPModel(Model):
                                near_planes=near_planes, far_planes=far_planes, binaries=og.binaries, aabbs=og.aabbs,
                                step=cfg.render_step_size, cone_angle=cfg.cone_angle, **self._blend_opts())
 
+    @torch.no_grad()
+    def _sample_packed(self, ray_bundle: RayBundle, jitter: Optional[Tensor]):
+        """The sampler call of get_outputs (models/nersemble_instant_ngp.py:283-291) through
+        NeRSembleVolumetricSampler.sample_packed: (RaySamples, ray_indices, packed_info) with one host synchronisation."""
+        from ..nerfstudio_shim import Frustums
+        cfg = self.config
+        wh, wd = self._windows()
+        o = ray_bundle.origins.reshape(-1, 3).contiguous()
+        d = ray_bundle.directions.reshape(-1, 3).contiguous()
+        ray_times = self._ray_times(ray_bundle)
+
+        def sigma_packed(cand):
+            """field_density_fn (:235-266) on the candidates' midpoints, sample count read on the device."""
+            if cfg.disable_occupancy_grid:
+                return torch.ones((cand["capacity"],), dtype=torch.float32, device=o.device), None
+            f = ops.field_forward(self.native_params(), window_hash=wh, window_deform=wd, use_deformation=cfg.use_deformation_field,
+                                  origins=o, directions=d, ray_times=ray_times, t_starts=cand["t_starts"], t_ends=cand["t_ends"],
+                                  ray_indices=cand["ray_indices"], n_samples_dev=cand["n_total"], want=("sigma",), **self._blend_opts())
+            return f["sigma"], None
+
+        s = self.sampler.sample_packed(ray_bundle, render_step_size=cfg.render_step_size, near_plane=cfg.near_plane,
+                                       far_plane=cfg.far_plane, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
+                                       early_stop_eps=cfg.early_stop_eps, jitter=jitter, sigma_packed_fn=sigma_packed)
+        ri = s["ray_indices"].long()
+        origins = o[ri]
+        ci = ray_bundle.camera_indices
+        ray_samples = RaySamples(frustums=Frustums(origins=origins, directions=d[ri], starts=s["t_starts"][:, None],
+                                                   ends=s["t_ends"][:, None], pixel_area=torch.zeros_like(origins[:, :1])),
+                                 camera_indices=None if ci is None else ci.reshape(-1, ci.shape[-1])[ri])
+        if ray_bundle.times is not None:
+            ray_samples.times = ray_bundle.times.reshape(-1, 1)[ri]
+        return ray_samples, ri, s["packed_info"]
+
     def _fused_ok(self) -> bool:
         return self.use_fused_render and not self.sampler.training and self.scene_aabb.is_cuda
 
@@ -374,19 +408,22 @@ class NeRSembleNGPModel(Model):
                     outputs["deformation"] = res["deformation"]
                 return outputs
             # no sample at all: the reference inserts one fake sample (nersemble_volumetric_sampler.py:110-114) -> general path
-        with torch.no_grad():
-            ray_samples, ray_indices = self.sampler(
-                ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
-                render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
-                early_stop_eps=cfg.early_stop_eps, jitter=jitter)
+        if self.use_fused_sampler and self.scene_aabb.is_cuda:
+            ray_samples, ray_indices, packed_info = self._sample_packed(ray_bundle, jitter)
+        else:
+            with torch.no_grad():
+                ray_samples, ray_indices = self.sampler(
+                    ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
+                    render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
+                    early_stop_eps=cfg.early_stop_eps, jitter=jitter)
+            cnt = torch.zeros(num_rays, dtype=torch.long, device=ray_indices.device).index_add_(
+                0, ray_indices, torch.ones_like(ray_indices))
+            packed_info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)           # nerfacc.pack_info (:325)
         if ray_samples.metadata is None:
             ray_samples.metadata = dict()
         ray_times = self._ray_times(ray_bundle)
         starts = ray_samples.frustums.starts[..., 0].contiguous()
         ends = ray_samples.frustums.ends[..., 0].contiguous()
-        cnt = torch.zeros(num_rays, dtype=torch.long, device=starts.device).index_add_(
-            0, ray_indices, torch.ones_like(ray_indices))
-        packed_info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)           # nerfacc.pack_info (:325)
         if needs_grad:
             he = self.field.hash_ensemble
             params = [he.tables, self.field.mlp_base.params, self.field.mlp_head.params,

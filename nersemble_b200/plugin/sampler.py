@@ -164,6 +164,49 @@ class NeRSembleVolumetricSampler(nn.Module):
             self.occupancy_grid.binaries[0] = self.occupancy_grid.binaries[0] & self.camera_frustum_grid.to(self.occupancy_grid.binaries.device)
         return near_planes, far_planes
 
+    @torch.no_grad()
+    def sample_packed(self, ray_bundle: RayBundle, render_step_size: float, near_plane: float = 0.0,
+                      far_plane: Optional[float] = None, alpha_thre: float = 0.01, cone_angle: float = 0.0,
+                      early_stop_eps: float = 1e-4, jitter: Optional[Tensor] = None, sigma_packed_fn=None):
+        """forward() for the model's own use, with ONE host synchronisation instead of four: the nerfacc march as a
+        cooperative launch whose count stays on the device (ops.march_occupancy_packed), the density of the candidates
+        from `sigma_packed_fn(candidates) -> (sigma [capacity], payload | None)` evaluated with a device-side count,
+        then visibility filter + packing in one launch (ops.visibility_compact, alpha_thre capped by occs.mean() on the
+        device).  Same kernels' arithmetic as forward(): the kept samples are identical.  Returns a dict with the packed
+        t_starts / t_ends / ray_indices (int32) [n], packed_info [R,2], optional payload rows, and n (a Python int: the
+        one sync, needed because the plugin contract hands out exact-size per-sample tensors)."""
+        near_planes, far_planes = self.eval_planes(ray_bundle, near_plane, far_plane)
+        rays_o = ray_bundle.origins.reshape(-1, 3).contiguous()
+        rays_d = ray_bundle.directions.reshape(-1, 3).contiguous()
+        og = self.occupancy_grid
+        if self.training:                                          # stratified = self.training (forward())
+            u = torch.rand_like(near_planes) if jitter is None else jitter.to(near_planes)
+            near_planes = near_planes + u * render_step_size
+        cand = ops.march_occupancy_packed(rays_o, rays_d, near_planes, far_planes, og.binaries, og.aabbs, render_step_size, cone_angle)
+        kept = cand
+        if (alpha_thre > 0.0 or early_stop_eps > 0.0) and self.density_fn is not None and self.training and sigma_packed_fn is not None:
+            sigma, payload = sigma_packed_fn(cand)
+            kept = ops.visibility_compact(cand, sigma, early_stop_eps, alpha_thre, alpha_thre_cap=og.occs.mean(), payload=payload)
+        head = kept["header"][:3].tolist()                        # the one host synchronisation: (.., status, n_total)
+        n, status = int(head[2]), int(head[1]) >> 32
+        if status != 0 or n > kept["capacity"]:
+            raise RuntimeError(f"sampler: the march produced more samples than its workspace holds ({n} > {kept['capacity']})")
+        out = {k: kept[k][:n] for k in ("t_starts", "t_ends", "ray_indices")}
+        for k in ("feat", "xs", "corner_vals"):
+            if k in kept:
+                out[k] = kept[k][:n]
+        out["packed_info"], out["n"] = kept["packed_info"], n
+        if n == 0:      # zero-sample guard (nersemble_volumetric_sampler.py:110-114): one fake sample on ray 0
+            dev = rays_o.device
+            out["t_starts"] = torch.ones((1,), dtype=torch.float32, device=dev)
+            out["t_ends"] = torch.ones((1,), dtype=torch.float32, device=dev)
+            out["ray_indices"] = torch.zeros((1,), dtype=torch.int32, device=dev)
+            pi = torch.zeros_like(kept["packed_info"]); pi[0, 1] = 1
+            out["packed_info"], out["n"] = pi, 1
+            for k in ("feat", "xs", "corner_vals"):
+                out.pop(k, None)
+        return out
+
     def forward(self, ray_bundle: RayBundle, render_step_size: float, near_plane: float = 0.0,
                 far_plane: Optional[float] = None, alpha_thre: float = 0.01, cone_angle: float = 0.0,
                 early_stop_eps: float = 1e-4, jitter: Optional[Tensor] = None) -> Tuple[RaySamples, Tensor]:

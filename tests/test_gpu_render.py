@@ -144,3 +144,82 @@ def test_plugin_eval_paths_use_the_fused_render(trained):
     rs, rs_ref = full["ray_samples"][0], full_ref["ray_samples"][0]
     assert _same(rs.frustums.starts, rs_ref.frustums.starts) and _same(rs.frustums.offsets, rs_ref.frustums.offsets)
     assert _same(rs.frustums.origins, rs_ref.frustums.origins) and _same(rs.times, rs_ref.times)
+
+
+def test_sync_free_training_sampler_matches_the_four_sync_path(trained):
+    """Training-mode get_outputs: cooperative march + density pre-pass with a device-side count + visibility/packing in
+    one launch (one host sync) against the original path (march count / cumsum / fill, occs.mean().item(), density_fn,
+    visibility kernel, boolean indexing): the same kept samples bit for bit, the same outputs and gradients."""
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    from oracle.gen_golden import blob_grid
+    from test_plugin_cpu import make_model
+    from test_plugin_gpu import load_oracle_params_into
+    P, _ = trained
+    m = make_model(T=4, log2T=14)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).train()
+    m.sched_window_hash_encodings.value = 32.0; m.sched_window_deform.value = 7.0
+    occ = blob_grid(5)
+    m.occupancy_grid.binaries[0] = occ.to(DEV)
+    m.occupancy_grid.occs.copy_((occ.flatten().float() * 0.05).to(DEV))
+    R = 900
+    o, d, t = _rays(R, 13)
+    o[6] = torch.tensor([50.0, 50.0, 50.0], device=DEV); d[6] = torch.tensor([0.0, 1.0, 0.0], device=DEV)
+    rb = RayBundle(origins=o, directions=d, pixel_area=torch.ones(R, 1, device=DEV),
+                   camera_indices=torch.zeros(R, 1, dtype=torch.long, device=DEV), times=t[:, None] if t.dim() == 1 else t)
+    jit = torch.rand(R, generator=torch.Generator().manual_seed(1)).to(DEV)
+    res = {}
+    for fused in (True, False):
+        m.use_fused_sampler = fused
+        m.zero_grad(set_to_none=True)
+        m.field.hash_ensemble.pending_table_grad = None
+        out = m.get_outputs(rb, jitter=jit)
+        (out["rgb"].sum() + out["accumulation"].sum() * 0.3).backward()
+        res[fused] = (out, m.field.mlp_base.params.grad.clone(), m.time_embedding.weight.grad.clone())
+    a, b = res[True][0], res[False][0]
+    assert a["ray_indices"][0].numel() > 2000
+    assert _same(a["ray_indices"][0], b["ray_indices"][0])
+    assert _same(a["ray_samples"][0].frustums.starts, b["ray_samples"][0].frustums.starts)
+    assert _same(a["ray_samples"][0].frustums.ends, b["ray_samples"][0].frustums.ends)
+    assert _same(a["num_samples_per_ray"], b["num_samples_per_ray"])
+    for k in ("rgb", "accumulation", "depth", "deformation"):
+        assert _same(a[k], b[k]), k
+    assert _same(a["weights"][0], b["weights"][0])
+    # gradients: float atomics in the scatter -> rounding-order noise only
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-3, atol=1e-7)
+    # an empty occupancy grid: the zero-sample guard (one fake sample on ray 0) on both paths
+    m.occupancy_grid.binaries[:] = False
+    with torch.no_grad():
+        m.use_fused_sampler = True
+        z1 = m.get_outputs(rb, jitter=jit)
+        m.use_fused_sampler = False
+        z0 = m.get_outputs(rb, jitter=jit)
+    assert z1["ray_indices"][0].numel() == 1 and _same(z1["rgb"], z0["rgb"]) and _same(z1["depth"], z0["depth"])
+    assert _same(z1["num_samples_per_ray"], z0["num_samples_per_ray"])
+
+
+def test_visibility_compact_moves_payload_rows_with_their_samples():
+    from nersemble_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    R = 300
+    cnt = torch.randint(0, 90, (R,), generator=g); cnt[7] = 0; cnt[R - 1] = 0
+    n = int(cnt.sum()); cap = n + 100
+    ri = torch.repeat_interleave(torch.arange(R), cnt)
+    ts = torch.rand((n,), generator=g); te = ts + 0.011
+    sig = torch.rand((n,), generator=g) * 60
+    pad = lambda x, fill=0: torch.cat([x, torch.full((cap - n,) + tuple(x.shape[1:]), fill, dtype=x.dtype)])
+    info = torch.stack([cnt.cumsum(0) - cnt, cnt], -1)
+    cand = {"t_starts": pad(ts).to(DEV), "t_ends": pad(te).to(DEV), "ray_indices": pad(ri.int()).to(DEV),
+            "packed_info": info.to(DEV), "capacity": cap}
+    payload = {"feat": torch.randn((cap, 32), generator=g).half().to(DEV), "xs": torch.rand((cap, 4), generator=g).to(DEV),
+               "corner_vals": torch.randn((cap, 16, 8, 2), generator=g).half().to(DEV)}
+    occs_mean = torch.tensor(0.3, device=DEV)
+    mask, kept = ops.visibility_mask(info.to(DEV), ts.to(DEV), te.to(DEV), sig.to(DEV), 1e-3, min(0.5, 0.3))
+    got = ops.visibility_compact(cand, pad(sig).to(DEV), 1e-3, 0.5, alpha_thre_cap=occs_mean, payload=payload)
+    k = int(got["n_total"].item())
+    assert k == int(mask.sum()) and 0 < k < n
+    assert _same(got["packed_info"][:, 1], kept.long())
+    assert _same(got["t_starts"][:k], ts.to(DEV)[mask]) and _same(got["ray_indices"][:k], ri.int().to(DEV)[mask])
+    for name in ("feat", "xs", "corner_vals"):
+        assert _same(got[name][:k], payload[name][:n][mask]), name
