@@ -500,7 +500,7 @@ def run_config2(args, occ=False):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp) and world == 1:
-            traffic = json.load(open(tp)).get("field_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("render_kernel_ws_dram_bytes_per_launch")
         line = {
             "metric": "M ray-samples/sec", "value": value, "unit": "M ray-samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_value / K, "higher_is_better": True,

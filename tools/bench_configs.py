@@ -49,26 +49,27 @@ def _train_loop(args, D, model, opts, params, batch, rb, with_allreduce):
     HE = [model.field.hash_ensemble]
     W, K = max(args.warmup, 3), args.steps
     phases = {k: 0.0 for k in ("forward", "losses", "backward", "allreduce", "optimizer")}
-    marks = []
+    host = {k: 0.0 for k in phases}          # host time to ENQUEUE each phase (no synchronisation inside the loop except the sampler's)
+    marks, hmarks = [], []
 
     def ev():
         e = torch.cuda.Event(enable_timing=True); e.record(); return e
 
     def step(record):
-        e = [ev()]
+        e = [ev()]; h = [time.perf_counter()]
         for o in opts:
             o.zero_grad(set_to_none=True)
-        out = model.get_outputs(rb); e.append(ev())
-        loss = sum(model.get_loss_dict(out, batch).values()); e.append(ev())
-        loss.backward(); e.append(ev())
+        out = model.get_outputs(rb); e.append(ev()); h.append(time.perf_counter())
+        loss = sum(model.get_loss_dict(out, batch).values()); e.append(ev()); h.append(time.perf_counter())
+        loss.backward(); e.append(ev()); h.append(time.perf_counter())
         if with_allreduce:
             allreduce_gradients(params, hash_ensembles=HE)
-        e.append(ev())
+        e.append(ev()); h.append(time.perf_counter())
         for o in opts:
             o.step()
-        e.append(ev())
+        e.append(ev()); h.append(time.perf_counter())
         if record:
-            marks.append(e)
+            marks.append(e); hmarks.append(h)
         return out, loss
 
     for _ in range(W):
@@ -83,10 +84,12 @@ def _train_loop(args, D, model, opts, params, batch, rb, with_allreduce):
         n_samples.add_(out["num_samples_per_ray"].sum())
     ms = B.timed(D, timed_step, K, sampler)
     sampler.stop_flag = True
-    for e in marks:
+    for e, h in zip(marks, hmarks):
         for i, k in enumerate(phases):
             phases[k] += e[i].elapsed_time(e[i + 1]) / len(marks)
-    return ms, int(n_samples.item()), phases, float(loss), sampler
+            host[k] += (h[i + 1] - h[i]) * 1e3 / len(marks)
+    phases["host_enqueue"] = host
+    return ms, int(n_samples.item()), phases, float(loss.detach()), sampler
 
 
 def run_config3(args, config5=False):
@@ -119,6 +122,7 @@ def run_config3(args, config5=False):
     ms, n_samples, phases, loss, sampler = _train_loop(args, D, model, opts, params, batch, rb, with_allreduce=world > 1)
     (ms,) = D.max_ms(ms)
     (tot_samples,) = D.sum(float(n_samples))
+    host = phases.pop("host_enqueue")
     ph = D.max_ms(*phases.values())
     if rank == 0:
         name = ("config5: seq-97 recipe, --disable_occupancy_grid dense march, lambda_dist 0, 4096 rays per GPU, full gradient step"
@@ -133,7 +137,7 @@ def run_config3(args, config5=False):
                                            + ("" if args.no_overlap else "; the 1.2 GB table-gradient reduction overlaps the deformation-field backward")
                                            if world > 1 else "single GPU"),
                            "tables": "32 x (16 levels, 2^19) fp32 master + fp16 shadow", "n_timesteps": B.N_TIMESTEPS},
-                "phases_ms": dict(zip(phases.keys(), ph)), "loss": loss, "clocks": sampler.summary(),
+                "phases_ms": dict(zip(phases.keys(), ph)), "host_enqueue_ms": host, "loss": loss, "clocks": sampler.summary(),
                 "gpu_launches": None}
         print(json.dumps(line), flush=True)
     D.close()

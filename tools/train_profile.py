@@ -34,3 +34,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     out = step(); torch.cuda.synchronize()
 print("kept samples", int(out["num_samples_per_ray"].sum()))
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+print("==== sorted by CPU time (host-side cost of one step)")
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=90))
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(10): step()
+t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"10 steps: host enqueue {1e2 * (t1 - t0):.2f} ms/step, wall {1e2 * (t2 - t0):.2f} ms/step")
