@@ -311,8 +311,28 @@ class Dist:
         return [float(x) for x in t.cpu()]
 
     def close(self):
+        """End of the run.  N > 1: communicators that were captured into CUDA graphs made destroy_process_group() hang
+        (r2i: rank 0 had printed its line, then torchrun sat until the outer timeout), so the graphs are reset first and
+        the process leaves through os._exit after a last barrier."""
+        import torch
+        for g in _GRAPHS:
+            try:
+                g.reset()
+            except Exception:  # noqa: BLE001
+                pass
+        _GRAPHS.clear()
+        torch.cuda.synchronize()
         if self.world > 1:
-            self.dist.destroy_process_group()
+            try:
+                self.dist.barrier()
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+
+_GRAPHS: list = []
 
 
 def timed(D, fn, K, sampler=None):
@@ -347,6 +367,7 @@ def graphed(fn, dev):
         with torch.cuda.graph(g):
             fn()
         torch.cuda.synchronize()
+        _GRAPHS.append(g)
         return g.replay, True
     except Exception as e:  # noqa: BLE001  (capture of a collective can be refused: fall back to eager launches)
         sys.stderr.write(f"[bench] CUDA-graph capture failed, running eagerly: {e!r}\n")
@@ -533,8 +554,9 @@ def run_config2(args, occ=False):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
         if parity is not None and not (parity["rgb_l2_max"] < 1e-3):
-            D.close()
-            raise SystemExit(f"parity FAILED: max per-ray RGB L2 vs the oracle = {parity['rgb_l2_max']:.3e} >= 1e-3")
+            sys.stderr.write(f"parity FAILED: max per-ray RGB L2 vs the oracle = {parity['rgb_l2_max']:.3e} >= 1e-3\n")
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(1)
     D.close()
 
 

@@ -103,6 +103,9 @@ typedef struct nsb_samples {
     const float *sample_directions; /* [n_samples][3] or NULL (density_fn uses ones: nersemble_nerfacto_field.py:240) */
     const int64_t *n_samples_dev;    /* optional DEVICE scalar: the packed sample count when only the device knows it (the
                                         sync-free training sampler); n_samples is then the capacity of the arrays */
+    const void *given_feat;          /* optional __half [n_samples][32]: blended hash features already gathered for these
+                                        samples (the density pre-pass of the training sampler, packed by
+                                        nsb_visibility_compact); the kernel then skips the table gather entirely */
     /* optional per-sample conditioning overriding the time-embedding tables (component APIs) */
     const float *sample_blend_codes; /* float  [n_samples][32] or NULL */
     const float *sample_code_bias;   /* float [n_samples][2][128] or NULL: W_code(layer 0|4) . warp_code[sample] + bias

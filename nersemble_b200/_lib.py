@@ -41,7 +41,8 @@ class Samples(C.Structure):
                 ("origins", C.c_void_p), ("directions", C.c_void_p), ("ray_times", C.c_void_p),
                 ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("ray_indices", C.c_void_p),
                 ("positions", C.c_void_p), ("sample_times", C.c_void_p), ("sample_directions", C.c_void_p),
-                ("n_samples_dev", C.c_void_p), ("sample_blend_codes", C.c_void_p), ("sample_code_bias", C.c_void_p)]
+                ("n_samples_dev", C.c_void_p), ("given_feat", C.c_void_p), ("sample_blend_codes", C.c_void_p),
+                ("sample_code_bias", C.c_void_p)]
 
 
 class FieldOut(C.Structure):

@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FEAT_GIVEN = false;
     // NOTE: nothing is computed ahead of the role split on purpose.  Values shared by both roles get registers that
     // suit the 88-register tensor role, and the 64-register gather role then pays for them with spills inside its
     // sample loop (measured: 2.59 -> 2.77 ms).  Each role derives its loop bounds itself.
@@ -322,6 +323,27 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws(const __gri
 #undef NSB_N_SAMPLES
 }
 
+// Training forward over the KEPT samples when the density pre-pass already gathered their features (SURVEY 8(f)-1:
+// "reuse the pre-pass evaluation"): deformation MLP (activations saved for the backward) + density / colour MLPs from
+// nsb_samples.given_feat; the gather warps exit at once -- no table line is read a second time.
+template <bool DEFORM>
+__global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_given(const __grid_constant__ FieldArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FIELD = true, HEAD = true, SAVE = true, FEAT_GIVEN = true;
+#define NSB_N_SAMPLES A.S.n_samples
+#include "nsb_field_setup.inc"
+    if (warp >= kTensorWarps) {
+        if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+#include "nsb_field_gather_role.inc"
+        return;
+    }
+    if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+#include "nsb_field_tensor_role.inc"
+#undef NSB_N_SAMPLES
+}
+
 // field_kernel_ws with the sample count read from DEVICE memory (nsb_samples.n_samples_dev; the sync-free training
 // sampler: the host never learns how many candidates the march produced).  grid = number of SMs; A.S.n_samples is the
 // capacity of the sample arrays.  Same role bodies.
@@ -330,6 +352,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_dyn(const _
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FEAT_GIVEN = false;
     if (tid == 0) sm.n_dyn = min(*A.S.n_samples_dev, A.S.n_samples);      // visible after the setup's __syncthreads
 #define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
 #include "nsb_field_setup.inc"
@@ -532,7 +555,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_ws(const __gr
     SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
     const FieldArgs &A = K.F;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr bool FIELD = true, HEAD = true, SAVE = false;
+    constexpr bool FIELD = true, HEAD = true, SAVE = false, FEAT_GIVEN = false;
 
 #define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
 #include "nsb_field_setup.inc"
@@ -644,8 +667,28 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
     return save ? launch_field_ws_<D, F, H, true>(A, st) : launch_field_ws_<D, F, H, false>(A, st);
 }
 
+template <bool D>
+static int launch_field_given(const FieldArgs &A, cudaStream_t st) {
+    const size_t smem = sizeof(SmemWS);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(field_kernel_ws_given<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(field_kernel_ws_given): %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms());
+    field_kernel_ws_given<D><<<grid, kThreadsWS, smem, st>>>(A);
+    return check_launch("field_kernel_ws_given");
+}
+
 template <bool D, bool F, bool H>
 static int launch_field(const FieldArgs &A, cudaStream_t st) {
+    if (A.S.given_feat) {
+        if (F && H && !A.S.n_samples_dev) return launch_field_given<D>(A, st);
+        set_error("nsb_field_forward: given_feat needs the full evaluation (rgb) and a host-side sample count");
+        return 1;
+    }
     if (A.S.n_samples_dev) {
         // always the SAVE instantiation (its stores are skipped at run time when the pointers are NULL): ptxas gives its
         // gather role 0 spill instructions, the non-SAVE density instantiation 37 (tools/spill_report.py)

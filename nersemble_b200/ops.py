@@ -180,6 +180,7 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
                   origins=None, directions=None, ray_times=None, t_starts=None, t_ends=None, ray_indices=None,
                   positions=None, sample_times=None, sample_directions=None, sample_blend_codes=None,
                   sample_warp_codes=None, n_samples_dev: Optional[torch.Tensor] = None,
+                  given_feat: Optional[torch.Tensor] = None,
                   want: Sequence[str] = ("sigma", "rgb", "offsets"),
                   disable_initial: bool = True, soft_transition: bool = True) -> Dict[str, torch.Tensor]:
     """Fused deformation + hash ensemble + field MLPs for packed samples (nsb_field_forward)."""
@@ -224,6 +225,11 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
     if n_samples_dev is not None:      # the arrays hold `n` slots, the device scalar says how many are samples (no host sync)
         assert n_samples_dev.dtype == torch.int64 and n_samples_dev.is_cuda and n_samples_dev.numel() == 1
         s.n_samples_dev = _ptr(n_samples_dev); keep.append(n_samples_dev)
+    if given_feat is not None:         # pre-pass reuse: the blended features are an INPUT, the table gather is skipped
+        assert given_feat.dtype == torch.float16 and given_feat.is_contiguous() and tuple(given_feat.shape) == (n, 32)
+        assert "feat" not in want and "corner_vals" not in want, "given_feat: feat / corner_vals come from the pre-pass"
+        _need_cuda(given_feat)
+        s.given_feat = _ptr(given_feat); keep.append(given_feat)
     out = {}
     o = _lib.FieldOut()
     if "sigma" in want:

@@ -94,14 +94,24 @@ class _RenderFunction(torch.autograd.Function):
         deform = model.config.use_deformation_field
         kw = dict(origins=origins, directions=directions, ray_times=ray_times, t_starts=starts, t_ends=ends,
                   ray_indices=ray_indices)
-        want = ("sigma", "rgb", "feat", "xs") + (("offsets", "deform_acts", "corner_vals") if deform else ())
-        f = ops.field_forward(P, window_hash=wh, window_deform=wd, use_deformation=deform, want=want, **kw,
-                              **model._blend_opts())
+        reuse = getattr(model, "_prepass_payload", None)       # (feat, corner_vals) of exactly these samples, or None
+        model._prepass_payload = None
+        if reuse is not None and reuse[0].shape[0] == starts.shape[0]:
+            want = ("sigma", "rgb", "xs") + (("offsets", "deform_acts") if deform else ())
+            f = ops.field_forward(P, window_hash=wh, window_deform=wd, use_deformation=deform, want=want, given_feat=reuse[0],
+                                  **kw, **model._blend_opts())
+            f["feat"], f["corner_vals"] = reuse
+        else:
+            want = ("sigma", "rgb", "feat", "xs") + (("offsets", "deform_acts", "corner_vals") if deform else ())
+            f = ops.field_forward(P, window_hash=wh, window_deform=wd, use_deformation=deform, want=want, **kw,
+                                  **model._blend_opts())
         c = ops.composite(packed_info, starts, ends, f["sigma"], f["rgb"], f["offsets"] if deform else None, training=True)
         ctx.model, ctx.P, ctx.kw, ctx.wh, ctx.wd, ctx.deform = model, P, kw, wh, wd, deform
         ctx.saved = {k: f[k] for k in ("feat", "xs", "sigma", "rgb")}
         if deform:
             ctx.saved.update(deform_acts=f["deform_acts"], deform_enc=f["deform_enc"], corner_vals=f["corner_vals"])
+        elif "corner_vals" in f:
+            ctx.saved.update(corner_vals=f["corner_vals"])
         ctx.packed_info, ctx.workspace = packed_info, c["workspace"]
         outs = (c["rgb"], c["accumulation"], c["depth"], c["weights"])
         if deform:
@@ -185,6 +195,8 @@ class NeRSembleNGPModel(Model):
         self.lpips = None                # optional callable(image[1,3,H,W], rgb[1,3,H,W]) -> scalar (needs pretrained weights)
         self.use_fused_render = True     # eval renders: sampler -> field -> composite fused, no host sync (ops.render_rays)
         self.use_fused_sampler = True    # training: march / density pre-pass / visibility / packing with one host sync
+        self.prepass_reuse = True        # ... and the pre-pass's blended features / corner values are packed with the kept
+                                         # samples, so the differentiable forward does not gather the tables a second time
 
     def populate_modules(self):
         """models/nersemble_instant_ngp.py:81-179 (+ BaseModel.populate_modules, base.py:38-47)."""
@@ -325,7 +337,7 @@ class NeRSembleNGPModel(Model):
                                step=cfg.render_step_size, cone_angle=cfg.cone_angle, **self._blend_opts())
 
     @torch.no_grad()
-    def _sample_packed(self, ray_bundle: RayBundle, jitter: Optional[Tensor]):
+    def _sample_packed(self, ray_bundle: RayBundle, jitter: Optional[Tensor], want_payload: bool = False):
         """The sampler call of get_outputs (models/nersemble_instant_ngp.py:283-291) through
         NeRSembleVolumetricSampler.sample_packed: (RaySamples, ray_indices, packed_info) with one host synchronisation."""
         from ..nerfstudio_shim import Frustums
@@ -339,10 +351,12 @@ class NeRSembleNGPModel(Model):
             """field_density_fn (:235-266) on the candidates' midpoints, sample count read on the device."""
             if cfg.disable_occupancy_grid:
                 return torch.ones((cand["capacity"],), dtype=torch.float32, device=o.device), None
+            reuse = self.prepass_reuse and want_payload
             f = ops.field_forward(self.native_params(), window_hash=wh, window_deform=wd, use_deformation=cfg.use_deformation_field,
                                   origins=o, directions=d, ray_times=ray_times, t_starts=cand["t_starts"], t_ends=cand["t_ends"],
-                                  ray_indices=cand["ray_indices"], n_samples_dev=cand["n_total"], want=("sigma",), **self._blend_opts())
-            return f["sigma"], None
+                                  ray_indices=cand["ray_indices"], n_samples_dev=cand["n_total"],
+                                  want=("sigma", "feat", "corner_vals") if reuse else ("sigma",), **self._blend_opts())
+            return f["sigma"], ({"feat": f["feat"], "corner_vals": f["corner_vals"]} if reuse else None)
 
         s = self.sampler.sample_packed(ray_bundle, render_step_size=cfg.render_step_size, near_plane=cfg.near_plane,
                                        far_plane=cfg.far_plane, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
@@ -355,6 +369,7 @@ class NeRSembleNGPModel(Model):
                                  camera_indices=None if ci is None else ci.reshape(-1, ci.shape[-1])[ri])
         if ray_bundle.times is not None:
             ray_samples.times = ray_bundle.times.reshape(-1, 1)[ri]
+        self._prepass_payload = (s["feat"], s["corner_vals"]) if "feat" in s else None
         return ray_samples, ri, s["packed_info"]
 
     def _fused_ok(self) -> bool:
@@ -409,7 +424,7 @@ class NeRSembleNGPModel(Model):
                 return outputs
             # no sample at all: the reference inserts one fake sample (nersemble_volumetric_sampler.py:110-114) -> general path
         if self.use_fused_sampler and self.scene_aabb.is_cuda:
-            ray_samples, ray_indices, packed_info = self._sample_packed(ray_bundle, jitter)
+            ray_samples, ray_indices, packed_info = self._sample_packed(ray_bundle, jitter, want_payload=needs_grad)
         else:
             with torch.no_grad():
                 ray_samples, ray_indices = self.sampler(

@@ -169,8 +169,9 @@ def test_sync_free_training_sampler_matches_the_four_sync_path(trained):
                    camera_indices=torch.zeros(R, 1, dtype=torch.long, device=DEV), times=t[:, None] if t.dim() == 1 else t)
     jit = torch.rand(R, generator=torch.Generator().manual_seed(1)).to(DEV)
     res = {}
-    for fused in (True, False):
-        m.use_fused_sampler = fused
+    for fused in (True, False, "no_reuse"):
+        m.use_fused_sampler = bool(fused)
+        m.prepass_reuse = fused is True          # True: the differentiable forward takes the pre-pass's packed features
         m.zero_grad(set_to_none=True)
         m.field.hash_ensemble.pending_table_grad = None
         out = m.get_outputs(rb, jitter=jit)
@@ -188,6 +189,12 @@ def test_sync_free_training_sampler_matches_the_four_sync_path(trained):
     # gradients: float atomics in the scatter -> rounding-order noise only
     torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-3, atol=1e-6)
     torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-3, atol=1e-7)
+    c = res["no_reuse"][0]          # pre-pass reuse on/off: the same features, so the same forward bit for bit
+    for k in ("rgb", "accumulation", "depth", "deformation"):
+        assert _same(a[k], c[k]), k
+    assert _same(a["weights"][0], c["weights"][0])
+    torch.testing.assert_close(res[True][1], res["no_reuse"][1], rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(res[True][2], res["no_reuse"][2], rtol=1e-3, atol=1e-7)
     # an empty occupancy grid: the zero-sample guard (one fake sample on ray 0) on both paths
     m.occupancy_grid.binaries[:] = False
     with torch.no_grad():
