@@ -402,6 +402,31 @@ typedef struct nsb_vis_compact_args {
 int nsb_visibility_compact(const nsb_vis_compact_args *args, void *stream);
 size_t nsb_vis_compact_workspace_bytes(int64_t n_rays, int64_t capacity);
 
+/* Training-batch assembly on the GPU (data/nersemble_pixel_sampler.py:23-69 + nerfstudio RayGenerator / Cameras
+ * [PERSPECTIVE]): for each sampled pixel (image, y, x) the ray (origin, unit direction, pixel area, time, camera index)
+ * and the supervision values gathered from an image cache resident in device memory.  One launch, no host round trip. */
+typedef struct nsb_ray_batch_args {
+    int64_t n_rays;
+    const int64_t *indices;        /* [n_rays][3] (image, y, x) */
+    int64_t height, width;         /* of every cached image */
+    const int64_t *image_camera;   /* [n_images] camera of each image, or NULL (image == camera) */
+    const float *image_times;      /* [n_images] time in [0,1] of each image, or NULL */
+    const float *intrinsics;       /* [n_cameras][4] fx, fy, cx, cy */
+    const float *camera_to_world;  /* [n_cameras][3][4] row-major */
+    const uint8_t *images;         /* [n_images][H][W][3] or NULL */
+    const uint8_t *alpha_maps;     /* [n_images][H][W]    or NULL */
+    const float *depth_maps;       /* [n_images][H][W]    or NULL */
+    float *origins, *directions;   /* [n_rays][3] out */
+    float *pixel_area;             /* [n_rays] out or NULL */
+    float *directions_norm;        /* [n_rays] out or NULL */
+    float *times;                  /* [n_rays] out or NULL */
+    int64_t *camera_indices;       /* [n_rays] out or NULL */
+    float *out_image;              /* [n_rays][3] in [0,1] out or NULL */
+    float *out_alpha;              /* [n_rays] in 0..255 out or NULL */
+    float *out_depth;              /* [n_rays] out or NULL */
+} nsb_ray_batch_args;
+int nsb_ray_batch(const nsb_ray_batch_args *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,15 @@ class VisCompactArgs(C.Structure):
                 ("corner_vals", C.c_void_p), ("out_corner_vals", C.c_void_p), ("workspace", C.c_void_p)]
 
 
+class RayBatchArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("indices", C.c_void_p), ("height", C.c_int64), ("width", C.c_int64),
+                ("image_camera", C.c_void_p), ("image_times", C.c_void_p), ("intrinsics", C.c_void_p),
+                ("camera_to_world", C.c_void_p), ("images", C.c_void_p), ("alpha_maps", C.c_void_p),
+                ("depth_maps", C.c_void_p), ("origins", C.c_void_p), ("directions", C.c_void_p), ("pixel_area", C.c_void_p),
+                ("directions_norm", C.c_void_p), ("times", C.c_void_p), ("camera_indices", C.c_void_p),
+                ("out_image", C.c_void_p), ("out_alpha", C.c_void_p), ("out_depth", C.c_void_p)]
+
+
 class RenderWsHeader(C.Structure):
     _fields_ = [("barrier", C.c_uint32), ("depth_range", C.c_uint32 * 2), ("status", C.c_int32), ("n_total", C.c_int64),
                 ("reserved", C.c_int64 * 5)]
@@ -165,6 +174,7 @@ SYMBOLS = {
                                  C.c_float, C.c_void_p, C.c_void_p]),
     "nsb_occ_update_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "nsb_render_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "nsb_ray_batch": (C.c_int, [C.POINTER(RayBatchArgs), C.c_void_p]),
     "nsb_march_occupancy_packed": (C.c_int, [C.POINTER(MarchArgs), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsb_visibility_compact": (C.c_int, [C.POINTER(VisCompactArgs), C.c_void_p]),
     "nsb_vis_compact_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),

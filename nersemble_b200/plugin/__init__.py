@@ -12,7 +12,9 @@ from .field import NeRSembleNeRFactoField
 from .sampler import NeRSembleVolumetricSampler, OccGridEstimator
 from .model import NeRSembleNGPModel, NeRSembleNGPModelConfig, BaseModelConfig
 from .occupancy_filter import filter_occupancy_grid
+from .datamanager import DeviceImageCache, DeviceRaySampler, ray_batch
 
 __all__ = ["HashEnsemble", "HashEnsembleConfig", "SE3DeformationField", "SE3DeformationFieldConfig",
            "TCNNHashEncodingConfig", "GenericScheduler", "NeRSembleNeRFactoField", "NeRSembleVolumetricSampler",
-           "OccGridEstimator", "NeRSembleNGPModel", "NeRSembleNGPModelConfig", "BaseModelConfig", "filter_occupancy_grid"]
+           "OccGridEstimator", "NeRSembleNGPModel", "NeRSembleNGPModelConfig", "BaseModelConfig", "filter_occupancy_grid",
+           "DeviceImageCache", "DeviceRaySampler", "ray_batch"]

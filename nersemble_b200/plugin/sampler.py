@@ -110,6 +110,30 @@ class OccGridEstimator(nn.Module):
         ops.occ_update(self.occs, self.binaries, torch.cat(ids), torch.cat(vals), ema_decay, occ_thre)
 
 
+def frustum_cull_grid(normals: Tensor, offsets: Tensor, scene_aabb: Tensor, resolution, min_views: int,
+                      device=None, chunk: int = 1 << 18) -> Tensor:
+    """View-frustum-cull mask of the occupancy grid, built on `device` (model_components/nersemble_volumetric_sampler.py:
+    28-40 over frustum.py:43-53): cell (i, j, k) -- sampled at linspace(aabb_min, aabb_max, res) like upstream -- is kept
+    when at least `min_views` camera frustums contain it; a frustum = 4 half spaces, inside iff n . (p - o) >= 0 for all
+    four (normals are normalised like TorchHalfSpace3D).  normals / offsets: [n_cameras, 4, 3].  Returns bool [rx, ry, rz].
+    The reference evaluates one camera at a time with a [B*4, 1, 3] @ [B*4, 3, 1] bmm; here all cameras of a chunk of
+    points are one einsum on the GPU."""
+    dev = torch.device(device) if device is not None else normals.device
+    n = normals.to(dev, torch.float32)
+    n = n / n.norm(dim=-1, keepdim=True)
+    o = offsets.to(dev, torch.float32)
+    res = [int(r) for r in (resolution.tolist() if torch.is_tensor(resolution) else ([resolution] * 3 if isinstance(resolution, int) else resolution))]
+    ab = scene_aabb.to(dev, torch.float32).reshape(2, 3)
+    gx, gy, gz = torch.meshgrid(*[torch.linspace(float(ab[0][k]), float(ab[1][k]), steps=res[k], device=dev) for k in range(3)], indexing="ij")
+    pts = torch.stack([gx, gy, gz], dim=-1).view(-1, 3)
+    d_const = (n * o).sum(-1)                                   # n . o  [C, 4]
+    out = torch.empty((pts.shape[0],), dtype=torch.bool, device=dev)
+    for i in range(0, pts.shape[0], chunk):
+        sd = torch.einsum("bk,cfk->bcf", pts[i:i + chunk], n) - d_const[None]        # n . p - n . o
+        out[i:i + chunk] = (sd >= 0).all(dim=-1).sum(dim=-1) >= min_views
+    return out.view(*res)
+
+
 class NeRSembleVolumetricSampler(nn.Module):
     """model_components/nersemble_volumetric_sampler.py:13-135."""
 
@@ -121,7 +145,12 @@ class NeRSembleVolumetricSampler(nn.Module):
         self.occupancy_grid = occupancy_grid
         self.camera_frustums = camera_frustums
         self.view_frustum_culling = view_frustum_culling
-        if camera_frustums is not None and view_frustum_culling is not None:
+        if camera_frustums is not None and view_frustum_culling is not None and isinstance(camera_frustums, (tuple, dict)):
+            # raw half-space arrays (normals [C,4,3], offsets [C,4,3]): the mask is built on the grid's device
+            nrm, off = (camera_frustums["normals"], camera_frustums["offsets"]) if isinstance(camera_frustums, dict) else camera_frustums
+            self.camera_frustum_grid = frustum_cull_grid(nrm, off, scene_aabb, self.occupancy_grid.resolution, view_frustum_culling,
+                                                         device=self.occupancy_grid.occs.device)
+        elif camera_frustums is not None and view_frustum_culling is not None:
             res = self.occupancy_grid.resolution
             gx, gy, gz = torch.meshgrid(torch.linspace(scene_aabb[0][0], scene_aabb[1][0], steps=int(res[0])),
                                         torch.linspace(scene_aabb[0][1], scene_aabb[1][1], steps=int(res[1])),

@@ -186,7 +186,7 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
              "nsb_table_adam_args": _lib.TableAdamArgs, "nsb_loss_args": _lib.LossArgs,
              "nsb_composite_args": _lib.CompositeArgs, "nsb_deform_bwd_args": _lib.DeformBwdArgs,
              "nsb_render_args": _lib.RenderArgs, "nsb_render_ws_header": _lib.RenderWsHeader,
-             "nsb_vis_compact_args": _lib.VisCompactArgs,
+             "nsb_vis_compact_args": _lib.VisCompactArgs, "nsb_ray_batch_args": _lib.RayBatchArgs,
              "nsb_composite_bwd_args": _lib.CompositeBwdArgs, "nsb_march_args": _lib.MarchArgs}
     header = open(os.path.join(ROOT, "include", "nsb.h")).read()
     assert set(re.findall(r"^typedef struct (nsb_\w+)", header, flags=re.M)) == set(pairs)     # every struct is mirrored

@@ -218,3 +218,28 @@ def test_image_metrics_and_update_to_step():
     assert m.sched_window_deform.value == pytest.approx(3.5) and m.sched_window_hash_encodings.value == 1
     m.update_to_step(60000)
     assert m.sched_window_deform.value == 7 and m.sched_window_hash_encodings.value == pytest.approx(16.5)
+
+
+def test_frustum_cull_grid_matches_the_reference_half_space_test():
+    """frustum_cull_grid (einsum over all cameras) against the reference's per-camera definition (frustum.py:43-53:
+    inside iff normal . (p - offset) >= 0 for the four half spaces; nersemble_volumetric_sampler.py:28-40: keep a cell
+    seen by >= view_frustum_culling cameras), restated with numpy loops."""
+    from nersemble_b200.plugin.sampler import frustum_cull_grid
+    g = torch.Generator().manual_seed(2)
+    C = 6
+    eye = torch.randn(C, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 6.0])
+    normals = torch.randn(C, 4, 3, generator=g) * 0.3 + torch.tensor([[[1.0, 0, -0.4]], [[-1.0, 0, -0.4]], [[0, 1.0, -0.4]], [[0, -1.0, -0.4]]]).reshape(1, 4, 3)
+    offsets = eye[:, None, :].expand(C, 4, 3).contiguous()
+    res = 12
+    got = frustum_cull_grid(normals, offsets, AABB, res, min_views=3)
+    n = (normals / normals.norm(dim=-1, keepdim=True)).numpy(); o = offsets.numpy()
+    ax = [np.linspace(float(AABB[0][k]), float(AABB[1][k]), res, dtype=np.float32) for k in range(3)]
+    want = np.zeros((res, res, res), bool)
+    for i in range(res):
+        for j in range(res):
+            for k in range(res):
+                p = np.array([ax[0][i], ax[1][j], ax[2][k]], np.float32)
+                views = sum(all(float(n[c, f] @ (p - o[c, f])) >= 0 for f in range(4)) for c in range(C))
+                want[i, j, k] = views >= 3
+    assert 0 < want.sum() < want.size
+    assert (got.numpy() != want).sum() <= 2          # a point exactly on a plane may flip with the summation order
