@@ -91,7 +91,7 @@ def overlap_table_allreduce(hash_ensemble, average: bool = True) -> None:
 _BIG = 1 << 24   # elements: tensors this large are reduced in place, not copied into the flat bucket
 
 
-def allreduce_gradients(params, average: bool = True, hash_ensembles=()) -> None:
+def allreduce_gradients(params, average: bool = True, hash_ensembles=(), reduce_pending: bool = True) -> None:
     """The training collective: gradients summed over ranks once per step, then divided by the world size.
     Small gradients (MLPs, embeddings) travel in ONE flat bucket; the table gradient (1.6 GB dense) is reduced in place
     -- copying it into a bucket and back costs three extra passes over it.  With the fused optimiser
@@ -104,7 +104,8 @@ def allreduce_gradients(params, average: bool = True, hash_ensembles=()) -> None
         return
     world = dist.get_world_size()
     for he in hash_ensembles:
-        allreduce_pending(he, average)
+        if reduce_pending:               # False: FusedFieldsAdam(shard_tables=True) reduce-scatters the parked gradient itself
+            allreduce_pending(he, average)
     params = [p for p in params if p.requires_grad]
     deferred = {id(he.tables) for he in hash_ensembles if he.pending_table_grad is not None}
     params = [p for p in params if id(p) not in deferred]

@@ -47,6 +47,7 @@ class FusedFieldsAdam(torch.optim.Adam):
         # extra factor on the parked gradient for trainers that scale the loss WITHOUT a GradScaler (1 / their scale)
         self.pending_grad_scale = 1.0
         self.auto_allreduce = True
+        self.shard_tables = False          # N > 1: reduce-scatter -> Adam on 1/N of the entries -> all-gather of the fp16 table
         self.last_step_skipped = False
         self._ensembles = []
         for group in self.param_groups:
@@ -64,6 +65,61 @@ class FusedFieldsAdam(torch.optim.Adam):
         for he, _, _ in self._ensembles:
             he.pending_table_grad = None
 
+    # ------------------------------------------------------------------ sharded table optimiser
+    @staticmethod
+    def _can_shard(he, p) -> bool:
+        import torch.distributed as dist
+        pend = he.pending_table_grad
+        return (pend is not None and not pend.get("reduced") and pend.get("slots_are_timesteps") and p.grad is None
+                and p.shape[0] % dist.get_world_size() == 0)
+
+    def _sharded_table_step(self, he, p, st, shadow, pending, gscale, kw) -> None:
+        """Reduce-scatter -> Adam on this rank's 1/N of the table entries -> all-gather of the fp16 table.
+        The parked gradient [slots][E][2] is reduce-scattered along the ENTRY axis slot by slot (one coalesced NCCL
+        group), which leaves [slots][E/N][2] -- exactly the workspace nsb_table_adam_step takes for the contiguous
+        entry range [rank E/N, (rank+1) E/N) of the master / moment / fp16 tensors.  Per step and rank: (N-1)/N x 1.2 GB
+        reduced + (N-1)/N x 0.8 GB gathered instead of 2 (N-1)/N x 1.2 GB all-reduced, and the 11.7 GB streaming pass of
+        the optimiser shrinks to 1/N.  The forward only reads the fp16 table, which is complete on every rank; the fp32
+        master and the Adam moments are current on their owner only -- call consolidate() on ALL ranks before a
+        state_dict() / checkpoint."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        E = p.shape[0]
+        n = E // world
+        lo = rank * n
+        g = pending["g_rank1"]
+        T = int(g.shape[0])
+        out = torch.empty((T, n, 2), dtype=g.dtype, device=g.device)
+        if g.is_cuda:
+            with dist._coalescing_manager(device=g.device, async_ops=False):
+                for t in range(T):
+                    dist.reduce_scatter_tensor(out[t], g[t], op=dist.ReduceOp.SUM)
+        else:                                            # gloo (CPU tests of this logic) has no reduce_scatter
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            out.copy_(g[:, lo:lo + n])
+        local = {"g_rank1": out, "cw_slots": pending["cw_slots"], "n_slots": T}
+        ops.table_adam_step(p.data[lo:lo + n], st["exp_avg"][lo:lo + n], st["exp_avg_sq"][lo:lo + n], shadow[lo:lo + n],
+                            pending=local, grad_scale=gscale / world, **kw)
+        mine = shadow[lo:lo + n].clone()                 # 1/N of 0.8 GB: all_gather_into_tensor wants a separate input
+        dist.all_gather_into_tensor(shadow.view(-1), mine.view(-1))
+        self._sharded = True
+
+    @torch.no_grad()
+    def consolidate(self) -> None:
+        """All ranks: gather the owners' fp32 master entries and Adam moments so that every replica (and a checkpoint
+        written by rank 0) holds the full, current tensors.  No-op unless the sharded table step ran."""
+        import torch.distributed as dist
+        if not getattr(self, "_sharded", False) or not (dist.is_available() and dist.is_initialized()):
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        for he, p, _ in self._ensembles:
+            st = self.state.get(p, {})
+            n = p.shape[0] // world
+            for t in (p.data, st.get("exp_avg"), st.get("exp_avg_sq")):
+                if t is not None:
+                    dist.all_gather_into_tensor(t.view(-1), t[rank * n:(rank + 1) * n].clone().view(-1))
+        self._sharded = False
+
     def _amp_state(self):
         """(skip, inv_scale) from the attributes GradScaler.step() sets on optimisers that support amp scaling."""
         gs, fi = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
@@ -80,10 +136,15 @@ class FusedFieldsAdam(torch.optim.Adam):
     @torch.no_grad()
     def step(self, closure=None):
         import torch.distributed as dist
-        if self.auto_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        sharded = set()
+        if multi:
             from .distributed import allreduce_pending
-            for he, _, _ in self._ensembles:
-                allreduce_pending(he, average=True)      # also waits for an overlapped reduction
+            for he, p, _ in self._ensembles:
+                if self.shard_tables and self._can_shard(he, p):
+                    sharded.add(id(p))                   # reduced inside the sharded step below
+                elif self.auto_allreduce:
+                    allreduce_pending(he, average=True)  # also waits for an overlapped reduction
         skip, inv_scale = self._amp_state()
         self.last_step_skipped = skip
         if skip:
@@ -115,8 +176,6 @@ class FusedFieldsAdam(torch.optim.Adam):
         for he, p, group, dense, pending in work:
             if dense is None and pending is None:
                 continue
-            if not p.is_cuda:
-                raise RuntimeError("FusedFieldsAdam needs the table on a CUDA device (there is no CPU fallback)")
             st = self.state[p]
             if len(st) == 0:
                 st["step"] = torch.tensor(0.0)
@@ -125,9 +184,12 @@ class FusedFieldsAdam(torch.optim.Adam):
             st["step"] += 1
             shadow = he.shadow_buffer()
             gscale = 1.0 if pending is None else float(pending.get("scale", 1.0)) * float(self.pending_grad_scale) * inv_scale
-            ops.table_adam_step(p.data, st["exp_avg"], st["exp_avg_sq"], shadow, step=int(st["step"].item()),
-                                lr=float(group["lr"]), betas=group["betas"], eps=group["eps"],
-                                weight_decay=group["weight_decay"], grad=dense, pending=pending, grad_scale=gscale)
+            kw = dict(step=int(st["step"].item()), lr=float(group["lr"]), betas=group["betas"], eps=group["eps"],
+                      weight_decay=group["weight_decay"])
+            if id(p) in sharded:
+                self._sharded_table_step(he, p, st, shadow, pending, gscale, kw)
+            else:
+                ops.table_adam_step(p.data, st["exp_avg"], st["exp_avg_sq"], shadow, grad=dense, pending=pending, grad_scale=gscale, **kw)
             torch.autograd.graph.increment_version(p)
             he.set_native_tables(shadow)
             he.pending_table_grad = None

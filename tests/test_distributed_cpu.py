@@ -111,3 +111,61 @@ def test_overlapped_table_gradient_allreduce_hook():
     allreduce_gradients / optimiser step only waits for it."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_overlap_worker, args=(2, port), nprocs=2, join=True)
+
+
+def _shard_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nersemble_b200 import ops
+    from nersemble_b200.optim import FusedFieldsAdam
+    E, T = 12, 3
+    calls = []
+
+    def fake_step(tables, m, v, shadow, *, step, lr, betas, eps, weight_decay, grad=None, pending=None, grad_scale=1.0):
+        """plain SGD stand-in with the kernel's interface: p -= lr * scale * sum_slots cw x g (what the shard must see)"""
+        g = torch.einsum("sm,sef->emf", pending["cw_slots"], pending["g_rank1"]) * grad_scale
+        tables -= lr * g
+        shadow.copy_(tables.half())
+        calls.append((tuple(tables.shape), float(grad_scale)))
+    ops.table_adam_step = fake_step
+
+    class FakeEnsemble:
+        def __init__(self):
+            self.tables = torch.nn.Parameter(torch.zeros(E, 32, 2))
+            self.defer_table_grad = False
+            self.pending_table_grad = None
+            self._shadow = torch.zeros(E, 32, 2, dtype=torch.float16)
+        def shadow_buffer(self): return self._shadow
+        def set_native_tables(self, s): self.native = s
+        def materialize_pending(self, scale=1.0): raise AssertionError("dense path must not run")
+    he = FakeEnsemble()
+    import weakref
+    he.tables._nsb_hash_ensemble = weakref.ref(he)
+    opt = FusedFieldsAdam([he.tables], lr=1.0)
+    opt.shard_tables = True
+    gen = torch.Generator().manual_seed(0)
+    g_all = [torch.randn(T, E, 2, generator=gen) for _ in range(world)]           # every rank knows every rank's gradient
+    cw = torch.rand(T, 32, generator=gen)
+    he.pending_table_grad = {"g_rank1": g_all[rank].clone(), "cw_slots": cw, "n_slots": T, "slots_are_timesteps": True}
+    with torch.no_grad():
+        opt.step()
+    want = -torch.einsum("sm,sef->emf", cw, sum(g_all) / world)                   # averaged gradient, lr = 1
+    n = E // world
+    assert calls == [((n, 32, 2), 1.0 / world)]                                   # the kernel saw only this rank's entries
+    # fp16 table: complete on every rank; fp32 master: the owner's range only, until consolidate()
+    torch.testing.assert_close(he._shadow.float(), want, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(he.tables.detach()[rank * n:(rank + 1) * n], want[rank * n:(rank + 1) * n], rtol=1e-6, atol=1e-6)
+    other = 1 - rank
+    assert torch.equal(he.tables.detach()[other * n:(other + 1) * n], torch.zeros(n, 32, 2))
+    opt.consolidate()
+    torch.testing.assert_close(he.tables.detach(), want, rtol=1e-6, atol=1e-6)
+    assert he.pending_table_grad is None
+    dist.destroy_process_group()
+
+
+def test_sharded_table_optimiser_reduce_scatter_step_all_gather():
+    """world_size 2, gloo: FusedFieldsAdam(shard_tables=True) hands the kernel only this rank's 1/N of the entries with
+    the reduced gradient, all-gathers the fp16 table, and consolidate() completes the fp32 master."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_shard_worker, args=(2, port), nprocs=2, join=True)

@@ -42,7 +42,7 @@ def _train_batch(dev, seed):
             "depth_maps": ((torch.rand(B.RAYS, generator=g) * 4 + 7) * (torch.rand(B.RAYS, generator=g) > 0.2)).to(dev)}
 
 
-def _train_loop(args, D, model, opts, params, batch, rb, with_allreduce):
+def _train_loop(args, D, model, opts, params, batch, rb, with_allreduce, reduce_pending=True):
     """W warm-up + K timed optimiser steps; per-phase CUDA-event times of the timed steps (ms, this rank)."""
     import torch
     from nersemble_b200.distributed import allreduce_gradients
@@ -63,7 +63,7 @@ def _train_loop(args, D, model, opts, params, batch, rb, with_allreduce):
         loss = sum(model.get_loss_dict(out, batch).values()); e.append(ev()); h.append(time.perf_counter())
         loss.backward(); e.append(ev()); h.append(time.perf_counter())
         if with_allreduce:
-            allreduce_gradients(params, hash_ensembles=HE)
+            allreduce_gradients(params, hash_ensembles=HE, reduce_pending=reduce_pending)
         e.append(ev()); h.append(time.perf_counter())
         for o in opts:
             o.step()
@@ -112,6 +112,8 @@ def run_config3(args, config5=False):
         model.occupancy_grid.binaries[0] = occ.to(dev)
         model.occupancy_grid.occs.copy_((occ.flatten().float() * 0.05).to(dev))
     opts, params = _optimizers(model)
+    shard = world > 1 and not args.no_shard and not args.overlap
+    opts[0].shard_tables = shard              # reduce-scatter -> Adam on 1/N of the entries -> all-gather of the fp16 table
     if world > 1 and args.overlap:
         from nersemble_b200.distributed import overlap_table_allreduce
         overlap_table_allreduce(model.field.hash_ensemble)        # table-gradient all-reduce overlaps the deformation backward
@@ -119,7 +121,8 @@ def run_config3(args, config5=False):
     rb = RayBundle(origins=o, directions=d, pixel_area=torch.ones(B.RAYS, 1, device=dev),
                    camera_indices=torch.zeros(B.RAYS, 1, dtype=torch.long, device=dev), times=t)
     batch = _train_batch(dev, 7 + rank)
-    ms, n_samples, phases, loss, sampler = _train_loop(args, D, model, opts, params, batch, rb, with_allreduce=world > 1)
+    ms, n_samples, phases, loss, sampler = _train_loop(args, D, model, opts, params, batch, rb, with_allreduce=world > 1,
+                                                       reduce_pending=not shard)
     (ms,) = D.max_ms(ms)
     (tot_samples,) = D.sum(float(n_samples))
     host = phases.pop("host_enqueue")
@@ -133,7 +136,9 @@ def run_config3(args, config5=False):
                 "it_per_s": K / (ms / 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 tables/MLP operands, f32 accumulate / master / Adam", "data": "synthetic",
                 "config": {"workload": name, "rays_per_gpu": B.RAYS, "samples_per_step_per_gpu": n_samples / K,
-                           "parallelism": (f"data parallel x{world}: NCCL all-reduce of the gradients every step inside the timed region"
+                           "parallelism": (f"data parallel x{world}: NCCL "
+                                           + ("reduce-scatter of the table gradient -> Adam on 1/N of the entries -> all-gather of the fp16 table; all-reduce of the MLP / embedding gradients"
+                                              if shard else "all-reduce of all gradients") + ", every step inside the timed region"
                                            + ("; the 1.2 GB table-gradient reduction is issued on a side stream during the backward" if args.overlap else "")
                                            if world > 1 else "single GPU"),
                            "tables": "32 x (16 levels, 2^19) fp32 master + fp16 shadow", "n_timesteps": B.N_TIMESTEPS},
