@@ -569,6 +569,7 @@ def main():
     ap.add_argument("--config", default="2", choices=["2", "2occ", "3", "4", "5"])
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ab", action="store_true", help="config 5, N > 1: also time all-reduce + full step vs the sharded optimiser in the same process")
     ap.add_argument("--no-shard", action="store_true", help="config 5: all-reduce the table gradient and step the full table on every rank")
     ap.add_argument("--overlap", action="store_true", help="config 5: issue the table-gradient all-reduce on a side stream as soon as the "
                     "gradient is parked (measured SLOWER on 2 x B200: 30.8 vs 22.9 ms per step, see DESIGN.md section 6)")

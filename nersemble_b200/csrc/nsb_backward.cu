@@ -500,6 +500,9 @@ constexpr int kExpWarps = 4, kExpLines = 32;
 // Block form (same as table_step_kernel, nsb_optim.cu): a warp owns 32 consecutive lines per iteration, reads every
 // slot's 2-vectors of those lines with one coalesced 256 B load per slot into a shared-memory panel, and then visits
 // only the lines some slot touched (lane = member; the fp16 table line is one coalesced 128 B read, four lines in flight).
+// TABLES = false (fused optimiser: the dense table gradient is never materialised): only the time-code gradient
+// is computed -- the member expansion's two FMAs per (line, slot) are compiled out.
+template <bool TABLES>
 __global__ void __launch_bounds__(kExpWarps * 32) hash_expand_kernel(const __grid_constant__ FieldBwdKArgs K, size_t total_entries) {
     __shared__ float cw_s[kMaxSlots][NSB_MEMBERS];
     __shared__ int slot_ts[kMaxSlots];
@@ -578,11 +581,13 @@ __global__ void __launch_bounds__(kExpWarps * 32) hash_expand_kernel(const __gri
                 for (int sl = 0; sl < kMaxSlots; ++sl) {
                     if (!((any_slot >> sl) & 1)) continue;     // warp-uniform
                     const float2 gv = gs[warp][sl][js[u]];
-                    a0 = fmaf(cw[sl], gv.x, a0);
-                    a1 = fmaf(cw[sl], gv.y, a1);
+                    if (TABLES) {
+                        a0 = fmaf(cw[sl], gv.x, a0);
+                        a1 = fmaf(cw[sl], gv.y, a1);
+                    }
                     dcode[sl] = fmaf(vs[u].x, gv.x, fmaf(vs[u].y, gv.y, dcode[sl]));
                 }
-                if (K.B.d_tables) {
+                if (TABLES && K.B.d_tables) {
                     float2 *dst = reinterpret_cast<float2 *>(K.B.d_tables + ((size_t)(e0 + js[u]) * NSB_MEMBERS + lane) * 2);
                     float2 cur = *dst;
                     cur.x += a0; cur.y += a1;
@@ -683,7 +688,8 @@ extern "C" int nsb_field_backward(const nsb_field_params *params, const nsb_fiel
         if (rc) return rc;
         if (args->g_rank1 && (args->d_tables || args->d_blend_codes || args->cw_slots_out)) {
             const size_t total = (size_t)params->levels.offset[NSB_MAX_LEVELS - 1] + params->levels.entries[NSB_MAX_LEVELS - 1];
-            hash_expand_kernel<<<g_bwd_sms * 6, kExpWarps * 32, 0, st>>>(K, total);
+            if (K.B.d_tables) hash_expand_kernel<true><<<g_bwd_sms * 6, kExpWarps * 32, 0, st>>>(K, total);
+            else hash_expand_kernel<false><<<g_bwd_sms * 6, kExpWarps * 32, 0, st>>>(K, total);
             rc = check_launch("hash_expand_kernel");
         }
     }

@@ -121,6 +121,19 @@ def run_config3(args, config5=False):
     rb = RayBundle(origins=o, directions=d, pixel_area=torch.ones(B.RAYS, 1, device=dev),
                    camera_indices=torch.zeros(B.RAYS, 1, dtype=torch.long, device=dev), times=t)
     batch = _train_batch(dev, 7 + rank)
+    variants = {}
+    if world > 1 and args.ab:
+        # in-process A/B (box-to-box variance of the host side is larger than the effect): blocking all-reduce + full
+        # table step on every rank, then the sharded optimiser; both on the same model state, same batches
+        for tag, sh in (("allreduce_full_step", False), ("sharded_optimiser", True)):
+            opts[0].shard_tables = sh
+            if not sh:
+                opts[0].consolidate()
+            v_ms, v_n, v_ph, _, _ = _train_loop(args, D, model, opts, params, batch, rb, with_allreduce=True, reduce_pending=not sh)
+            v_ph.pop("host_enqueue")
+            (v_ms,) = D.max_ms(v_ms)
+            variants[tag] = {"ms_per_step": v_ms / K, "phases_ms": dict(zip(v_ph.keys(), D.max_ms(*v_ph.values())))}
+        opts[0].shard_tables = shard
     ms, n_samples, phases, loss, sampler = _train_loop(args, D, model, opts, params, batch, rb, with_allreduce=world > 1,
                                                        reduce_pending=not shard)
     (ms,) = D.max_ms(ms)
@@ -144,6 +157,8 @@ def run_config3(args, config5=False):
                            "tables": "32 x (16 levels, 2^19) fp32 master + fp16 shadow", "n_timesteps": B.N_TIMESTEPS},
                 "phases_ms": dict(zip(phases.keys(), ph)), "host_enqueue_ms": host, "loss": loss, "clocks": sampler.summary(),
                 "gpu_launches": None}
+        if variants:
+            line["ab_same_process"] = variants
         print(json.dumps(line), flush=True)
     D.close()
 
