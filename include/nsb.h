@@ -66,6 +66,11 @@ typedef struct nsb_field_params {
     const float *deform_code_bias;  /* float [n_timesteps][2][128]: W_code(layer 0|4) . warp_code[t] + bias, fp32: the
                                        warp code only depends on the timestep, so its columns cost no tensor work
                                        (-26 % MACs).  Per-sample warp codes (component API): nsb_samples.sample_code_bias. */
+    const void *deform_packed_umma; /* optional: the same deformation weights as tcgen05 B operands -- 14 blocks per tile in
+                                       order of use (L0 | L1 x2 | L2 x2 | L3 x2 | L4 hidden x2, posenc | L5 x2 | heads x2), each
+                                       [128 outputs x 64 inputs] fp16 (heads [16 x 64]) in K-major 8 x 16-byte core matrices
+                                       (python: pack_deform_umma; nsb_deform_packed_umma_bytes()).  When set, the inference
+                                       kernels run the deformation MLP on tcgen05.mma with the accumulator in TMEM. */
     const void *field_packed;  /* fp16 mlp_base + mlp_head weights in MMA-B fragment order */
     const void *warp_codes;    /* __half [n_timesteps][128]  (time_embedding_deformation) */
     const float *blend_codes;  /* float  [n_timesteps][32]   (time_embedding) */
@@ -133,6 +138,7 @@ const char *nsb_last_error(void);
 
 /* Sizes (bytes) of the packed weight buffers the python packer must produce. */
 size_t nsb_deform_packed_bytes(void);
+size_t nsb_deform_packed_umma_bytes(void);
 size_t nsb_field_packed_bytes(void);
 
 /* Fused per-sample field evaluation (deformation MLP -> SE(3) warp -> 32-member hash ensemble

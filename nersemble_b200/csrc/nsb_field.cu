@@ -20,6 +20,7 @@
 #include "nsb_gather.cuh"
 #include "nsb_march.cuh"
 #include "nsb_mlp.cuh"
+#include "nsb_tc.cuh"
 
 namespace nsb {
 
@@ -133,6 +134,7 @@ struct alignas(128) SmemWS {
     uint64_t feat_full[2];
     int tile_ctr[2];
     int64_t n_dyn;                          // fused render kernel: the packed sample count (known on the device only)
+    uint64_t sampler_done;                  // fused render kernel: mbarrier, the tensor warps' sampler phase -> the gather warps
     alignas(16) float xs[2][NSB_TILE][4];  // normalised warped position (0 outside the box), w = timestep bits
     alignas(16) __half feat[2][NSB_TILE * kFeatStride];
     TensorScratch ts[kTensorWarps];
@@ -344,6 +346,75 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_given(const
 #undef NSB_N_SAMPLES
 }
 
+// ===========================================================================================
+// tcgen05 variant of the inference kernels: the deformation MLP on the 5th-generation tensor cores (TMEM accumulator,
+// one issuing thread, weights read from shared memory once per 128-row tile) -- nsb_field_tensor_role_tc.inc.
+// The gather role is the unchanged include; only the tensor role and the shared-memory plan differ.
+// ===========================================================================================
+constexpr int kTcStages = 4, kTcBlocksPerTile = 14, kTcTmemCols = 128;
+constexpr size_t kTcPackedBytes = 12 * 16384 + 2 * 2048;
+
+struct alignas(1024) SmemTC {
+    uint8_t wring[kTcStages][16384];        // weight blocks [128 n x 64 k] (heads: [16 x 64]) in UMMA core-matrix order
+    uint8_t a_enc[16384];                   // posenc A operand [128 rows x 64 k]
+    uint8_t act[32768];                     // hidden activations A operand [128 rows x 128 k]
+    uint4 field_w[kFieldPackedU4];
+    alignas(16) float bias[kBiasFloats];
+    uint64_t full[kTcStages], empty[kTcStages], acc_bar;
+    uint64_t xs_full[2], feat_full[2];
+    uint32_t tmem_base;
+    int tile_ctr[2];
+    int64_t n_dyn;
+    uint64_t sampler_done;
+    alignas(16) float xs[2][NSB_TILE][4];
+    alignas(16) __half feat[2][NSB_TILE * kFeatStride];
+    alignas(16) float dirsel[2][NSB_TILE][4];
+    uint2 blend_b[kGatherWarps][4 * 32];
+    uint4 cv_stage[kGatherWarps][1];        // SAVE is never instantiated with the tc role; the gather include names it
+};
+static_assert(sizeof(SmemTC) <= 227 * 1024, "shared memory plan");
+
+// setup shared by the tc kernels (textual for the same reason as the other role bodies)
+#define NSB_TC_SETUP()                                                                                              \
+    {                                                                                                               \
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.P.field_packed);                                      \
+        for (int i = tid; i < kFieldPackedU4; i += kThreadsWS) sm.field_w[i] = __ldg(src + i);                     \
+        for (int i = tid; i < kBiasFloats; i += kThreadsWS) sm.bias[i] = __ldg(A.P.deform_bias + i);               \
+        for (int i = tid; i < 16384 / 16; i += kThreadsWS) reinterpret_cast<uint4 *>(sm.a_enc)[i] = make_uint4(0u, 0u, 0u, 0u); \
+        if (tid == 0) {                                                                                             \
+            for (int s = 0; s < kTcStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }         \
+            mbar_init(&sm.acc_bar, 1);                                                                              \
+            for (int b = 0; b < 2; ++b) {                                                                           \
+                mbar_init(&sm.xs_full[b], 4);                                                                       \
+                mbar_init(&sm.feat_full[b], kGatherWarps);                                                          \
+                sm.tile_ctr[b] = 0;                                                                                 \
+            }                                                                                                       \
+            mbar_fence_init();                                                                                      \
+        }                                                                                                           \
+        if (warp == 0) tc::tmem_alloc(&sm.tmem_base, kTcTmemCols);                                                  \
+        tc::fence_before_sync();                                                                                    \
+        __syncthreads();                                                                                            \
+        tc::fence_after_sync();                                                                                     \
+    }
+
+template <bool HEAD>
+__global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_tc(const __grid_constant__ FieldArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemTC &sm = *reinterpret_cast<SmemTC *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FIELD = true, SAVE = false, FEAT_GIVEN = false;
+#define NSB_N_SAMPLES A.S.n_samples
+    NSB_TC_SETUP()
+    if (warp >= kTensorWarps) {
+        if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+#include "nsb_field_gather_role.inc"
+        return;
+    }
+    if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+#include "nsb_field_tensor_role_tc.inc"
+#undef NSB_N_SAMPLES
+}
+
 // field_kernel_ws with the sample count read from DEVICE memory (nsb_samples.n_samples_dev; the sync-free training
 // sampler: the host never learns how many candidates the march produced).  grid = number of SMs; A.S.n_samples is the
 // capacity of the sample arrays.  Same role bodies.
@@ -436,11 +507,11 @@ constexpr int kPhaseThreads = kTensorWarps * 32;
 #endif
 // SAMPLER: 0 fixed-stride march fused; 1 occupancy march fused (count | scan | fill); 2 samples GIVEN: a preceding
 // launch (march_occ_coop_kernel, nsb_render.cu) filled the packed arrays and left the count in the workspace header.
-template <int SAMPLER>
+template <int SAMPLER, class SM = SmemWS>
 __device__ NSB_RK_SAMPLER_ATTR void render_sampler_phase(const RenderKArgs &K) {
     constexpr bool OCC = SAMPLER == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    SmemWS &sm = *reinterpret_cast<SmemWS *>(smem_raw);
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
     const FieldArgs &A = K.F;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;      // tid < kPhaseThreads
     uint32_t *const bar = &K.hdr->barrier;
@@ -450,10 +521,10 @@ __device__ NSB_RK_SAMPLER_ATTR void render_sampler_phase(const RenderKArgs &K) {
         K.hdr->depth_range[1] = 0u;
         if (SAMPLER != 2) K.hdr->status = 0;
     }
-    if (SAMPLER == 2) {
+    if constexpr (SAMPLER == 2) {
         if (tid == 0) sm.n_dyn = min(__ldcg(&K.hdr->n_total), K.capacity);
         grid_barrier(bar, 1u * gridDim.x);          // depth_range initialised before any CTA composites
-    } else if (!OCC) {
+    } else if constexpr (!OCC) {
         for (int64_t r = (int64_t)blockIdx.x * kTensorWarps + warp; r < R; r += (int64_t)gridDim.x * kTensorWarps) {
             const float t0 = march_fixed_t0(A.S.origins, A.S.directions, A.P.aabb, r, K.near_plane);
             march_fixed_warp(t0, r, K.n_per_ray, K.M.step, K.M.t_starts, K.M.t_ends, K.M.ray_indices, lane);
@@ -558,21 +629,51 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_ws(const __gr
     constexpr bool FIELD = true, HEAD = true, SAVE = false, FEAT_GIVEN = false;
 
 #define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
+    if (tid == 0) mbar_init(&sm.sampler_done, 1);                          // fenced + published by the setup below
 #include "nsb_field_setup.inc"
     if (warp >= kTensorWarps) {
         if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
-        asm volatile("bar.sync 2, %0;" ::"n"(kThreadsWS) : "memory");      // the sampler is done, sm.n_dyn is set
+        mbar_wait<200>(&sm.sampler_done, 0);                               // the sampler is done, sm.n_dyn is set
 #include "nsb_field_gather_role.inc"
         return;
     }
     if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
     render_sampler_phase<SAMPLER>(K);                                      // S (ends with a grid barrier)
-    asm volatile("bar.sync 2, %0;" ::"n"(kThreadsWS) : "memory");
+    // hand-off through an mbarrier rather than a named barrier shared by the two roles: compute-sanitizer synccheck
+    // reports a barrier that warps reach from two different instructions as divergent
+    if (tid == 0) mbar_arrive(&sm.sampler_done);
     {
 #include "nsb_field_tensor_role.inc"
     }
 #undef NSB_N_SAMPLES
     render_composite_phase<SAMPLER>(K);                                    // C
+}
+
+// render_kernel_ws with the deformation MLP on tcgen05 / TMEM (nsb_field_tensor_role_tc.inc); SAMPLER 0 or 2
+template <int SAMPLER>
+__global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __grid_constant__ RenderKArgs K) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SmemTC &sm = *reinterpret_cast<SmemTC *>(smem_raw);
+    const FieldArgs &A = K.F;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr bool FIELD = true, HEAD = true, SAVE = false, FEAT_GIVEN = false;
+#define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
+    if (tid == 0) mbar_init(&sm.sampler_done, 1);
+    NSB_TC_SETUP()
+    if (warp >= kTensorWarps) {
+        if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+        mbar_wait<200>(&sm.sampler_done, 0);
+#include "nsb_field_gather_role.inc"
+        return;
+    }
+    if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+    render_sampler_phase<SAMPLER, SmemTC>(K);
+    if (tid == 0) mbar_arrive(&sm.sampler_done);
+    {
+#include "nsb_field_tensor_role_tc.inc"
+    }
+#undef NSB_N_SAMPLES
+    render_composite_phase<SAMPLER>(K);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -667,6 +768,21 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
     return save ? launch_field_ws_<D, F, H, true>(A, st) : launch_field_ws_<D, F, H, false>(A, st);
 }
 
+template <bool H>
+static int launch_field_tc(const FieldArgs &A, cudaStream_t st) {
+    const size_t smem = sizeof(SmemTC);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(field_kernel_tc<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(field_kernel_tc): %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms());
+    field_kernel_tc<H><<<grid, kThreadsWS, smem, st>>>(A);
+    return check_launch("field_kernel_tc");
+}
+
 template <bool D>
 static int launch_field_given(const FieldArgs &A, cudaStream_t st) {
     const size_t smem = sizeof(SmemWS);
@@ -696,6 +812,8 @@ static int launch_field(const FieldArgs &A, cudaStream_t st) {
         set_error("nsb_field_forward: n_samples_dev is supported for the density evaluation (no rgb) only");
         return 1;
     }
+    if (D && F && A.P.deform_packed_umma && !A.S.sample_code_bias && !(A.out.xs || A.out.deform_acts || A.out.deform_enc || A.out.corner_vals || A.out.feat))
+        return launch_field_tc<H>(A, st);       // inference with the deformation MLP on tcgen05 / TMEM
     return launch_field_ws<D, F, H>(A, st);
 }
 
@@ -705,6 +823,7 @@ using namespace nsb;
 
 extern "C" size_t nsb_deform_packed_bytes(void) { return (size_t)kTbNumSlabs * kSlabBytes; }
 extern "C" size_t nsb_field_packed_bytes(void) { return kFieldPackedU4 * sizeof(uint4); }
+extern "C" size_t nsb_deform_packed_umma_bytes(void) { return kTcPackedBytes; }
 
 extern "C" int nsb_field_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                                  const nsb_field_out *out, void *stream) {
@@ -762,8 +881,29 @@ namespace nsb {
 constexpr size_t kRenderHdrBytes = 64, kRenderPartials = 1024;
 static_assert(sizeof(nsb_render_ws_header) == kRenderHdrBytes, "workspace header layout");
 
+template <int SAMPLER>
+static int launch_render_tc(const RenderKArgs &K, cudaStream_t st) {
+    const size_t smem = sizeof(SmemTC);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(render_kernel_tc<SAMPLER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(render_kernel_tc): %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    const int grid = num_sms();
+    if ((size_t)grid > kRenderPartials) { set_error("nsb_render_forward: more SMs than scan partials"); return 1; }
+    cudaError_t e = cudaMemsetAsync(&K.hdr->barrier, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) { set_error("nsb_render_forward: memset: %s", cudaGetErrorString(e)); return 2; }
+    void *kargs[] = {const_cast<RenderKArgs *>(&K)};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(render_kernel_tc<SAMPLER>), dim3(grid), dim3(kThreadsWS), kargs, smem, st);
+    if (e != cudaSuccess) { set_error("render_kernel_tc: %s", cudaGetErrorString(e)); return 2; }
+    return check_launch("render_kernel_tc");
+}
+
 template <bool D, int SAMPLER>
 static int launch_render(const RenderKArgs &K, cudaStream_t st) {
+    if constexpr (D && SAMPLER != 1)
+        if (K.F.P.deform_packed_umma) return launch_render_tc<SAMPLER>(K, st);
     const size_t smem = sizeof(SmemWS);
     static bool configured = false;
     if (!configured) {

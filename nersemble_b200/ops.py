@@ -16,6 +16,11 @@ from . import _lib, packing
 
 _F32 = torch.float32
 
+# Deformation MLP of the inference kernels on tcgen05 / TMEM (NativeParams.build(tcgen05=...) overrides it per instance;
+# NSB_TCGEN05=0/1 in the environment overrides the default).
+import os as _os
+USE_TCGEN05 = _os.environ.get("NSB_TCGEN05", "0") == "1"
+
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
@@ -80,6 +85,7 @@ class NativeParams:
     deform_packed_tb: Optional[torch.Tensor] = None   # half, fragment order, no warp-code columns
     deform_code_w: Optional[list] = None              # (stem_w[0], stem_w[4], stem_b[0], stem_b[4]): per-sample code bias
     deform_code_bias: Optional[torch.Tensor] = None   # float [T, 2, 128]
+    deform_packed_umma: Optional[torch.Tensor] = None # half, tcgen05 core-matrix order (inference kernels; opt-in)
 
     def __post_init__(self):
         self.aabb_list = [float(v) for v in self.aabb.detach().cpu().reshape(-1)]
@@ -94,7 +100,7 @@ class NativeParams:
 
     @staticmethod
     def build(*, tables, time_emb, aabb, levels, base_w=None, head_w=None, deform=None, time_emb_deform=None,
-              device="cuda") -> "NativeParams":
+              device="cuda", tcgen05: Optional[bool] = None) -> "NativeParams":
         """tables: [entries,32,2] (any float dtype); base_w/head_w: lists of [out,in] matrices;
         deform: dict(stem_w, stem_b, r_w, r_b, v_w, v_b) or None."""
         dev = torch.device(device)
@@ -124,6 +130,8 @@ class NativeParams:
         if deform is not None:
             P.deform_packed_tb, P.deform_code_bias, P.deform_packed_t = dtb, dcb, dpt
             P.deform_code_w = [sw[0].detach(), sw[4].detach(), sb[0].detach(), sb[4].detach()]
+            if USE_TCGEN05 if tcgen05 is None else tcgen05:
+                P.deform_packed_umma = packing.pack_deform_umma_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
         P.field_packed_t = fpt
         return P
 
@@ -136,6 +144,7 @@ class NativeParams:
         p.deform_bias = _ptr(self.deform_bias)
         p.deform_packed_tb = _ptr(self.deform_packed_tb)
         p.deform_code_bias = _ptr(self.deform_code_bias)
+        p.deform_packed_umma = _ptr(self.deform_packed_umma)
         p.field_packed = _ptr(self.field_packed)
         p.warp_codes = _ptr(self.warp_codes)
         p.blend_codes = _ptr(self.blend_codes)

@@ -250,6 +250,47 @@ def pack_all_fast(stem_w, r_w, v_w, base_w, head_w):
     return torch.split(packed, sizes)
 
 
+def _umma_block(Wb: torch.Tensor) -> torch.Tensor:
+    """[N, 64] (N % 8 == 0) -> the tcgen05 K-major no-swizzle core-matrix order: 8 x 8 fp16 core matrices (8 rows x 16 B),
+    byte offset = (n / 8) * 1024 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2  (descriptor LBO = 128, SBO = 1024)."""
+    N = Wb.shape[0]
+    assert Wb.shape[1] == 64 and N % 8 == 0
+    return Wb.reshape(N // 8, 8, 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
+
+
+def _pad2(W: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    out = torch.zeros((rows, cols), dtype=W.dtype, device=W.device)
+    out[:W.shape[0], :W.shape[1]] = W
+    return out
+
+
+def pack_deform_umma(stem_w, r_w, v_w) -> torch.Tensor:
+    """Deformation weights for the tcgen05 tensor role (nsb_field_tensor_role_tc.inc): 14 blocks in order of use, each
+    [n x 64 k] in core-matrix order (_umma_block).  K follows the reference's input column order
+    (windowed_nerf_encoding.py:50-73: sin 21 | cos 21 | 2 pi p 3), zero-padded to 64; the 128 warp-code columns of
+    layers 0 and 4 are not here (they enter as the per-timestep code bias, deform_code_bias):
+      L0 [128 x 45->64] | L1, L2, L3 [128 x 64] x 2 each | L4 hidden (reference columns 173..300) x 2, posenc 45->64 |
+      L5 x 2 | heads (rows v0..2, r0..2, zero to 16) x 2.   12 * 16 KB + 2 * 2 KB = 200704 bytes."""
+    W = [_f(w) for w in stem_w]
+    blocks = [_umma_block(_pad2(W[0][:, :45], 128, 64))]
+    for l in (1, 2, 3):
+        blocks += [_umma_block(W[l][:, :64]), _umma_block(W[l][:, 64:128])]
+    h0 = DEFORM_IN_DIM
+    blocks += [_umma_block(W[4][:, h0:h0 + 64]), _umma_block(W[4][:, h0 + 64:h0 + 128]), _umma_block(_pad2(W[4][:, :45], 128, 64))]
+    blocks += [_umma_block(W[5][:, :64]), _umma_block(W[5][:, 64:128])]
+    heads = _pad2(torch.cat([_f(v_w), _f(r_w)], 0), 16, 128)
+    blocks += [_umma_block(heads[:, :64]), _umma_block(heads[:, 64:])]
+    out = torch.cat(blocks)
+    assert out.numel() * 2 == 12 * 16384 + 2 * 2048
+    return out if out.dtype == torch.int64 else out.half().contiguous()
+
+
+def pack_deform_umma_fast(stem_w, r_w, v_w) -> torch.Tensor:
+    dev = stem_w[0].device
+    plan = gather_plan("deform_umma", lambda *w: pack_deform_umma(w[:6], w[6], w[7]), _STEM_SHAPES + [(3, 128), (3, 128)], dev)
+    return apply_plan(plan, list(stem_w) + [r_w, v_w])
+
+
 def _deform_weights(stem_w, r_w, v_w, in_map):
     """The weight part shared by pack_deform (in_map = 176 columns) and pack_deform_tb (48 posenc columns)."""
     ident = list(range(128))

@@ -10,6 +10,6 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throug
 M=$M,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_active
 M=$M,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed
 M=$M,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__inst_executed.sum
-ncu --metrics $M --clock-control none -k regex:"nsb" --launch-skip 120 -c 40 --csv --log-file gpurun_out/r2_train_kernels_cfg$CFG.csv \
+ncu --metrics $M --clock-control none -k regex:"field_kernel|field_mlp_bwd|deform_bwd|deform_dw|hash_bwd|hash_expand|table_step|composite|losses_|march_occ|vis_compact|depth_" --launch-skip 120 -c 40 --csv --log-file gpurun_out/r2_train_kernels_cfg$CFG.csv \
     python tools/train_profile.py $CFG > gpurun_out/r2_train_ncu_cfg$CFG.log 2>&1
 python tools/ncu_summary.py gpurun_out/r2_train_kernels_cfg$CFG.csv

@@ -5,7 +5,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 CS=${CS:-/usr/local/cuda/bin/compute-sanitizer}
-for tool in memcheck racecheck synccheck initcheck; do
+for tool in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
   extra=""
   [ "$tool" = racecheck ] && extra="--racecheck-report all"
   SAN_RAYS=${SAN_RAYS:-96} timeout ${SAN_TIMEOUT:-600} $CS --tool $tool $extra --print-limit 20 \
