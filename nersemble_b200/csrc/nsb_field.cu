@@ -352,6 +352,9 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_given(const
 // The gather role is the unchanged include; only the tensor role and the shared-memory plan differ.
 // ===========================================================================================
 constexpr int kTcStages = 4, kTcBlocksPerTile = 14, kTcTmemCols = 128;
+#ifndef NSB_TC_SPLIT
+#define NSB_TC_SPLIT 1      // deformation (tcgen05) and density / colour MLPs (mma.sync) on separate warp groups
+#endif
 constexpr size_t kTcPackedBytes = 12 * 16384 + 2 * 2048;
 
 struct alignas(1024) SmemTC {
@@ -360,7 +363,7 @@ struct alignas(1024) SmemTC {
     uint8_t act[32768];                     // hidden activations A operand [128 rows x 128 k]
     uint4 field_w[kFieldPackedU4];
     alignas(16) float bias[kBiasFloats];
-    uint64_t full[kTcStages], empty[kTcStages], acc_bar;
+    uint64_t full[kTcStages], empty[kTcStages], acc_bar, f_done[2];
     uint64_t xs_full[2], feat_full[2];
     uint32_t tmem_base;
     int tile_ctr[2];
@@ -384,6 +387,7 @@ static_assert(sizeof(SmemTC) <= 227 * 1024, "shared memory plan");
         if (tid == 0) {                                                                                             \
             for (int s = 0; s < kTcStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }         \
             mbar_init(&sm.acc_bar, 1);                                                                              \
+            mbar_init(&sm.f_done[0], 4); mbar_init(&sm.f_done[1], 4);                                               \
             for (int b = 0; b < 2; ++b) {                                                                           \
                 mbar_init(&sm.xs_full[b], 4);                                                                       \
                 mbar_init(&sm.feat_full[b], kGatherWarps);                                                          \

@@ -27,4 +27,4 @@ for (name, _), m in per.items():
         if s == "Minst": v /= 1e6
         vals.append(v)
     t_us, rd, wr = vals[0], vals[1], vals[2]
-    print(f"{name:62s} " + " ".join(f"{v:9.1f}" for v in vals) + f"   {(rd + wr) / t_us * 1e3 / 1e3:9.0f}")
+    print(f"{name:62s} " + " ".join(f"{v:9.1f}" for v in vals) + f"   {(rd + wr) / t_us * 1e3:9.0f}")
