@@ -19,7 +19,7 @@ _F32 = torch.float32
 # Deformation MLP of the inference kernels on tcgen05 / TMEM (NativeParams.build(tcgen05=...) overrides it per instance;
 # NSB_TCGEN05=0/1 in the environment overrides the default).
 import os as _os
-USE_TCGEN05 = _os.environ.get("NSB_TCGEN05", "0") == "1"
+USE_TCGEN05 = _os.environ.get("NSB_TCGEN05", "1") == "1"
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -130,12 +130,16 @@ class NativeParams:
         if deform is not None:
             P.deform_packed_tb, P.deform_code_bias, P.deform_packed_t = dtb, dcb, dpt
             P.deform_code_w = [sw[0].detach(), sw[4].detach(), sb[0].detach(), sb[4].detach()]
-            if USE_TCGEN05 if tcgen05 is None else tcgen05:
-                P.deform_packed_umma = packing.pack_deform_umma_fast(sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
+            if USE_TCGEN05 if tcgen05 is None else tcgen05:     # packed lazily, by the first inference call (c_params)
+                P._umma_src = (sw, deform["r_w"].to(dev), deform["v_w"].to(dev))
         P.field_packed_t = fpt
         return P
 
-    def c_params(self) -> _lib.FieldParams:
+    def c_params(self, inference: bool = False) -> _lib.FieldParams:
+        """inference: the call saves nothing for a backward pass -- the kernels may then run the deformation MLP on
+        tcgen05 / TMEM, which takes its weights in another order (packed here on first use: a training step never pays)."""
+        if inference and self.deform_packed_umma is None and getattr(self, "_umma_src", None) is not None:
+            self.deform_packed_umma = packing.pack_deform_umma_fast(*self._umma_src)
         p = getattr(self, "_cp", None)      # the level table / aabb part never changes: fill it once (host time matters:
         fresh = p is None                   # a training step is ~6 ms of host work against ~20 ms of GPU work)
         if fresh:
@@ -144,7 +148,7 @@ class NativeParams:
         p.deform_bias = _ptr(self.deform_bias)
         p.deform_packed_tb = _ptr(self.deform_packed_tb)
         p.deform_code_bias = _ptr(self.deform_code_bias)
-        p.deform_packed_umma = _ptr(self.deform_packed_umma)
+        p.deform_packed_umma = _ptr(self.deform_packed_umma) if inference else None
         p.field_packed = _ptr(self.field_packed)
         p.warp_codes = _ptr(self.warp_codes)
         p.blend_codes = _ptr(self.blend_codes)
@@ -265,7 +269,8 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
     if n == 0:
         return out
     opts = make_opts(window_hash, window_deform, use_deformation, "rgb" in want, disable_initial, soft_transition)
-    cp = P.c_params()
+    cp = P.c_params(inference=use_deformation and n_samples_dev is None and given_feat is None and sample_warp_codes is None
+                    and not any(k in want for k in ("feat", "xs", "corner_vals", "deform_acts")))
     rc = lib.nsb_field_forward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(o), _stream())
     _lib.check(rc, "nsb_field_forward")
     return out
@@ -824,7 +829,7 @@ def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=
     if R == 0:
         return out
     opts = make_opts(window_hash, window_deform, use_deformation, True, disable_initial, soft_transition)
-    cp = P.c_params()
+    cp = P.c_params(inference=True)
     _lib.check(lib.nsb_render_forward(C.byref(cp), C.byref(opts), C.byref(a), _stream()), "nsb_render_forward")
     return out
 

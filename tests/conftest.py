@@ -36,7 +36,7 @@ def oracle_params(knobs):
     return _PARAM_CACHE[key]
 
 
-def native_from_oracle(P, device="cuda"):
+def native_from_oracle(P, device="cuda", tcgen05=None):
     """oracle FieldParams -> nersemble_b200.ops.NativeParams (same numbers, kernel layouts)."""
     from nersemble_b200 import ops, packing
     lv = P.levels
@@ -46,4 +46,4 @@ def native_from_oracle(P, device="cuda"):
     deform = dict(stem_w=P.deform_w, stem_b=P.deform_b, r_w=P.r_w, r_b=P.r_b, v_w=P.v_w, v_b=P.v_b)
     return ops.NativeParams.build(tables=P.tables, base_w=P.base_w, head_w=P.head_w, time_emb=P.time_emb,
                                   aabb=P.aabb, levels=levels, deform=deform, time_emb_deform=P.time_emb_deform,
-                                  device=device)
+                                  device=device, tcgen05=tcgen05)

@@ -37,10 +37,19 @@ def _oracle_stages(P, o, d, times, ts, te, ri, w_hash, w_deform):
         return pl.render(P, o, d, times, ts, te, ri, window_hash=w_hash, window_deform=w_deform, training=False)
 
 
+@pytest.fixture(scope="module")
+def trained_mma(trained):
+    return trained[0], native_from_oracle(trained[0], DEV, tcgen05=False)
+
+
+@pytest.mark.parametrize("tensor_role", ["tcgen05", "mma.sync"])
 @pytest.mark.parametrize("w_hash,w_deform", [(32.0, 7.0), (1.5, 3.3), (1, 0.0), (None, None)])
-def test_field_and_composite_vs_oracle(trained, w_hash, w_deform):
+def test_field_and_composite_vs_oracle(trained, trained_mma, w_hash, w_deform, tensor_role):
+    """Both inference instantiations of the deformation MLP against the oracle: the tcgen05 / TMEM role (the default,
+    nsb_field_tensor_role_tc.inc) and the mma.sync role (NSB_TCGEN05=0; also what the training kernels run)."""
     from nersemble_b200 import ops
-    P, NP = trained
+    P, NP = trained if tensor_role == "tcgen05" else trained_mma
+    assert (getattr(NP, "_umma_src", None) is not None) == (tensor_role == "tcgen05")
     R = 40
     o, d, times, _ = _rays(R, 3)
     ts, te, ri = pl.fixed_samples(o, d, P.aabb, 50, 0.011, near=0.2)      # 2000 samples: ragged last tile

@@ -157,6 +157,29 @@ def test_gather_plans_reproduce_the_packers():
     assert torch.equal(pk.deform_bias_vector(sb, r_b, v_b), pk.pack_deform(stem, sb, r_w, r_b, v_w, v_b)[1])
 
 
+def test_pack_deform_umma_layout():
+    """tcgen05 B operands (packing.pack_deform_umma): 14 blocks per tile in order of use, [n x 64 k] in K-major
+    no-swizzle core-matrix order -- byte offset (n/8)*1024 + (k/8)*128 + (n%8)*16 + (k%8)*2 (descriptor LBO 128, SBO 1024);
+    K = the reference's encoding column order, zero padded; the gather-plan version is identical."""
+    from nersemble_b200 import packing as pk
+    g = torch.Generator().manual_seed(1)
+    stem = [torch.randn(s, generator=g) for s in pk._STEM_SHAPES]
+    r_w, v_w = torch.randn(3, 128, generator=g), torch.randn(3, 128, generator=g)
+    a = pk.pack_deform_umma(stem, r_w, v_w)
+    assert a.dtype == torch.float16 and a.numel() * 2 == 12 * 16384 + 2 * 2048
+    assert torch.equal(a, pk.pack_deform_umma_fast(stem, r_w, v_w))
+    el = lambda blk, n, k: float(a[blk * 8192 + (n // 8) * 512 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)])
+    h = lambda x: float(x.half())
+    assert el(0, 37, 21) == h(stem[0][37, 21]) and el(0, 37, 45) == 0.0 and el(0, 127, 44) == h(stem[0][127, 44])
+    assert el(1, 5, 63) == h(stem[1][5, 63]) and el(2, 5, 0) == h(stem[1][5, 64])            # layer 1: two 64-wide K blocks
+    assert el(7, 9, 3) == h(stem[4][9, 173 + 3]) and el(8, 9, 3) == h(stem[4][9, 173 + 67])    # layer 4: hidden columns first
+    assert el(9, 9, 44) == h(stem[4][9, 44]) and el(9, 9, 47) == 0.0                         # ... then the posenc columns
+    assert el(10, 100, 7) == h(stem[5][100, 7])
+    heads = lambda half, n, k: float(a[12 * 8192 + half * 1024 + (n // 8) * 512 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)])
+    assert heads(0, 1, 5) == h(v_w[1, 5]) and heads(0, 4, 5) == h(r_w[1, 5]) and heads(1, 4, 5) == h(r_w[1, 69])
+    assert heads(0, 6, 0) == 0.0 and heads(1, 15, 63) == 0.0
+
+
 def test_forward_kernel_gather_role_has_no_spill_storm():
     """Regression guard for a performance cliff, not for correctness: local-memory traffic inside the 64-register gather
     role of field_kernel_ws is catastrophic (48 spill instructions per sample: 2.6 -> 4.0 ms on B200, profiles/README.md)
