@@ -519,9 +519,11 @@ def run_config2(args, occ=False):
         field_samples = (hi - lo) * SAMPLES_PER_RAY
         achieved = ALG_BYTES_PER_SAMPLE * field_samples / (field_ms / 1e3) / 1e9
         traffic = None
+        from nersemble_b200 import ops as _ops
+        kname = "render_kernel_tc" if _ops.USE_TCGEN05 else "render_kernel_ws"      # NSB_TCGEN05=0 selects the mma.sync role
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp) and world == 1:
-            traffic = json.load(open(tp)).get("render_kernel_ws_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(f"{kname}_dram_bytes_per_launch")
         line = {
             "metric": "M ray-samples/sec", "value": value, "unit": "M ray-samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_value / K, "higher_is_better": True,
@@ -540,7 +542,8 @@ def run_config2(args, occ=False):
                             "cooperative march launch + one fused field/composite launch, no host sync",
                     "samples_per_step": samples_e2e_total, "ms_per_step": ms_e2e / K, "rgb_l2_max_vs_op_path": e2e_l2},
             "gpu_launches": 1 * K,
-            "roofline": {"bound": "hbm", "kernel": "nsb::render_kernel_ws<deform, fixed march> (march + field + composite, one launch)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": f"nsb::{kname}<fixed march> (march + field + composite, one launch; deformation MLP on "
+                                                      + ("tcgen05/TMEM)" if _ops.USE_TCGEN05 else "mma.sync)"), "achieved": achieved,
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "kernel_ms": field_ms, "samples_per_launch": field_samples},
             "clocks": sampler.summary(),

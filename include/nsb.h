@@ -71,6 +71,10 @@ typedef struct nsb_field_params {
                                        [128 outputs x 64 inputs] fp16 (heads [16 x 64]) in K-major 8 x 16-byte core matrices
                                        (python: pack_deform_umma; nsb_deform_packed_umma_bytes()).  When set, the inference
                                        kernels run the deformation MLP on tcgen05.mma with the accumulator in TMEM. */
+    const void *frame_table;   /* optional, float2 [total_entries]: the tables blended with ONE timestep's member weights
+                                  (nsb_blend_tables).  Only valid when EVERY sample of the call has that timestep (one
+                                  camera frame): the gather then reads 8 B per corner from a 67 MB table that stays in L2
+                                  instead of a 128 B line from HBM.  Used by the tcgen05 inference kernels. */
     const void *field_packed;  /* fp16 mlp_base + mlp_head weights in MMA-B fragment order */
     const void *warp_codes;    /* __half [n_timesteps][128]  (time_embedding_deformation) */
     const float *blend_codes;  /* float  [n_timesteps][32]   (time_embedding) */
@@ -139,6 +143,11 @@ const char *nsb_last_error(void);
 /* Sizes (bytes) of the packed weight buffers the python packer must produce. */
 size_t nsb_deform_packed_bytes(void);
 size_t nsb_deform_packed_umma_bytes(void);
+/* Frame table of one timestep: out[e] = sum_m (blend_codes[timestep][m] * cw_scale[m] + cw_bias[m]) * tables[e][m][:]
+ * (float2 per entry, fp32 accumulation) -- HashEnsemble.forward's member blend (hash_ensemble.py:119-139) hoisted out of
+ * the per-sample path for calls whose samples all share that timestep (nsb_field_params.frame_table). */
+int nsb_blend_tables(const nsb_field_params *params, const nsb_field_opts *opts, int32_t timestep, int64_t n_entries,
+                     void *out, void *stream);
 size_t nsb_field_packed_bytes(void);
 
 /* Fused per-sample field evaluation (deformation MLP -> SE(3) warp -> 32-member hash ensemble

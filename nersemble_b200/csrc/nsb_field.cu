@@ -401,7 +401,8 @@ static_assert(sizeof(SmemTC) <= 227 * 1024, "shared memory plan");
         tc::fence_after_sync();                                                                                     \
     }
 
-template <bool HEAD>
+// FRAME: the gather role reads the member-blended frame table (nsb_field_gather_role_frame.inc)
+template <bool HEAD, bool FRAME>
 __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_tc(const __grid_constant__ FieldArgs A) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemTC &sm = *reinterpret_cast<SmemTC *>(smem_raw);
@@ -411,7 +412,11 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_tc(const __gri
     NSB_TC_SETUP()
     if (warp >= kTensorWarps) {
         if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
+        if constexpr (FRAME) {
+#include "nsb_field_gather_role_frame.inc"
+        } else {
 #include "nsb_field_gather_role.inc"
+        }
         return;
     }
     if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_ws(const __gr
 }
 
 // render_kernel_ws with the deformation MLP on tcgen05 / TMEM (nsb_field_tensor_role_tc.inc); SAMPLER 0 or 2
-template <int SAMPLER>
+template <int SAMPLER, bool FRAME>
 __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __grid_constant__ RenderKArgs K) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemTC &sm = *reinterpret_cast<SmemTC *>(smem_raw);
@@ -667,7 +672,11 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __gr
     if (warp >= kTensorWarps) {
         if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
         mbar_wait<200>(&sm.sampler_done, 0);
+        if constexpr (FRAME) {
+#include "nsb_field_gather_role_frame.inc"
+        } else {
 #include "nsb_field_gather_role.inc"
+        }
         return;
     }
     if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
@@ -772,19 +781,23 @@ static int launch_field_ws(const FieldArgs &A, cudaStream_t st) {
     return save ? launch_field_ws_<D, F, H, true>(A, st) : launch_field_ws_<D, F, H, false>(A, st);
 }
 
-template <bool H>
-static int launch_field_tc(const FieldArgs &A, cudaStream_t st) {
+template <bool H, bool FR>
+static int launch_field_tc_(const FieldArgs &A, cudaStream_t st) {
     const size_t smem = sizeof(SmemTC);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(field_kernel_tc<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(field_kernel_tc<H, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(field_kernel_tc): %s", cudaGetErrorString(e)); return 1; }
         configured = true;
     }
     const int64_t n_tiles = (A.S.n_samples + NSB_TILE - 1) / NSB_TILE;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms());
-    field_kernel_tc<H><<<grid, kThreadsWS, smem, st>>>(A);
+    field_kernel_tc<H, FR><<<grid, kThreadsWS, smem, st>>>(A);
     return check_launch("field_kernel_tc");
+}
+template <bool H>
+static int launch_field_tc(const FieldArgs &A, cudaStream_t st) {
+    return A.P.frame_table ? launch_field_tc_<H, true>(A, st) : launch_field_tc_<H, false>(A, st);
 }
 
 template <bool D>
@@ -879,18 +892,62 @@ extern "C" int nsb_hash_blend_forward(const nsb_field_params *params, const nsb_
 }
 
 // -------------------------------------------------------------------------------------------
+// nsb_blend_tables: frame table = the 32 members of every table entry blended with ONE timestep's weights
+// (cw[m] = code[m] * cw_scale[m] + cw_bias[m], hash_ensemble.py:119-139), float2 per entry.  8 lanes per entry
+// (16 B = 4 members each), fp32 accumulation; one streaming pass over the tables (HBM-bound: 1 GB at ~6 TB/s).
+// -------------------------------------------------------------------------------------------
+namespace nsb {
+__global__ void __launch_bounds__(256) blend_tables_kernel(const uint4 *__restrict__ tables, const float *__restrict__ code,
+                                                           const __grid_constant__ nsb_field_opts O, float2 *__restrict__ out,
+                                                           int64_t n_entries) {
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    float cw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cw[i] = fmaf(__ldg(code + 4 * sub + i), O.cw_scale[4 * sub + i], O.cw_bias[4 * sub + i]);
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 3);
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); e < ((n_entries + 3) & ~(int64_t)3); e += stride) {
+        float f0 = 0.f, f1 = 0.f;
+        if (e < n_entries) {
+            const uint4 v = __ldcs(tables + e * 8 + sub);          // streamed once: evict-first
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_h2(u[i]);
+                f0 = fmaf(cw[i], f.x, f0); f1 = fmaf(cw[i], f.y, f1);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o); }
+        if (sub == 0 && e < n_entries) out[e] = make_float2(f0, f1);
+    }
+}
+}  // namespace nsb
+
+extern "C" int nsb_blend_tables(const nsb_field_params *params, const nsb_field_opts *opts, int32_t timestep, int64_t n_entries,
+                                void *out, void *stream) {
+    if (!params || !opts || !out || !params->tables || !params->blend_codes) { set_error("nsb_blend_tables: null argument"); return 1; }
+    if (timestep < 0 || timestep >= params->n_timesteps) { set_error("nsb_blend_tables: timestep out of range"); return 1; }
+    if (n_entries <= 0) return 0;
+    const int blocks = (int)std::min<int64_t>((n_entries + 31) / 32, (int64_t)num_sms() * 8);
+    blend_tables_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4 *>(params->tables),
+                                                                  params->blend_codes + (size_t)timestep * NSB_MEMBERS, *opts,
+                                                                  reinterpret_cast<float2 *>(out), n_entries);
+    return check_launch("blend_tables_kernel");
+}
+
+// -------------------------------------------------------------------------------------------
 // nsb_render_forward: host side of render_kernel_ws
 // -------------------------------------------------------------------------------------------
 namespace nsb {
 constexpr size_t kRenderHdrBytes = 64, kRenderPartials = 1024;
 static_assert(sizeof(nsb_render_ws_header) == kRenderHdrBytes, "workspace header layout");
 
-template <int SAMPLER>
-static int launch_render_tc(const RenderKArgs &K, cudaStream_t st) {
+template <int SAMPLER, bool FR>
+static int launch_render_tc_(const RenderKArgs &K, cudaStream_t st) {
     const size_t smem = sizeof(SmemTC);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(render_kernel_tc<SAMPLER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(render_kernel_tc<SAMPLER, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(render_kernel_tc): %s", cudaGetErrorString(e)); return 1; }
         configured = true;
     }
@@ -899,9 +956,13 @@ static int launch_render_tc(const RenderKArgs &K, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(&K.hdr->barrier, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) { set_error("nsb_render_forward: memset: %s", cudaGetErrorString(e)); return 2; }
     void *kargs[] = {const_cast<RenderKArgs *>(&K)};
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(render_kernel_tc<SAMPLER>), dim3(grid), dim3(kThreadsWS), kargs, smem, st);
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(render_kernel_tc<SAMPLER, FR>), dim3(grid), dim3(kThreadsWS), kargs, smem, st);
     if (e != cudaSuccess) { set_error("render_kernel_tc: %s", cudaGetErrorString(e)); return 2; }
     return check_launch("render_kernel_tc");
+}
+template <int SAMPLER>
+static int launch_render_tc(const RenderKArgs &K, cudaStream_t st) {
+    return K.F.P.frame_table ? launch_render_tc_<SAMPLER, true>(K, st) : launch_render_tc_<SAMPLER, false>(K, st);
 }
 
 template <bool D, int SAMPLER>

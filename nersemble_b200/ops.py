@@ -135,7 +135,28 @@ class NativeParams:
         P.field_packed_t = fpt
         return P
 
-    def c_params(self, inference: bool = False) -> _lib.FieldParams:
+    def frame_table(self, uniform_time: float, window_hash, disable_initial: bool, soft_transition: bool) -> Optional[torch.Tensor]:
+        """float [total_entries, 2]: the tables blended with the member weights of ONE timestep (nsb_blend_tables), for
+        calls whose samples all carry `uniform_time` (a camera frame).  Cached per (timestep, window, table version); None
+        when the tcgen05 inference kernels (the only ones that read it) are not in use."""
+        if getattr(self, "_umma_src", None) is None or self.tables is None or self.blend_codes is None:
+            return None
+        import numpy as np
+        tsi = int(np.rint(np.float32(uniform_time) * np.float32(self.n_timesteps - 1)))     # the kernels' __float2int_rn(t * (T - 1))
+        tsi = min(max(tsi, 0), self.n_timesteps - 1)
+        key = (tsi, None if window_hash is None else float(window_hash), bool(disable_initial), bool(soft_transition),
+               self.tables.data_ptr(), self.tables._version, self.blend_codes.data_ptr(), self.blend_codes._version)
+        cached = getattr(self, "_frame", None)
+        if cached is None or cached[0] != key:
+            out = cached[1] if cached is not None else torch.empty((self.tables.shape[0], 2), dtype=_F32, device=self.tables.device)
+            opts = make_opts(window_hash, None, True, True, disable_initial, soft_transition)
+            cp = self.c_params()
+            _lib.check(_lib.load().nsb_blend_tables(C.byref(cp), C.byref(opts), tsi, int(self.tables.shape[0]), _ptr(out), _stream()),
+                       "nsb_blend_tables")
+            self._frame = cached = (key, out)
+        return cached[1]
+
+    def c_params(self, inference: bool = False, frame: Optional[torch.Tensor] = None) -> _lib.FieldParams:
         """inference: the call saves nothing for a backward pass -- the kernels may then run the deformation MLP on
         tcgen05 / TMEM, which takes its weights in another order (packed here on first use: a training step never pays)."""
         if inference and self.deform_packed_umma is None and getattr(self, "_umma_src", None) is not None:
@@ -149,6 +170,7 @@ class NativeParams:
         p.deform_packed_tb = _ptr(self.deform_packed_tb)
         p.deform_code_bias = _ptr(self.deform_code_bias)
         p.deform_packed_umma = _ptr(self.deform_packed_umma) if inference else None
+        p.frame_table = _ptr(frame) if (inference and self.deform_packed_umma is not None) else None
         p.field_packed = _ptr(self.field_packed)
         p.warp_codes = _ptr(self.warp_codes)
         p.blend_codes = _ptr(self.blend_codes)
@@ -193,7 +215,7 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
                   origins=None, directions=None, ray_times=None, t_starts=None, t_ends=None, ray_indices=None,
                   positions=None, sample_times=None, sample_directions=None, sample_blend_codes=None,
                   sample_warp_codes=None, n_samples_dev: Optional[torch.Tensor] = None,
-                  given_feat: Optional[torch.Tensor] = None,
+                  given_feat: Optional[torch.Tensor] = None, uniform_time: Optional[float] = None,
                   want: Sequence[str] = ("sigma", "rgb", "offsets"),
                   disable_initial: bool = True, soft_transition: bool = True) -> Dict[str, torch.Tensor]:
     """Fused deformation + hash ensemble + field MLPs for packed samples (nsb_field_forward)."""
@@ -269,8 +291,13 @@ def field_forward(P: NativeParams, *, window_hash=None, window_deform=None, use_
     if n == 0:
         return out
     opts = make_opts(window_hash, window_deform, use_deformation, "rgb" in want, disable_initial, soft_transition)
-    cp = P.c_params(inference=use_deformation and n_samples_dev is None and given_feat is None and sample_warp_codes is None
-                    and not any(k in want for k in ("feat", "xs", "corner_vals", "deform_acts")))
+    inference = (use_deformation and n_samples_dev is None and given_feat is None and sample_warp_codes is None
+                 and not any(k in want for k in ("feat", "xs", "corner_vals", "deform_acts")))
+    frame = None
+    if inference and uniform_time is not None and sample_blend_codes is None and ("sigma" in want or "rgb" in want):
+        # every sample carries this time (the caller's promise, e.g. one camera frame): gather the blended frame table
+        frame = P.frame_table(uniform_time, window_hash, disable_initial, soft_transition)
+    cp = P.c_params(inference=inference, frame=frame)
     rc = lib.nsb_field_forward(C.byref(cp), C.byref(opts), C.byref(s), C.byref(o), _stream())
     _lib.check(rc, "nsb_field_forward")
     return out
@@ -763,7 +790,7 @@ def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=
                 near_plane: float = 0.0, near_planes=None, far_planes=None, binaries=None, aabbs=None,
                 step: float = 1e-3, cone_angle: float = 0.0, capacity: Optional[int] = None,
                 disable_initial=True, soft_transition=True, single_launch: bool = False,
-                single_traversal: bool = True) -> RenderResult:
+                single_traversal: bool = True, uniform_time: Optional[float] = None) -> RenderResult:
     """The fused inference render (nsb_render_forward): sampler -> field -> composite without a host synchronisation.
     sampler 'fixed' (n_per_ray steps from the box entry: ONE launch) or 'occupancy' (nerfacc march of `binaries`
     [levels,res,res,res] within per-ray near_planes / far_planes: the cooperative march launch + one fused launch;
@@ -829,7 +856,11 @@ def render_rays(P: NativeParams, origins, directions, ray_times, *, window_hash=
     if R == 0:
         return out
     opts = make_opts(window_hash, window_deform, use_deformation, True, disable_initial, soft_transition)
-    cp = P.c_params(inference=True)
+    frame = None
+    if uniform_time is not None and use_deformation and not single_launch:
+        # all rays carry this time (one camera frame): the member blend is hoisted into a per-frame table (frame_table)
+        frame = P.frame_table(uniform_time, window_hash, disable_initial, soft_transition)
+    cp = P.c_params(inference=True, frame=frame)
     _lib.check(lib.nsb_render_forward(C.byref(cp), C.byref(opts), C.byref(a), _stream()), "nsb_render_forward")
     return out
 

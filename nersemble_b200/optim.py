@@ -191,7 +191,8 @@ class FusedFieldsAdam(torch.optim.Adam):
             else:
                 ops.table_adam_step(p.data, st["exp_avg"], st["exp_avg_sq"], shadow, grad=dense, pending=pending, grad_scale=gscale, **kw)
             torch.autograd.graph.increment_version(p)
-            he.set_native_tables(shadow)
+            torch.autograd.graph.increment_version(shadow)      # written in place by the kernel: caches keyed on the fp16
+            he.set_native_tables(shadow)                        # copy's version (NativeParams.frame_table) must see it
             he.pending_table_grad = None
         return loss
 

@@ -195,6 +195,7 @@ class NeRSembleNGPModel(Model):
         self.lpips = None                # optional callable(image[1,3,H,W], rgb[1,3,H,W]) -> scalar (needs pretrained weights)
         self.use_fused_render = True     # eval renders: sampler -> field -> composite fused, no host sync (ops.render_rays)
         self.use_fused_sampler = True    # training: march / density pre-pass / visibility / packing with one host sync
+        self.frame_tables = True         # eval frames (one timestep per camera frame): gather a per-frame blended table
         self.prepass_reuse = True        # ... and the pre-pass's blended features / corner values are packed with the kept
                                          # samples, so the differentiable forward does not gather the tables a second time
 
@@ -323,9 +324,10 @@ class NeRSembleNGPModel(Model):
             return ray_bundle.times.reshape(-1).float()
         return ray_bundle.metadata['timesteps'].reshape(-1).float() / max(self.config.n_timesteps - 1, 1)
 
-    def _fused_render(self, ray_bundle: RayBundle) -> "ops.RenderResult":
+    def _fused_render(self, ray_bundle: RayBundle, uniform_time: Optional[float] = None) -> "ops.RenderResult":
         """Eval render of a (flat) ray bundle through nsb_render_forward: the nerfacc occupancy march as one cooperative
-        launch + field and compositing fused into one launch; the packed sample count stays on the device."""
+        launch + field and compositing fused into one launch; the packed sample count stays on the device.
+        uniform_time: every ray of the bundle carries this time (a camera frame) -> per-frame blended table."""
         cfg = self.config
         wh, wd = self._windows()
         near_planes, far_planes = self.sampler.eval_planes(ray_bundle, cfg.near_plane, cfg.far_plane)
@@ -334,7 +336,8 @@ class NeRSembleNGPModel(Model):
                                self._ray_times(ray_bundle), window_hash=wh, window_deform=wd,
                                use_deformation=cfg.use_deformation_field, training=self.training, sampler="occupancy",
                                near_planes=near_planes, far_planes=far_planes, binaries=og.binaries, aabbs=og.aabbs,
-                               step=cfg.render_step_size, cone_angle=cfg.cone_angle, **self._blend_opts())
+                               step=cfg.render_step_size, cone_angle=cfg.cone_angle, uniform_time=uniform_time,
+                               **self._blend_opts())
 
     @torch.no_grad()
     def _sample_packed(self, ray_bundle: RayBundle, jitter: Optional[Tensor], want_payload: bool = False):
@@ -384,10 +387,18 @@ class NeRSembleNGPModel(Model):
             return super().get_outputs_for_camera_ray_bundle(camera_ray_bundle)
         n = self.config.eval_num_rays_per_chunk
         h, w = camera_ray_bundle.origins.shape[:2]
+        # A camera frame has ONE timestep (evaluate_nersemble.py renders camera x timestep): when all rays carry the same
+        # time (checked here: one host synchronisation per FRAME), the 32-member blend is hoisted out of the per-sample
+        # path into a per-frame table (ops.NativeParams.frame_table) that every chunk of the frame gathers from L2.
+        uniform_time = None
+        if self.frame_tables and camera_ray_bundle.times is not None and self.config.use_hash_ensemble:
+            t = camera_ray_bundle.times
+            lo, hi = torch.stack([t.min(), t.max()]).tolist()
+            uniform_time = lo if lo == hi else None
         lists: Dict[str, list] = {}
         for i in range(0, h * w, n):
             rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(i, i + n)
-            res = self._fused_render(rb)
+            res = self._fused_render(rb, uniform_time)
             for name in ("rgb", "accumulation", "depth", "num_samples_per_ray", "deformation"):
                 if name in res:
                     lists.setdefault(name, []).append(res[name])

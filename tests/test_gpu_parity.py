@@ -228,3 +228,43 @@ def test_size_independent_properties_at_full_size():
     want_acc = 1 - np.exp(-0.7 * 0.011 * S)
     assert abs(c["accumulation"].mean().item() - want_acc) < 2e-4
     torch.testing.assert_close(c["rgb"], torch.full((R, 3), 0.25 * want_acc + 1 - want_acc, device=DEV), rtol=0, atol=3e-4)
+
+
+@pytest.mark.parametrize("w_hash", [32.0, 1.5, None])
+def test_frame_table_path_vs_oracle_and_per_sample_blend(trained, w_hash):
+    """One timestep for the whole call (a camera frame): the member blend is hoisted into a per-frame table
+    (nsb_blend_tables, float2 per entry) and the gather reads 8 B per corner.  Linear in the member features, so the
+    result equals HashEnsemble.forward's per-sample blend (hash_ensemble.py:75-139) up to rounding: checked against the
+    oracle at the tolerances of the per-sample path, and against that path itself."""
+    from nersemble_b200 import ops
+    P, NP = trained
+    R = 40
+    o, d, times, _ = _rays(R, 3)
+    t0 = float(times[7])
+    times = torch.full_like(times, t0)
+    ts, te, ri = pl.fixed_samples(o, d, P.aabb, 50, 0.011, near=0.2)
+    want = _oracle_stages(P, o, d, times, ts, te, ri, w_hash, 7.0)
+    info = nerfacc_cpu.pack_info(ri, R)
+    # the table itself: sum_m cw[m] * tables[e][m][:]
+    ft = NP.frame_table(t0, w_hash, True, True)
+    tsi = int(round(t0 * (P.time_emb.shape[0] - 1)))
+    from nersemble_b200 import packing
+    sc, bi = packing.blend_fold(w_hash, 32, True, True)
+    cw = P.time_emb[tsi].float() * torch.tensor(sc) + torch.tensor(bi)
+    ref_tab = torch.einsum("emf,m->ef", NP.tables.float().cpu(), cw)
+    torch.testing.assert_close(ft.cpu(), ref_tab, rtol=1e-5, atol=1e-6)
+    kw = dict(origins=o.to(DEV), directions=d.to(DEV), ray_times=times.to(DEV), t_starts=ts.to(DEV), t_ends=te.to(DEV),
+              ray_indices=ri.to(DEV), window_hash=w_hash, window_deform=7.0)
+    per_sample = ops.field_forward(NP, **kw)
+    frame = ops.field_forward(NP, uniform_time=t0, **kw)
+    assert torch.equal(frame["offsets"], per_sample["offsets"])                       # the deformation does not change
+    torch.testing.assert_close(frame["sigma"], per_sample["sigma"], rtol=5e-3, atol=1e-5)
+    torch.testing.assert_close(frame["rgb"], per_sample["rgb"], rtol=0, atol=2e-3)
+    torch.testing.assert_close(frame["sigma"].cpu(), want["density"][:, 0], rtol=5e-3, atol=1e-5)
+    torch.testing.assert_close(frame["rgb"].cpu(), want["rgb_samples"], rtol=0, atol=2e-3)
+    # fused render, fixed march: per-ray outputs against the oracle (north-star tolerance 1e-3 L2 per pixel)
+    got = ops.render_rays(NP, o.to(DEV), d.to(DEV), times.to(DEV), window_hash=w_hash, window_deform=7.0, sampler="fixed",
+                          n_per_ray=50, near_plane=0.2, step=0.011, uniform_time=t0)
+    assert (got["rgb"].cpu() - want["rgb"]).norm(dim=-1).max() < 1e-3
+    torch.testing.assert_close(got["accumulation"].cpu(), want["accumulation"], rtol=0, atol=1e-3)
+    torch.testing.assert_close(got["depth"].cpu(), want["depth"], rtol=1e-3, atol=1e-3)

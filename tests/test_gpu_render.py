@@ -18,6 +18,13 @@ def trained():
     return P, native_from_oracle(P, DEV)
 
 
+@pytest.fixture(scope="module")
+def trained_mma(trained):
+    """The same parameters with the deformation MLP of the inference kernels on mma.sync (NSB_TCGEN05=0): what the
+    single-launch occupancy variant (render_kernel_ws<.,1>) and the training kernels run."""
+    return trained[0], native_from_oracle(trained[0], DEV, tcgen05=False)
+
+
 def _rays(R, seed):
     from oracle.gen_golden import ring_rays
     o, d, t, _ = ring_rays(R, seed)
@@ -51,13 +58,13 @@ def test_fixed_march_one_launch_is_bit_identical_to_the_three_kernel_path(traine
 
 @pytest.mark.parametrize("single_launch", [False, True, "two_pass"])
 @pytest.mark.parametrize("levels", [1, 2])
-def test_occupancy_march_fused_is_bit_identical(trained, levels, single_launch):
+def test_occupancy_march_fused_is_bit_identical(trained, trained_mma, levels, single_launch):
     from nersemble_b200 import ops
     from oracle.gen_golden import blob_grid
     from oracle.tp import nerfacc_cpu
     if single_launch is True and levels != 1:
         pytest.skip("the single-launch variant marches single-level grids")
-    P, NP = trained
+    P, NP = trained_mma if single_launch is True else trained       # bit-identity holds within one tensor role
     R = 700                                            # > 256 * ... several scan slabs per CTA chunk is covered by R = 40 000 below
     o, d, t = _rays(R, 11)
     d[5] = torch.tensor([0.0, 0.0, -1.0]); o[5] = torch.tensor([0.1, 0.2, 9.0])
@@ -110,10 +117,14 @@ def test_occupancy_scan_over_many_rays_and_capacity_overflow(trained):
         small.packed()
 
 
-def test_plugin_eval_paths_use_the_fused_render(trained):
+@pytest.mark.parametrize("tensor_role", ["mma.sync", "tcgen05"])
+def test_plugin_eval_paths_use_the_fused_render(trained, monkeypatch, tensor_role):
     """NeRSembleNGPModel eval: get_outputs_for_camera_ray_bundle (no host sync) and get_outputs (full contract) agree bit
-    for bit with the training-path kernels run in eval mode."""
+    for bit with the training-path kernels run in eval mode when both run the mma.sync deformation role; with the
+    tcgen05 role (the default of the fused render) they agree to fp16-operand rounding."""
+    from nersemble_b200 import ops
     from nersemble_b200.nerfstudio_shim import RayBundle
+    monkeypatch.setattr(ops, "USE_TCGEN05", tensor_role == "tcgen05")
     from oracle.gen_golden import blob_grid
     from test_plugin_cpu import make_model
     from test_plugin_gpu import load_oracle_params_into
@@ -137,13 +148,23 @@ def test_plugin_eval_paths_use_the_fused_render(trained):
         full = m.get_outputs(flat)
         m.use_fused_render = False
         full_ref = m.get_outputs(flat)
-    for k in ("rgb", "accumulation", "depth", "deformation", "num_samples_per_ray"):
-        assert _same(img[k], ref[k]), k
-        assert _same(full[k], full_ref[k]), k
-    assert _same(full["weights"][0], full_ref["weights"][0]) and _same(full["ray_indices"][0], full_ref["ray_indices"][0])
     rs, rs_ref = full["ray_samples"][0], full_ref["ray_samples"][0]
-    assert _same(rs.frustums.starts, rs_ref.frustums.starts) and _same(rs.frustums.offsets, rs_ref.frustums.offsets)
+    assert _same(full["ray_indices"][0], full_ref["ray_indices"][0]) and _same(rs.frustums.starts, rs_ref.frustums.starts)
     assert _same(rs.frustums.origins, rs_ref.frustums.origins) and _same(rs.times, rs_ref.times)
+    assert _same(img["num_samples_per_ray"], ref["num_samples_per_ray"]) and _same(full["num_samples_per_ray"], full_ref["num_samples_per_ray"])
+    if tensor_role == "mma.sync":
+        for k in ("rgb", "accumulation", "depth", "deformation"):
+            assert _same(img[k], ref[k]), k
+            assert _same(full[k], full_ref[k]), k
+        assert _same(full["weights"][0], full_ref["weights"][0]) and _same(rs.frustums.offsets, rs_ref.frustums.offsets)
+    else:
+        for a, b in ((img, ref), (full, full_ref)):
+            assert (a["rgb"] - b["rgb"]).norm(dim=-1).max() < 1e-3
+            torch.testing.assert_close(a["accumulation"], b["accumulation"], rtol=0, atol=1e-3)
+            torch.testing.assert_close(a["depth"], b["depth"], rtol=1e-3, atol=1e-3)
+            torch.testing.assert_close(a["deformation"], b["deformation"], rtol=5e-3, atol=1e-5)
+        torch.testing.assert_close(full["weights"][0], full_ref["weights"][0], rtol=5e-3, atol=2e-5)
+        torch.testing.assert_close(rs.frustums.offsets, rs_ref.frustums.offsets, rtol=2e-3, atol=3e-6)
 
 
 def test_sync_free_training_sampler_matches_the_four_sync_path(trained):
@@ -230,3 +251,46 @@ def test_visibility_compact_moves_payload_rows_with_their_samples():
     assert _same(got["t_starts"][:k], ts.to(DEV)[mask]) and _same(got["ray_indices"][:k], ri.int().to(DEV)[mask])
     for name in ("feat", "xs", "corner_vals"):
         assert _same(got[name][:k], payload[name][:n][mask]), name
+
+
+def test_plugin_camera_frame_uses_the_frame_table(trained):
+    """A camera frame carries ONE timestep: get_outputs_for_camera_ray_bundle hoists the member blend into a per-frame
+    table (NeRSembleNGPModel.frame_tables).  Same image as the per-sample blend within the north-star tolerance; the
+    cached table follows the timestep and the table values (in-place optimiser updates bump the version)."""
+    from nersemble_b200.nerfstudio_shim import RayBundle
+    from oracle.gen_golden import blob_grid
+    from test_plugin_cpu import make_model
+    from test_plugin_gpu import load_oracle_params_into
+    P, _ = trained
+    m = make_model(T=4, log2T=14, eval_num_rays_per_chunk=700)
+    load_oracle_params_into(m, P)
+    m = m.to(DEV).eval()
+    m.sched_window_hash_encodings.value = 32.0; m.sched_window_deform.value = 7.0
+    m.occupancy_grid.binaries[0] = blob_grid(5).to(DEV)
+    H, W = 30, 40
+    o, d, _ = _rays(H * W, 9)
+    imgs = {}
+    with torch.no_grad():
+        for tv in (1.0 / 3.0, 1.0):
+            rb = RayBundle(origins=o.view(H, W, 3), directions=d.view(H, W, 3), pixel_area=torch.ones(H, W, 1, device=DEV),
+                           camera_indices=torch.zeros(H, W, 1, dtype=torch.long, device=DEV),
+                           times=torch.full((H, W, 1), tv, device=DEV))
+            m.frame_tables = True
+            a = m.get_outputs_for_camera_ray_bundle(rb)
+            assert m.native_params()._frame[0][0] == round(tv * 3)          # the cached table is this frame's timestep
+            m.frame_tables = False
+            b = m.get_outputs_for_camera_ray_bundle(rb)
+            assert _same(a["num_samples_per_ray"], b["num_samples_per_ray"])
+            torch.testing.assert_close(a["deformation"], b["deformation"], rtol=5e-3, atol=1e-6)    # weights differ by rounding
+            assert (a["rgb"] - b["rgb"]).norm(dim=-1).max() < 1e-3
+            torch.testing.assert_close(a["accumulation"], b["accumulation"], rtol=0, atol=1e-3)
+            torch.testing.assert_close(a["depth"], b["depth"], rtol=1e-3, atol=1e-3)
+            imgs[tv] = a["rgb"]
+        assert (imgs[1.0] - imgs[1.0 / 3.0]).abs().max() > 1e-3              # the two timesteps differ
+        # the tables change in place (an optimiser step): the cached frame table must not be reused
+        m.frame_tables = True
+        m.field.hash_ensemble.tables.mul_(0.5)
+        c = m.get_outputs_for_camera_ray_bundle(rb)["rgb"]
+        m.frame_tables = False
+        e = m.get_outputs_for_camera_ray_bundle(rb)["rgb"]
+        assert (c - e).norm(dim=-1).max() < 1e-3 and (c - imgs[1.0]).abs().max() > 1e-3

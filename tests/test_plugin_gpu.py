@@ -130,7 +130,10 @@ def test_occupancy_update_and_full_frame_render():
     d = torch.stack([xs, ys, torch.full_like(xs, -9.0)], -1); d = d / d.norm(dim=-1, keepdim=True)
     rb = RayBundle(origins=o.contiguous().to(DEV), directions=d.to(DEV), pixel_area=torch.ones(H, W, 1, device=DEV),
                    camera_indices=torch.zeros(H, W, 1, dtype=torch.long, device=DEV), times=torch.full((H, W, 1), 0.34, device=DEV))
-    img = m.get_outputs_for_camera_ray_bundle(rb)
+    img_frame = m.get_outputs_for_camera_ray_bundle(rb)      # one timestep for the frame: per-frame blended table
+    m.frame_tables = False
+    img = m.get_outputs_for_camera_ray_bundle(rb)            # per-sample member blend
+    assert (img_frame["rgb"] - img["rgb"]).norm(dim=-1).max() < 1e-3 and torch.equal(img_frame["num_samples_per_ray"], img["num_samples_per_ray"])
     assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W, 1) and torch.isfinite(img["rgb"]).all()
     assert img["rgb"].min() >= 0 and img["rgb"].max() <= 1
     flat = RayBundle(origins=rb.origins.view(-1, 3), directions=rb.directions.view(-1, 3),

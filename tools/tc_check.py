@@ -35,3 +35,20 @@ def timeit(fn, reps=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 print(f"field kernel ms ({ts.numel()} samples): mma.sync {timeit(lambda: run(P0)):.3f}   tcgen05 {timeit(lambda: run(P1)):.3f}")
+
+# camera-frame case: ONE timestep for all rays -> per-frame blended table (NativeParams.frame_table) vs the per-sample blend
+tu = torch.full_like(t, 0.5)
+kwu = dict(kw, ray_times=tu)
+per = ops.field_forward(P1, window_hash=32.0, window_deform=7.0, want=want, **kwu)
+P1.frame_table(0.5, 32.0, True, True); torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+P1._frame = None
+e0.record(); P1.frame_table(0.5, 32.0, True, True); e1.record(); torch.cuda.synchronize()
+print(f"nsb_blend_tables (one pass over the tables): {e0.elapsed_time(e1):.3f} ms")
+fr = ops.field_forward(P1, window_hash=32.0, window_deform=7.0, want=want, uniform_time=0.5, **kwu)
+for k in want:
+    x, y = per[k].float(), fr[k].float()
+    print(f"frame {k:8s} max|diff| {float((x - y).abs().max()):.3e}   max|ref| {float(x.abs().max()):.3e}")
+tp = timeit(lambda: ops.field_forward(P1, window_hash=32.0, window_deform=7.0, want=want, **kwu))
+tf = timeit(lambda: ops.field_forward(P1, window_hash=32.0, window_deform=7.0, want=want, uniform_time=0.5, **kwu))
+print(f"uniform-time field kernel ms: per-sample blend {tp:.3f}   frame table {tf:.3f}")

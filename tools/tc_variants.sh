@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for so in nersemble_b200/libnsb.so tools/_variants/*.so; do
   echo "== $so"
-  NSB_LIB=$PWD/$so timeout 200 python tools/tc_check.py 2>&1 | tail -4
+  NSB_LIB=$PWD/$so timeout 200 python tools/tc_check.py 2>&1 | tail -6 | grep -v "^frame"
 done
 if [ -n "$NCU" ]; then
   ncu --set full --import-source on --clock-control none -k regex:field_kernel_tc -s 4 -c 1 -o gpurun_out/$NCU -f \
