@@ -352,6 +352,9 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_given(const
 // The gather role is the unchanged include; only the tensor role and the shared-memory plan differ.
 // ===========================================================================================
 constexpr int kTcStages = 4, kTcBlocksPerTile = 14, kTcTmemCols = 128;
+#ifdef NSB_TC_PROF
+__device__ unsigned long long g_tc_prof[8];
+#endif
 #ifndef NSB_TC_SPLIT
 #define NSB_TC_SPLIT 1      // deformation (tcgen05) and density / colour MLPs (mma.sync) on separate warp groups
 #endif
@@ -841,6 +844,11 @@ using namespace nsb;
 extern "C" size_t nsb_deform_packed_bytes(void) { return (size_t)kTbNumSlabs * kSlabBytes; }
 extern "C" size_t nsb_field_packed_bytes(void) { return kFieldPackedU4 * sizeof(uint4); }
 extern "C" size_t nsb_deform_packed_umma_bytes(void) { return kTcPackedBytes; }
+#ifdef NSB_TC_PROF
+extern "C" int nsb_debug_tc_prof(unsigned long long *out8) {
+    return (int)cudaMemcpyFromSymbol(out8, nsb::g_tc_prof, sizeof(unsigned long long) * 8);
+}
+#endif
 
 extern "C" int nsb_field_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
                                  const nsb_field_out *out, void *stream) {

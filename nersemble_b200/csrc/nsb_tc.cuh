@@ -63,6 +63,23 @@ __device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 columns, NO wait: pair with wait_ld() (tcgen05.wait::ld waits for every outstanding load of the thread, so a
+// software pipeline is  wait -> issue next -> process current)
+__device__ __forceinline__ void ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -72,6 +89,33 @@ __device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// exactly one lane of a converged warp (the issuing lane of tcgen05.mma / commit / bulk copies)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// (x0, x1) += (b0, b1) as ONE packed fp32x2 add (sm_100: FADD2)
+__device__ __forceinline__ void add_f32x2(float &x0, float &x1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "+f"(x0), "+f"(x1)
+        : "f"(b0), "f"(b1));
+}
+// half2(relu(lo), relu(hi)), round-to-nearest: the ReLU rides on the conversion
+__device__ __forceinline__ uint32_t cvt_relu_h2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// sin(x) for |x| up to a few thousand: two-constant Cody-Waite reduction to [-pi, pi] (k * 2pi_hi is exact inside the
+// FMA), then MUFU.SIN (abs error < 4e-7 there).  The result feeds an fp16 MMA operand (spacing 4.9e-4 near 1).
+__device__ __forceinline__ float sin_reduced(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484555314695172e-07f, r);
+    return __sinf(r);
 }
 
 }  // namespace tc
