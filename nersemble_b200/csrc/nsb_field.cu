@@ -351,7 +351,18 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_ws_given(const
 // one issuing thread, weights read from shared memory once per 128-row tile) -- nsb_field_tensor_role_tc.inc.
 // The gather role is the unchanged include; only the tensor role and the shared-memory plan differ.
 // ===========================================================================================
-constexpr int kTcStages = 4, kTcBlocksPerTile = 14, kTcTmemCols = 128;
+#ifndef NSB_TC_PAIR
+#define NSB_TC_PAIR 0       // 1: two tiles per pass over the weights (nsb_field_tensor_role_tc2.inc); 0: one tile (..._tc.inc)
+#endif
+#ifndef NSB_FRAME_GATHER_WARPS
+#define NSB_FRAME_GATHER_WARPS 8     // measured (2^20 samples): 20 warps 1.25 ms, 16: 1.24, 12: 1.21, 8: 1.14
+#endif
+constexpr int kFrameGatherWarps = NSB_FRAME_GATHER_WARPS;   // frame-table gather: how many of the gather warps do work
+#if NSB_TC_PAIR
+constexpr int kTcStages = 3, kTcBlocksPerTile = 14, kTcTmemCols = 256, kTcTiles = 2;
+#else
+constexpr int kTcStages = 4, kTcBlocksPerTile = 14, kTcTmemCols = 128, kTcTiles = 1;
+#endif
 #ifdef NSB_TC_PROF
 __device__ unsigned long long g_tc_prof[8];
 #endif
@@ -362,11 +373,20 @@ constexpr size_t kTcPackedBytes = 12 * 16384 + 2 * 2048;
 
 struct alignas(1024) SmemTC {
     uint8_t wring[kTcStages][16384];        // weight blocks [128 n x 64 k] (heads: [16 x 64]) in UMMA core-matrix order
+#if NSB_TC_PAIR
+    uint8_t a_enc[2][16384];                // posenc A operand [128 rows x 64 k] of the pair's two tiles
+    uint8_t act[2][32768];                  // hidden activations A operand [128 rows x 128 k] of the two tiles
+#else
     uint8_t a_enc[16384];                   // posenc A operand [128 rows x 64 k]
     uint8_t act[32768];                     // hidden activations A operand [128 rows x 128 k]
+#endif
     uint4 field_w[kFieldPackedU4];
     alignas(16) float bias[kBiasFloats];
+#if NSB_TC_PAIR
+    uint64_t full[kTcStages], empty[kTcStages], acc_bar[2], f_done[2];
+#else
     uint64_t full[kTcStages], empty[kTcStages], acc_bar, f_done[2];
+#endif
     uint64_t xs_full[2], feat_full[2];
     uint32_t tmem_base;
     int tile_ctr[2];
@@ -386,10 +406,10 @@ static_assert(sizeof(SmemTC) <= 227 * 1024, "shared memory plan");
         const uint4 *src = reinterpret_cast<const uint4 *>(A.P.field_packed);                                      \
         for (int i = tid; i < kFieldPackedU4; i += kThreadsWS) sm.field_w[i] = __ldg(src + i);                     \
         for (int i = tid; i < kBiasFloats; i += kThreadsWS) sm.bias[i] = __ldg(A.P.deform_bias + i);               \
-        for (int i = tid; i < 16384 / 16; i += kThreadsWS) reinterpret_cast<uint4 *>(sm.a_enc)[i] = make_uint4(0u, 0u, 0u, 0u); \
+        for (int i = tid; i < (int)(sizeof(sm.a_enc) / 16); i += kThreadsWS) reinterpret_cast<uint4 *>(&sm.a_enc)[i] = make_uint4(0u, 0u, 0u, 0u); \
         if (tid == 0) {                                                                                             \
             for (int s = 0; s < kTcStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }         \
-            mbar_init(&sm.acc_bar, 1);                                                                              \
+            for (int t = 0; t < kTcTiles; ++t) mbar_init(reinterpret_cast<uint64_t *>(&sm.acc_bar) + t, 1);            \
             mbar_init(&sm.f_done[0], 4); mbar_init(&sm.f_done[1], 4);                                               \
             for (int b = 0; b < 2; ++b) {                                                                           \
                 mbar_init(&sm.xs_full[b], 4);                                                                       \
@@ -423,7 +443,11 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) field_kernel_tc(const __gri
         return;
     }
     if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
+#if NSB_TC_PAIR
+#include "nsb_field_tensor_role_tc2.inc"
+#else
 #include "nsb_field_tensor_role_tc.inc"
+#endif
 #undef NSB_N_SAMPLES
 }
 
@@ -686,7 +710,11 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __gr
     render_sampler_phase<SAMPLER, SmemTC>(K);
     if (tid == 0) mbar_arrive(&sm.sampler_done);
     {
+#if NSB_TC_PAIR
+#include "nsb_field_tensor_role_tc2.inc"
+#else
 #include "nsb_field_tensor_role_tc.inc"
+#endif
     }
 #undef NSB_N_SAMPLES
     render_composite_phase<SAMPLER>(K);

@@ -196,6 +196,8 @@ class NeRSembleNGPModel(Model):
         self.use_fused_render = True     # eval renders: sampler -> field -> composite fused, no host sync (ops.render_rays)
         self.use_fused_sampler = True    # training: march / density pre-pass / visibility / packing with one host sync
         self.frame_tables = True         # eval frames (one timestep per camera frame): gather a per-frame blended table
+        self.frame_table_min_rays = 16384  # ... for frames of at least this many rays (the check is one host sync per frame,
+                                           # the table one 0.17 ms pass over the hash tables)
         self.prepass_reuse = True        # ... and the pre-pass's blended features / corner values are packed with the kept
                                          # samples, so the differentiable forward does not gather the tables a second time
 
@@ -391,7 +393,8 @@ class NeRSembleNGPModel(Model):
         # time (checked here: one host synchronisation per FRAME), the 32-member blend is hoisted out of the per-sample
         # path into a per-frame table (ops.NativeParams.frame_table) that every chunk of the frame gathers from L2.
         uniform_time = None
-        if self.frame_tables and camera_ray_bundle.times is not None and self.config.use_hash_ensemble:
+        if (self.frame_tables and camera_ray_bundle.times is not None and self.config.use_hash_ensemble
+                and h * w >= self.frame_table_min_rays):
             t = camera_ray_bundle.times
             lo, hi = torch.stack([t.min(), t.max()]).tolist()
             uniform_time = lo if lo == hi else None

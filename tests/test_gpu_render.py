@@ -265,6 +265,7 @@ def test_plugin_camera_frame_uses_the_frame_table(trained):
     m = make_model(T=4, log2T=14, eval_num_rays_per_chunk=700)
     load_oracle_params_into(m, P)
     m = m.to(DEV).eval()
+    m.frame_table_min_rays = 1
     m.sched_window_hash_encodings.value = 32.0; m.sched_window_deform.value = 7.0
     m.occupancy_grid.binaries[0] = blob_grid(5).to(DEV)
     H, W = 30, 40

@@ -130,6 +130,7 @@ def test_occupancy_update_and_full_frame_render():
     d = torch.stack([xs, ys, torch.full_like(xs, -9.0)], -1); d = d / d.norm(dim=-1, keepdim=True)
     rb = RayBundle(origins=o.contiguous().to(DEV), directions=d.to(DEV), pixel_area=torch.ones(H, W, 1, device=DEV),
                    camera_indices=torch.zeros(H, W, 1, dtype=torch.long, device=DEV), times=torch.full((H, W, 1), 0.34, device=DEV))
+    m.frame_table_min_rays = 1
     img_frame = m.get_outputs_for_camera_ray_bundle(rb)      # one timestep for the frame: per-frame blended table
     m.frame_tables = False
     img = m.get_outputs_for_camera_ray_bundle(rb)            # per-sample member blend
