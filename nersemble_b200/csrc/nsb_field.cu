@@ -364,7 +364,10 @@ constexpr int kTcStages = 3, kTcBlocksPerTile = 14, kTcTmemCols = 256, kTcTiles 
 constexpr int kTcStages = 4, kTcBlocksPerTile = 14, kTcTmemCols = 128, kTcTiles = 1;
 #endif
 #ifdef NSB_TC_PROF
-__device__ unsigned long long g_tc_prof[8];
+__device__ unsigned long long g_tc_prof[8], g_tc_prof_k[8];
+#define KPROF(i) if (threadIdx.x == 0 && blockIdx.x == 3) g_tc_prof_k[i] = (unsigned long long)clock64();
+#else
+#define KPROF(i)
 #endif
 #ifndef NSB_TC_SPLIT
 #define NSB_TC_SPLIT 1      // deformation (tcgen05) and density / colour MLPs (mma.sync) on separate warp groups
@@ -543,6 +546,16 @@ constexpr int kPhaseThreads = kTensorWarps * 32;
 #endif
 // SAMPLER: 0 fixed-stride march fused; 1 occupancy march fused (count | scan | fill); 2 samples GIVEN: a preceding
 // launch (march_occ_coop_kernel, nsb_render.cu) filled the packed arrays and left the count in the workspace header.
+// the fixed-stride march of this CTA's rays as a real call (tensor warps, after the role split)
+__device__ __noinline__ void fixed_march_rays(const RenderKArgs &K, const int warp, const int lane) {
+    const int64_t R = K.C.n_rays;
+    for (int64_t r = (int64_t)blockIdx.x * kTensorWarps + warp; r < R; r += (int64_t)gridDim.x * kTensorWarps) {
+        const float t0 = march_fixed_t0(K.F.S.origins, K.F.S.directions, K.F.P.aabb, r, K.near_plane);
+        march_fixed_warp(t0, r, K.n_per_ray, K.M.step, K.M.t_starts, K.M.t_ends, K.M.ray_indices, lane);
+        if (lane == 0) { K.packed_info[2 * r] = r * K.n_per_ray; K.packed_info[2 * r + 1] = K.n_per_ray; }
+    }
+}
+
 template <int SAMPLER, class SM = SmemWS>
 __device__ NSB_RK_SAMPLER_ATTR void render_sampler_phase(const RenderKArgs &K) {
     constexpr bool OCC = SAMPLER == 1;
@@ -555,9 +568,22 @@ __device__ NSB_RK_SAMPLER_ATTR void render_sampler_phase(const RenderKArgs &K) {
     if (blockIdx.x == 0 && tid == 0) {
         K.hdr->depth_range[0] = 0xffffffffu;
         K.hdr->depth_range[1] = 0u;
-        if (SAMPLER != 2) K.hdr->status = 0;
+        if (SAMPLER != 2 && !(SAMPLER == 4 && K.sampler != 0)) K.hdr->status = 0;
     }
-    if constexpr (SAMPLER == 2) {
+    if constexpr (SAMPLER == 4) {
+        // run-time choice between the fixed march and given samples in ONE binary (the tcgen05 render kernel): two
+        // instantiations were two draws of ptxas' allocation of the gather role, and the fixed-march draw ran 15 % slower
+        if (K.sampler == 0) {
+            fixed_march_rays(K, warp, lane);
+            if (tid == 0) {
+                sm.n_dyn = R * K.n_per_ray;
+                if (blockIdx.x == 0) K.hdr->n_total = R * K.n_per_ray;
+            }
+        } else if (tid == 0) {
+            sm.n_dyn = min(__ldcg(&K.hdr->n_total), K.capacity);
+        }
+        grid_barrier(bar, 1u * gridDim.x);
+    } else if constexpr (SAMPLER == 2) {
         if (tid == 0) sm.n_dyn = min(__ldcg(&K.hdr->n_total), K.capacity);
         grid_barrier(bar, 1u * gridDim.x);          // depth_range initialised before any CTA composites
     } else if constexpr (!OCC) {
@@ -694,8 +720,10 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool FIELD = true, HEAD = true, SAVE = false, FEAT_GIVEN = false;
 #define NSB_N_SAMPLES (*reinterpret_cast<const volatile int64_t *>(&sm.n_dyn))
+    KPROF(0)
     if (tid == 0) mbar_init(&sm.sampler_done, 1);
     NSB_TC_SETUP()
+    KPROF(1)
     if (warp >= kTensorWarps) {
         if (kGatherRegs != 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGatherRegs));
         mbar_wait<200>(&sm.sampler_done, 0);
@@ -708,6 +736,7 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __gr
     }
     if (kTensorRegs != 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTensorRegs));
     render_sampler_phase<SAMPLER, SmemTC>(K);
+    KPROF(2)
     if (tid == 0) mbar_arrive(&sm.sampler_done);
     {
 #if NSB_TC_PAIR
@@ -717,7 +746,9 @@ __global__ void __launch_bounds__(kLaunchBoundWS, 1) render_kernel_tc(const __gr
 #endif
     }
 #undef NSB_N_SAMPLES
+    KPROF(3)
     render_composite_phase<SAMPLER>(K);
+    KPROF(4)
 }
 
 // -------------------------------------------------------------------------------------------
@@ -876,6 +907,9 @@ extern "C" size_t nsb_deform_packed_umma_bytes(void) { return kTcPackedBytes; }
 extern "C" int nsb_debug_tc_prof(unsigned long long *out8) {
     return (int)cudaMemcpyFromSymbol(out8, nsb::g_tc_prof, sizeof(unsigned long long) * 8);
 }
+extern "C" int nsb_debug_tc_prof_kernel(unsigned long long *out8) {      // clock64 at the phase boundaries of render_kernel_tc
+    return (int)cudaMemcpyFromSymbol(out8, nsb::g_tc_prof_k, sizeof(unsigned long long) * 8);
+}
 #endif
 
 extern "C" int nsb_field_forward(const nsb_field_params *params, const nsb_field_opts *opts, const nsb_samples *samples,
@@ -1004,7 +1038,10 @@ static int launch_render_tc(const RenderKArgs &K, cudaStream_t st) {
 template <bool D, int SAMPLER>
 static int launch_render(const RenderKArgs &K, cudaStream_t st) {
     if constexpr (D && SAMPLER != 1)
-        if (K.F.P.deform_packed_umma) return launch_render_tc<SAMPLER>(K, st);
+        if (K.F.P.deform_packed_umma)       // every instantiation is its own draw of ptxas' allocation: measured (tools/
+            // render_time.py, 2^20 samples) <0> 2.35 ms, <4> (run-time sampler choice, fixed march as a call) 2.13 fixed /
+            // 2.18 given, <2> 2.02 given -> the fixed march runs the <4> binary, given samples the <2> binary
+            return SAMPLER == 0 ? launch_render_tc<4>(K, st) : launch_render_tc<2>(K, st);
     const size_t smem = sizeof(SmemWS);
     static bool configured = false;
     if (!configured) {
