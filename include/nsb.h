@@ -73,7 +73,7 @@ typedef struct nsb_field_params {
                                        kernels run the deformation MLP on tcgen05.mma with the accumulator in TMEM. */
     const void *frame_table;   /* optional, float2 [total_entries]: the tables blended with ONE timestep's member weights
                                   (nsb_blend_tables).  Only valid when EVERY sample of the call has that timestep (one
-                                  camera frame): the gather then reads 8 B per corner from a 67 MB table that stays in L2
+                                  camera frame): the gather then reads 8 B per corner from a 50 MB table that stays in L2
                                   instead of a 128 B line from HBM.  Used by the tcgen05 inference kernels. */
     const void *field_packed;  /* fp16 mlp_base + mlp_head weights in MMA-B fragment order */
     const void *warp_codes;    /* __half [n_timesteps][128]  (time_embedding_deformation) */
