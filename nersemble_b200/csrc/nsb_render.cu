@@ -357,14 +357,16 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
         MarchArgs S1; S1.a = K.M;
         S1.a.t_starts = K.scratch; S1.a.t_ends = K.scratch + K.capacity; S1.a.ray_indices = nullptr;
         bool over = false;
-        for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads) {
+        // rays are dealt round-robin to the CTAs (ray = block + grid * k): a thread per ray writes 2 scattered words per
+        // sample, and with consecutive rays per CTA 4096 rays kept the store pipes of 16 SMs busy while 132 SMs idled
+        for (int64_t r = (int64_t)blockIdx.x + (int64_t)gridDim.x * tid; r < R; r += (int64_t)gridDim.x * kCoopThreads) {
             const int32_t c = march_occ_ray<true, LV>(S1.a, r, r * K.slot, (r + 1) * K.slot);
             over |= c > K.slot;
             K.M.counts[r] = (int32_t)min((int64_t)c, K.slot);
         }
         if (over) K.hdr->reserved[0] = 1;                 // folded into status by block 0 after the barrier
     } else {
-        for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
+        for (int64_t r = (int64_t)blockIdx.x + (int64_t)gridDim.x * tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
             K.M.counts[r] = march_occ_ray<false, LV>(K.M, r, 0, 0);
     }
     coop_grid_barrier(bar, 1u * gridDim.x);
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kCoopThreads) march_occ_coop_kernel(const __gr
             }
         }
     } else {
-        for (int64_t r = (int64_t)blockIdx.x * kCoopThreads + tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
+        for (int64_t r = (int64_t)blockIdx.x + (int64_t)gridDim.x * tid; r < R; r += (int64_t)gridDim.x * kCoopThreads)
             march_occ_ray<true, LV>(K.M, r, __ldcg(K.packed_info + 2 * r), K.capacity);
     }
 }
