@@ -196,6 +196,13 @@ def test_forward_kernel_gather_role_has_no_spill_storm():
     assert len(rows) >= 12
     for r in rows:
         assert int(r[r.index("gather") + 1]) <= 16, out
+    # the tcgen05 instantiations (the default for inference): the committed source builds with 4-6 (per-sample blend) and
+    # 0-6 (frame table) spill instructions in the gather role
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "spill_report.py"), obj, "kernel_tc"], capture_output=True, text=True).stdout
+    rows = [l.split() for l in out.splitlines() if "gather" in l]
+    assert len(rows) >= 8
+    for r in rows:
+        assert int(r[r.index("gather") + 1]) <= 12, out
 
 
 def test_ctypes_structs_match_the_c_header_layout(tmp_path):
