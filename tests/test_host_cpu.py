@@ -261,3 +261,25 @@ def test_rank1_slot_map_for_many_timesteps():
     # explicit positions use per-sample times
     slot, n = ops._rank1_slots(SimpleNamespace(n_timesteps=T), dev, {"positions": torch.zeros(3, 3), "sample_times": times[:3]})
     assert n == 2
+
+
+def test_posenc_sine_reduction_constants():
+    """tc::sin_reduced (nsb_tc.cuh) = two-constant Cody-Waite reduction to [-pi, pi] + MUFU.SIN, the posenc of the tcgen05
+    deformation role.  Emulated in numpy (fp32 operands, the FMA's exact product in float64): over the argument range of
+    the encoding -- fl(2 pi p) * 2^j for j < 7 and positions up to 4 box widths outside the box -- the REDUCTION moves the
+    sine by < 2e-7 (MUFU.SIN adds < 4e-7 on the reduced range, B300_MICROARCH); the value then becomes an fp16 MMA operand
+    (spacing 4.9e-4 near 1), as in the oracle's kernel mode."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    p = rng.uniform(-4.0, 5.0, size=200000).astype(np.float32)
+    a = (np.float32(6.283185307179586) * p).astype(np.float32)
+    worst = 0.0
+    for j in range(7):
+        for shift in (np.float32(0.0), np.float32(1.5707963267948966)):
+            x = (a * np.float32(1 << j) + shift).astype(np.float32)
+            k = np.rint((x * np.float32(0.15915494309189535)).astype(np.float32)).astype(np.float32)
+            r = (x.astype(np.float64) - k.astype(np.float64) * np.float64(np.float32(6.2831854820251465))).astype(np.float32)
+            r = (r.astype(np.float64) - k.astype(np.float64) * np.float64(np.float32(-1.7484555314695172e-07))).astype(np.float32)
+            assert np.abs(r).max() < 3.1416 + 1e-3
+            worst = max(worst, float(np.abs(np.sin(r.astype(np.float64)) - np.sin(x.astype(np.float64))).max()))
+    assert worst < 2e-7, worst
