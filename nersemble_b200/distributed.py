@@ -36,6 +36,34 @@ def gather_rays(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
 
 
+def shard_rows_round_robin(n_rows: int, rank: int, world: int, device=None) -> torch.Tensor:
+    """Row indices of an image for this rank, dealt round-robin (row r -> rank r % world; n_rows % world == 0).
+    For camera frames: the subject sits in the middle of the image, and with contiguous row blocks the central ranks march
+    several times the samples of the outer ones (8 GPUs: 2.85x instead of 7.36x)."""
+    assert n_rows % world == 0, "frames are sharded by rows: the row count must divide by the world size"
+    return torch.arange(rank, n_rows, world, device=device)
+
+
+def gather_rows_round_robin(local: torch.Tensor, out: torch.Tensor = None, scratch: torch.Tensor = None) -> torch.Tensor:
+    """Inverse of shard_rows_round_robin for a per-pixel output: local [rows, W, C] of every rank -> [rows * world, W, C]
+    in image order on every rank (one all_gather_into_tensor + one strided copy).  `out` / `scratch` may be passed to
+    avoid allocations in a frame loop (shapes [rows * world, W, C] and [world, rows, W, C])."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if out is None:
+            return local
+        out.copy_(local)
+        return out
+    world = dist.get_world_size()
+    rows, w, c = local.shape
+    if scratch is None:
+        scratch = torch.empty((world, rows, w, c), dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty((rows * world, w, c), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(scratch.view(-1), local.reshape(-1))
+    out.view(rows, world, w, c).copy_(scratch.permute(1, 0, 2, 3))          # image row r * world + k came from rank k
+    return out
+
+
 def allreduce_pending(he, average: bool = True) -> None:
     """All-reduce of a HashEnsemble's parked rank-1 table gradient (fused optimiser), once: a reduced gradient is marked.
     Same slot map and blend weights on every rank (n_timesteps <= 32: slot = timestep, cw_slots from the replicated

@@ -169,3 +169,31 @@ def test_sharded_table_optimiser_reduce_scatter_step_all_gather():
     the reduced gradient, all-gathers the fp16 table, and consolidate() completes the fp32 master."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_shard_worker, args=(2, port), nprocs=2, join=True)
+
+
+def _rows_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nersemble_b200.distributed import gather_rows_round_robin, shard_rows_round_robin
+    H, W = 12, 5
+    image = torch.arange(H * W * 3, dtype=torch.float32).view(H, W, 3)
+    rows = shard_rows_round_robin(H, rank, world)
+    assert rows.tolist() == list(range(rank, H, world))
+    local = image[rows] * 2.0                        # "render" = x2 on this rank's rows
+    out = gather_rows_round_robin(local)
+    assert torch.equal(out, image * 2.0)             # image order restored on every rank
+    frame, scratch = torch.empty((H, W, 3)), torch.empty((world, H // world, W, 3))
+    assert gather_rows_round_robin(local, out=frame, scratch=scratch) is frame and torch.equal(frame, image * 2.0)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_round_robin_frame_rows():
+    """Frames are sharded by rows dealt round-robin (load balance: the subject is in the middle of the image); the
+    all-gather + strided copy puts the rows back in image order on every rank.  world_size 1 is the identity."""
+    from nersemble_b200.distributed import gather_rows_round_robin, shard_rows_round_robin
+    assert shard_rows_round_robin(6, 0, 1).tolist() == [0, 1, 2, 3, 4, 5]
+    x = torch.rand(6, 4, 3)
+    assert gather_rows_round_robin(x) is x
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_rows_worker, args=(2, port), nprocs=2, join=True)

@@ -184,7 +184,8 @@ def run_config4(args):
     rows = H // world
     # rows are dealt out round-robin (row r -> rank r % N), not in contiguous blocks: the head sits in the middle of the
     # frame, and with contiguous blocks the central ranks marched 4x the samples of the outer ones (r2m: 8 GPUs only 2.85x)
-    my_rows = torch.arange(rank, H, world, device=dev)
+    from nersemble_b200.distributed import gather_rows_round_robin, shard_rows_round_robin
+    my_rows = shard_rows_round_robin(H, rank, world, device=dev)
 
     def camera_rays(frame, row_idx=None):
         row_idx = my_rows if row_idx is None else row_idx
@@ -211,11 +212,7 @@ def run_config4(args):
     def render_frame():
         rb = camera_rays(state["f"] % n_frames)
         out = model.get_outputs_for_camera_ray_bundle(rb)
-        if world > 1:
-            D.dist.all_gather_into_tensor(gather_buf.view(-1), out["rgb"].reshape(-1))
-            frame_buf.view(rows, world, Wd, 3).copy_(gather_buf.permute(1, 0, 2, 3))      # row r * N + k came from rank k
-        else:
-            frame_buf.copy_(out["rgb"])
+        gather_rows_round_robin(out["rgb"], out=frame_buf, scratch=gather_buf)      # NCCL all-gather + one strided copy
         n_samples.add_(out["num_samples_per_ray"].sum())
         state["f"] += 1
 
