@@ -286,10 +286,6 @@ class Dist:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, the launcher's default on some boxes)
-            # goes to stdout too -- keep warnings, drop the banner; an explicit INFO / TRACE setting is left alone
-            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", device_id=self.dev)
         self.dist = dist
 
