@@ -10,4 +10,4 @@ mkdir -p $OUT
     $FLAGS -c nsb_field.cu -o $OUT/$NAME.field.o 2> $OUT/$NAME.ptxas.log || (cat $OUT/$NAME.ptxas.log; false)
 /usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $OUT/$NAME.so $OUT/$NAME.field.o \
     nsb_api.o nsb_render.o nsb_backward.o nsb_deform_bwd.o nsb_optim.o nsb_losses.o nsb_rays.o -lcudart
-python ../../tools/spill_report.py $OUT/$NAME.field.o kernel_tc | head -4
+python ../../tools/spill_report.py $OUT/$NAME.field.o kernel_tc
